@@ -1,0 +1,109 @@
+"""oracle/gen_golden.py — TEST INFRASTRUCTURE: regenerate tests/golden/*.npz.
+
+Runs the UNMODIFIED reference (oracle/_ref/ref_* binaries = /root/reference/tinyspec.cpp compiled where
+it lies + stub headers + offline fake JACK + FFTW-ABI shim; `make -C oracle ref`) on the synthetic
+inputs of SURVEY.md §8(d) and stores what it produced.  The fixtures travel to the GPU box; the
+reference tree does not.  Usage:  python oracle/gen_golden.py
+"""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.path.join(HERE, "_ref")
+GOLD = os.path.join(HERE, "..", "tests", "golden")
+
+
+def run_ref(binary, env, dumps=(), want_out=True):
+    with tempfile.TemporaryDirectory() as d:
+        e = dict(os.environ, TSREF_DUMP_DIR=d, **{k: str(v) for k, v in env.items()})
+        if want_out:
+            e["TSREF_OUT"] = os.path.join(d, "out.f32")
+        subprocess.run([os.path.join(REF, binary)], env=e, cwd=d, check=True, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL)
+        res = {}
+        for name, dt in dumps:
+            p = os.path.join(d, name + ".bin")
+            res[name] = np.fromfile(p, dtype=dt) if os.path.exists(p) else np.zeros(0, dt)
+        if want_out:
+            res["stream"] = np.fromfile(e["TSREF_OUT"], dtype=np.float32)
+        return res
+
+
+PV_DUMPS = [("frame", np.int64), ("t", np.float64), ("in", np.float64), ("out", np.float64),
+            ("last_phase", np.float64), ("phase_sum", np.float64), ("pv_data", np.float64)]
+
+
+def pv_case(name, n, hop_ratio, shift, ch, samples, first, every, stream=0, tail_only=False, binary="ref_pv_tap"):
+    r = run_ref(binary, dict(TSREF_N=n, TSREF_HOP_RATIO=hop_ratio, TSREF_SHIFT=shift, TSREF_CH=ch,
+                             TSREF_SAMPLES=samples, TSREF_STREAM=stream, TSREF_DUMP_FIRST=first,
+                             TSREF_DUMP_EVERY=every), PV_DUMPS)
+    k = len(r["frame"])
+    out = dict(meta=np.array([n, ch, samples, stream], np.int64), params=np.array([hop_ratio, shift], np.float64),
+               frame=r["frame"], t=r["t"], out=r["out"].reshape(k, ch, n),
+               last_phase=r["last_phase"].reshape(k, ch, n), phase_sum=r["phase_sum"].reshape(k, ch, n),
+               pv_data=r["pv_data"].reshape(k, ch, n, 2), stream_len=np.array([len(r["stream"])], np.int64))
+    if not tail_only:
+        out["in"] = r["in"].reshape(k, ch, n)
+    s = r["stream"].reshape(-1, ch)
+    out["stream"] = s[-8192:] if tail_only else s
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(name, "frames dumped", k, "stream", s.shape)
+
+
+def filter_case(name, n, hop_ratio, ch, samples, filt, first, every):
+    r = run_ref("ref_filter_tap", dict(TSREF_N=n, TSREF_HOP_RATIO=hop_ratio, TSREF_CH=ch, TSREF_SAMPLES=samples,
+                                       TSREF_FILTER=filt, TSREF_DUMP_FIRST=first, TSREF_DUMP_EVERY=every),
+                [("frame", np.int64), ("t", np.float64), ("in", np.float64), ("out", np.float64),
+                 ("spec", np.complex128)])
+    k = len(r["frame"])
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), meta=np.array([n, ch, samples, filt], np.int64),
+                        params=np.array([hop_ratio], np.float64), frame=r["frame"], t=r["t"],
+                        out=r["out"].reshape(k, ch, n), spec=r["spec"].reshape(k, ch, n),
+                        stream=r["stream"].reshape(-1, ch))
+    print(name, "frames dumped", k, "stream", r["stream"].shape)
+
+
+def helpers_case():
+    r = run_ref("ref_helpers_tap", {}, [("hann", np.float64), ("sqrt_hann", np.float64),
+                                        ("frft_in", np.complex128), ("frft_out", np.complex128),
+                                        ("frft_inplace", np.complex128), ("pv_in", np.float64),
+                                        ("pv_analyzed", np.float64), ("pv_shifted", np.float64),
+                                        ("pv_out", np.float64), ("pv_phase_sum", np.float64),
+                                        ("pv_last_phase", np.float64), ("hop_fixed", np.uint64)], want_out=False)
+    np.savez_compressed(os.path.join(GOLD, "helpers.npz"), frft_sizes=np.array([8, 64, 100, 512]),
+                        frft_exps=np.array([1.0, -1.0, 2.0, 0.5]), pv_sizes=np.array([64, 256]),
+                        pv_ratios=np.array([2.0, 1.5, 0.5]), hops=np.array([256.0, 256.5, 100.25, 0.75, 1023.999]),
+                        **r)
+    print("helpers", {k: v.shape for k, v in r.items()})
+
+
+def granular_case(name, samples, vary, n_first=0, stream=0):
+    r = run_ref("ref_granular_tap", dict(TSREF_SAMPLES=samples, TSREF_VARY=vary, TSREF_NFIRST=n_first,
+                                         TSREF_STREAM=stream, TSREF_DUMP_FIRST=1 << 30),
+                [("frame", np.int64), ("t", np.float64), ("win", np.int64), ("osize", np.int64)])
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"),
+                        meta=np.array([samples, vary, n_first, stream], np.int64), t=r["t"], win=r["win"],
+                        osize=r["osize"], stream=r["stream"].reshape(-1, 2))
+    print(name, "frames", len(r["t"]), "stream", r["stream"].shape)
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL)
+    helpers_case()
+    # cfg1 shape, short: every frame's state would be 1.3 MB; keep the first 6 + every 16th
+    pv_case("pv_cfg1_short", 1024, 0.25, 2.0, 2, 24000, 6, 16)
+    pv_case("pv_x1p5_n256", 256, 0.25, 1.5, 2, 12000, 4, 32)
+    pv_case("pv_down_n512_fracthop", 512, 0.2003, 0.75, 1, 16000, 4, 32, stream=3)
+    pv_case("pv_cfg3_shape", 4096, 0.25, 1.5, 8, 16384 + 2048, 0, 8, tail_only=True)
+    # cfg1 full length (60 s): final state + last 8192 output samples pin long-run phase accumulation
+    pv_case("pv_cfg1_60s_tail", 1024, 0.25, 2.0, 2, 2880000, 0, 11238, tail_only=True)
+    filter_case("filter_pass_n2048", 2048, 0.25, 1, 24000, 0, 3, 16)
+    filter_case("filter_lp_n2048", 2048, 0.25, 1, 24000, 1, 3, 16)
+    filter_case("filter_lp_n512_stereo", 512, 0.5, 2, 12000, 1, 3, 16)
+    granular_case("granular_1800", 60000, 0)
+    granular_case("granular_vary", 60000, 1, n_first=64, stream=2)

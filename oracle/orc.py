@@ -1,0 +1,257 @@
+"""oracle/orc.py — TEST INFRASTRUCTURE: ctypes binding of the plain-C oracle (oracle/oracle.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module; the product package never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_build", "liboracle.so")
+
+
+def build(force=False):
+    """Compile oracle.c -> _build/liboracle.so (gcc only; seconds)."""
+    src = os.path.join(HERE, "oracle.c")
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(
+            os.path.getmtime(src), os.path.getmtime(os.path.join(HERE, "signal_gen.h"))):
+        subprocess.check_call(["make", "-C", HERE, "oracle"], stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+class _Result(C.Structure):
+    _fields_ = [("frames", C.c_size_t), ("out_len", C.c_size_t)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB_PATH)
+        P = C.c_void_p
+        L.orc_gen_signal.argtypes = [C.c_int, C.c_int, C.c_double, C.c_size_t, P]
+        L.orc_fft_forward.argtypes = [P, P, C.c_size_t]
+        L.orc_window_hann.argtypes = [P, C.c_size_t, C.c_size_t]
+        L.orc_window_sqrt_hann.argtypes = [P, C.c_size_t, C.c_size_t]
+        L.orc_frft.argtypes = [P, P, C.c_size_t, C.c_size_t, C.c_double]
+        L.orc_set_hop.argtypes = [C.c_double, P, P, P]
+        L.orc_set_hop.restype = C.c_int
+        L.orc_pv_new.argtypes = [P, P]
+        L.orc_pv_new.restype = P
+        L.orc_pv_free.argtypes = [P]
+        L.orc_pv_set_hop.argtypes = [P, C.c_double]
+        L.orc_pv_reset.argtypes = [P, C.c_int, C.c_int]
+        for name in ("orc_pv_data", "orc_pv_last_phase", "orc_pv_phase_sum", "orc_pv_fft"):
+            getattr(L, name).argtypes = [P]
+            getattr(L, name).restype = P
+        L.orc_pv_size.argtypes = [P]
+        L.orc_pv_size.restype = C.c_size_t
+        L.orc_pv_nch.argtypes = [P]
+        L.orc_pv_nch.restype = C.c_size_t
+        L.orc_pv_analyze.argtypes = [P, P, C.c_size_t, C.c_size_t]
+        L.orc_pv_analyze_fft.argtypes = [P, P, C.c_size_t, C.c_size_t]
+        L.orc_pv_shift_scale.argtypes = [P, C.c_double]
+        L.orc_pv_synthesize.argtypes = [P, P]
+        L.orc_render_pv.restype = _Result
+        L.orc_render_pv.argtypes = [P, C.c_size_t, C.c_size_t, C.c_uint32, C.c_double, C.c_double, C.c_double,
+                                    C.c_size_t, P, C.c_size_t, P, C.c_size_t, P, C.c_size_t, P, C.c_size_t,
+                                    C.c_size_t, P, P, P, P, P, P, P, C.c_size_t]
+        L.orc_render_filter.restype = _Result
+        L.orc_render_filter.argtypes = [P, C.c_size_t, C.c_size_t, C.c_uint32, C.c_double, P, C.c_int, C.c_int,
+                                        C.c_double, C.c_size_t, P, C.c_size_t, P, C.c_size_t, P, C.c_size_t]
+        L.orc_render_granular.restype = _Result
+        L.orc_render_granular.argtypes = [P, C.c_size_t, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
+                                          C.c_double, C.c_size_t, P, C.c_size_t, P, C.c_size_t, P, P, P, P, P,
+                                          C.c_size_t]
+        L.orc_hop_clock.argtypes = [C.c_double, C.c_double, C.c_size_t, P, P]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def gen_signal(stream, nch, count, rate=48000.0):
+    """Interleaved float32 [count, nch] (SURVEY §8d generator)."""
+    out = np.empty((count, nch), np.float32)
+    lib().orc_gen_signal(stream, nch, rate, count, _p(out))
+    return out
+
+
+def fft_forward(x):
+    x = np.ascontiguousarray(x, np.complex128)
+    y = np.empty_like(x)
+    lib().orc_fft_forward(_p(x), _p(y), x.shape[-1])
+    return y
+
+
+def window(data, kind):
+    d = np.array(data, np.float64, order="C")
+    nch, size = d.shape
+    (lib().orc_window_hann if kind == "hann" else lib().orc_window_sqrt_hann)(_p(d), nch, size)
+    return d
+
+
+def frft(x, exponent, inplace=True):
+    x = np.array(x, np.complex128, order="C")
+    nch, n = x.shape
+    if inplace:
+        lib().orc_frft(_p(x), _p(x), nch, n, exponent)
+        return x
+    y = np.zeros_like(x)
+    lib().orc_frft(_p(x), _p(y), nch, n, exponent)
+    return y
+
+
+def set_hop(h):
+    hop = C.c_double()
+    hs = C.c_uint64()
+    hf = C.c_uint64()
+    ok = lib().orc_set_hop(h, C.byref(hop), C.byref(hs), C.byref(hf))
+    return ok, hs.value, hf.value
+
+
+def hop_clock(hop, rate, frames):
+    ch = np.empty(frames, np.int64)
+    t = np.empty(frames, np.float64)
+    lib().orc_hop_clock(hop, rate, frames, _p(ch), _p(t))
+    return ch, t
+
+
+class PV:
+    """Step-wise PhaseVocoder oracle with explicit hop (rtinc/pv.hpp:12-63)."""
+
+    def __init__(self, hop, rate=48000.0):
+        self._hop = C.c_double(hop)
+        self._rate = C.c_double(rate)
+        self.h = lib().orc_pv_new(C.addressof(self._hop), C.addressof(self._rate))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_pv_free(self.h)
+            self.h = None
+
+    def _view(self, fn, width):
+        n = lib().orc_pv_nch(self.h) * lib().orc_pv_size(self.h) * width
+        ptr = getattr(lib(), fn)(self.h)
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(n,)).copy()
+
+    def analyze(self, wave):
+        w = np.array(wave, np.float64, order="C")
+        lib().orc_pv_analyze(self.h, _p(w), w.shape[0], w.shape[1])
+        return w  # windowed in place, like the reference
+
+    def shift(self, ratio):
+        lib().orc_pv_shift_scale(self.h, ratio)
+
+    def synthesize(self):
+        nch, size = lib().orc_pv_nch(self.h), lib().orc_pv_size(self.h)
+        out = np.empty((nch, size), np.float64)
+        lib().orc_pv_synthesize(self.h, _p(out))
+        return out
+
+    @property
+    def data(self):
+        nch, size = lib().orc_pv_nch(self.h), lib().orc_pv_size(self.h)
+        return self._view("orc_pv_data", 2).reshape(nch, size, 2)
+
+    @property
+    def last_phase(self):
+        nch, size = lib().orc_pv_nch(self.h), lib().orc_pv_size(self.h)
+        return self._view("orc_pv_last_phase", 1).reshape(nch, size)
+
+    @property
+    def phase_sum(self):
+        nch, size = lib().orc_pv_nch(self.h), lib().orc_pv_size(self.h)
+        return self._view("orc_pv_phase_sum", 1).reshape(nch, size)
+
+
+def n_frames(length, n, hop):
+    """Frame count for a length-`length` input at constant integer hop (tinyspec.cpp:142-149)."""
+    if length < 2048 + n:
+        return 0
+    return (length - 2048 - n) // hop + 1
+
+
+def render_pv(x, n, hop_ratio, shift, rate=48000.0, max_frames=0, want_frames=False, state_every=0,
+              want_tables=False):
+    """x: interleaved float32 [L, nch].  Returns dict(stream=float32 [P, nch], ola64=float64 [P+n, nch],
+    frames=F, frame_out=[F, nch, n] (optional), state=[slots, 2, nch, n] (optional), last_phase, phase_sum)."""
+    x = np.ascontiguousarray(x, np.float32)
+    L, nch = x.shape
+    hop = n * hop_ratio
+    est_frames = max(1, int((L - 2048 - n) / max(hop, 1e-9)) + 4)
+    if max_frames:
+        est_frames = min(est_frames, max_frames)
+    out_cap = (L + 2 * n + 4096) * nch
+    stream = np.zeros(out_cap, np.float32)
+    ola64 = np.zeros(out_cap, np.float64)
+    frame_out = np.zeros((est_frames, nch, n), np.float64) if want_frames else None
+    slots = (est_frames + state_every - 1) // state_every + 1 if state_every else 0
+    state = np.zeros((slots, 2, nch, n), np.float64) if state_every else None
+    lp = np.zeros((nch, n), np.float64)
+    ps = np.zeros((nch, n), np.float64)
+    tabs = [np.zeros(est_frames, np.int64) for _ in range(4)] + [np.zeros(est_frames, np.float64)] \
+        if want_tables else [None] * 5
+    r = lib().orc_render_pv(_p(x), L, nch, n, hop_ratio, shift, rate, max_frames, _p(stream), out_cap, _p(ola64),
+                            out_cap, _p(frame_out), frame_out.size if want_frames else 0, _p(state), state_every,
+                            state.size if state_every else 0, _p(lp), _p(ps), *[_p(t) for t in tabs],
+                            est_frames if want_tables else 0)
+    F = r.frames
+    res = dict(frames=F, stream=stream[:r.out_len].reshape(-1, nch), ola64=ola64.reshape(-1, nch),
+               last_phase=lp, phase_sum=ps)
+    if want_frames:
+        res["frame_out"] = frame_out[:F]
+    if state_every:
+        res["state"] = state[:(F + state_every - 1) // state_every]
+    if want_tables:
+        res["tables"] = dict(in_off=tabs[0][:F], out_off=tabs[1][:F], hop=tabs[2][:F], win=tabs[3][:F], t=tabs[4][:F])
+    return res
+
+
+WIN = {"none": 0, None: 0, "hann": 1, "sqrt_hann": 2}
+
+
+def render_filter(x, n, hop_ratio, gain=None, win_in="sqrt_hann", win_out="sqrt_hann", rate=48000.0, max_frames=0,
+                  want_frames=False):
+    x = np.ascontiguousarray(x, np.float32)
+    L, nch = x.shape
+    hop = n * hop_ratio
+    est_frames = max(1, int((L - 2048 - n) / max(hop, 1e-9)) + 4)
+    if max_frames:
+        est_frames = min(est_frames, max_frames)
+    out_cap = (L + 2 * n + 4096) * nch
+    stream = np.zeros(out_cap, np.float32)
+    ola64 = np.zeros(out_cap, np.float64)
+    frame_out = np.zeros((est_frames, nch, n), np.float64) if want_frames else None
+    g = None if gain is None else np.ascontiguousarray(gain, np.float64)
+    assert g is None or g.shape == (n // 2 + 1,)
+    r = lib().orc_render_filter(_p(x), L, nch, n, hop_ratio, _p(g), WIN[win_in], WIN[win_out], rate, max_frames,
+                                _p(stream), out_cap, _p(ola64), out_cap, _p(frame_out),
+                                frame_out.size if want_frames else 0)
+    res = dict(frames=r.frames, stream=stream[:r.out_len].reshape(-1, nch), ola64=ola64.reshape(-1, nch))
+    if want_frames:
+        res["frame_out"] = frame_out[:r.frames]
+    return res
+
+
+def render_granular(x, n_first=0, n_base=1800, vary=False, stream_idx=0, rate=48000.0, max_frames=0):
+    x = np.ascontiguousarray(x, np.float32)
+    L, nch = x.shape
+    out_cap = (4 * L + 65536) * nch
+    cap = max_frames or (L // 16 + 16)
+    stream = np.zeros(out_cap, np.float32)
+    ola64 = np.zeros(out_cap, np.float64)
+    tabs = [np.zeros(cap, np.int64) for _ in range(4)] + [np.zeros(cap, np.float64)]
+    r = lib().orc_render_granular(_p(x), L, nch, n_first, n_base, int(vary), stream_idx, rate, max_frames,
+                                  _p(stream), out_cap, _p(ola64), out_cap, *[_p(t) for t in tabs], cap)
+    F = r.frames
+    return dict(frames=F, stream=stream[:r.out_len].reshape(-1, nch), ola64=ola64.reshape(-1, nch),
+                tables=dict(in_off=tabs[0][:F], out_off=tabs[1][:F], hop=tabs[2][:F], win=tabs[3][:F], t=tabs[4][:F]))
