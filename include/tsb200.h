@@ -1,0 +1,131 @@
+/* tsb200.h — C ABI of libtsb200, the B200 (sm_100a) backend for tinyspec-cling's overlap-add
+ * spectral hot path (window -> FFT -> phase vocoder / spectral gain -> inverse FFT -> overlap-add).
+ *
+ * The reference (nwoeanhinnogaehr/tinyspec-cling) has no binary plugin interface: a "hack" is C++
+ * source compiled against rtinc/root.hpp and run frame by frame by tinyspec.cpp's scheduler
+ * (SURVEY.md §8b).  This header is the boundary a binding of that interface calls into; the
+ * source-compatible C++ facade (tinyspec-cling_b200/rtinc/) and the Python host mirror
+ * (tinyspec-cling_b200/api.py) are both thin layers over exactly these entry points.  Each entry
+ * point cites the reference code it replaces.
+ *
+ * Conventions: every function returns 0 on success or a negative TSB_E* code; tsb_last_error()
+ * gives the message of the calling thread's last failure.  Nothing here falls back to the CPU: with
+ * no usable CUDA device every device entry point fails with TSB_ECUDA.
+ * A context is bound to one device and one CUDA stream and is not thread-safe (the reference runs
+ * all frames on one worker thread, tinyspec.cpp:284).
+ *
+ * Lanes: a lane is one channel of one stream.  Channels never interact anywhere on the path
+ * (rtlib/pv.hpp loops, fftw howmany, tinyspec.cpp:173-200), so S streams x C channels are S*C lanes,
+ * lane = stream*C + channel, each a planar row of samples.
+ */
+#ifndef TSB200_H
+#define TSB200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSB_ABI_VERSION 1
+
+enum { TSB_OK = 0, TSB_EINVAL = -1, TSB_ECUDA = -2, TSB_EUNSUPPORTED = -3, TSB_ENOMEM = -4 };
+enum { TSB_F32 = 0, TSB_F64 = 1 };            /* arithmetic of the chain (phase accumulators are fp64 in both) */
+enum { TSB_PROG_PV_SHIFT = 0, TSB_PROG_GAIN = 1 };
+enum { TSB_WIN_NONE = 0, TSB_WIN_HANN = 1, TSB_WIN_SQRT_HANN = 2 }; /* rtlib/windowfn.hpp:1-14 */
+
+typedef struct tsb_ctx tsb_ctx;
+typedef struct tsb_plan tsb_plan;
+
+int tsb_abi_version(void);
+const char *tsb_last_error(void);
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* `cuda_stream` is a cudaStream_t to run on (e.g. the caller's current stream) or NULL to create one. */
+int tsb_ctx_create(int device, void *cuda_stream, tsb_ctx **ctx);
+int tsb_ctx_destroy(tsb_ctx *ctx);
+int tsb_ctx_sync(tsb_ctx *ctx);
+/* device memory for bindings that have no CUDA runtime of their own (cgo / JNI / ctypes) */
+int tsb_malloc(tsb_ctx *ctx, size_t bytes, void **dptr);
+int tsb_free(tsb_ctx *ctx, void *dptr);
+int tsb_memset(tsb_ctx *ctx, void *dptr, int value, size_t bytes);
+int tsb_upload(tsb_ctx *ctx, void *dptr, const void *host, size_t bytes);   /* async on the ctx stream */
+int tsb_download(tsb_ctx *ctx, void *host, const void *dptr, size_t bytes); /* async on the ctx stream */
+
+/* ---- host-side control logic (no device needed) --------------------------------------------- */
+/* set_hop(): rtlib/control.hpp:22-29.  Returns TSB_EINVAL for a negative hop ("ignoring invalid hop"). */
+int tsb_hop_fixed(double hop, uint64_t *hop_samples, uint64_t *hop_fract);
+
+/* Frame schedule of a render in which every frame asks for next_hop_samples(n, hop), set before the
+ * first frame: restates tinyspec.cpp:135-149 (latch, starve test, advance by the PREVIOUS hop; the
+ * first advance is the initial computed_hop 2048), :110-112 (t) and :163-168 (fractional-hop carry).
+ * Tables may be NULL; returns the number of frames (<= cap when tables are given) in *n_frames.
+ *   in_off[f]  first input sample of frame f (I_f)        out_off[f] output position of frame f (P_f)
+ *   hop[f]     samples emitted after frame f              t[f]       time handed to the callback   */
+int tsb_schedule_const(int64_t in_len, uint32_t n, double hop, double rate, int64_t max_frames, int64_t cap,
+                       int64_t *n_frames, int64_t *in_off, int64_t *out_off, int32_t *hop_tab, double *t);
+
+/* PhaseVocoder::shift bin remap (rtlib/pv.hpp:59-61,70-78) for fn values on the n/2 bin centres:
+ * dest[j] = destination bin of source bin j, or -1 if it is dropped. */
+int tsb_shift_map(uint32_t n, double rate, const double *fn_bins, int32_t *dest);
+
+/* ---- plans ---------------------------------------------------------------------------------- */
+/* A plan fixes what the reference's helpers recompute on every frame: window tables
+ * (rtlib/windowfn.hpp), FFT plan/twiddles (fftw_plan_many_dft, rtlib/fft.hpp:13-16), the shift map
+ * and the per-bin phase constants of PhaseVocoder (rtlib/pv.hpp:39-48). */
+typedef struct tsb_plan_desc {
+    uint32_t n;          /* frame size: power of two, 64..8192 */
+    int32_t precision;   /* TSB_F32 | TSB_F64 */
+    int32_t program;     /* TSB_PROG_PV_SHIFT: pv.analyze(in); pv.shift(fn); pv.synthesize(out)  (hacks/pitchshift-pv.cpp:5-7)
+                            TSB_PROG_GAIN:     window(in); frft(+1); spectrum *= gain; frft(-1); real; window(out) */
+    int32_t win_in;      /* TSB_PROG_GAIN only (PV always uses sqrt-Hann twice, rtlib/pv.hpp:5,15) */
+    int32_t win_out;
+    double hop;          /* PhaseVocoder::hop() (rtinc/pv.hpp:50-53); may be fractional */
+    double rate;         /* RATE */
+    double ratio;        /* PV: fn(x) = ratio*x applied to the bin frequencies (rtlib/pv.hpp:66) */
+    const double *fn_bins; /* PV: fn(bin centre), n/2 values, or NULL for centre*ratio (rtlib/pv.hpp:65) */
+    const double *gain;  /* GAIN: n/2+1 real gains for bins k and (n-k)%n, or NULL for all ones */
+} tsb_plan_desc;
+int tsb_plan_create(tsb_ctx *ctx, const tsb_plan_desc *desc, tsb_plan **plan);
+int tsb_plan_destroy(tsb_plan *plan);
+
+/* ---- the fused chain ------------------------------------------------------------------------ */
+/* Runs `n_frames` consecutive frames of every lane: replaces tinyspec.cpp:146-157 (gather),
+ * the hack's helper chain (rtlib/pv.hpp:4-79, rtlib/fft.hpp:3-42, rtlib/windowfn.hpp) and
+ * tinyspec.cpp:170-200 (overlap-add).  All pointers are DEVICE pointers; the call is asynchronous on
+ * the context's stream.
+ *   in        [lanes][in_stride]  float32 (the reference's queues are float, tinyspec.cpp:43)
+ *   out       [lanes][out_stride] float32 (TSB_F32) or float64 (TSB_F64): position p of a lane
+ *             receives the finished overlap-added sample p; n_frames frames finish sum(hop) samples
+ *   hop_tab   per-frame emitted samples (device, int32) or NULL for the constant `hop`
+ *   state_*   float64 [lanes][n/2], [lanes][n/2], [lanes][n]: PhaseVocoder::last_phase / phase_sum
+ *             (live bins 0..n/2-1) and the overlap tail relative to the next output position.
+ *             load_state = 0 starts from PhaseVocoder::reset() and an empty tail; the arrays (may be
+ *             NULL) receive the state after the last frame, so a render can be continued, split into
+ *             time segments, or teacher-forced. */
+typedef struct tsb_chain_args {
+    const float *in;
+    int64_t in_stride, in_len;
+    void *out;
+    int64_t out_stride, out_len;
+    int64_t n_frames;
+    int64_t in_off0, out_off0;
+    int32_t hop;
+    const int32_t *hop_tab;
+    double *state_last_phase, *state_phase_sum, *state_ola;
+    int32_t load_state;
+    int32_t lanes;
+} tsb_chain_args;
+int tsb_chain_render(tsb_ctx *ctx, tsb_plan *plan, const tsb_chain_args *args);
+
+/* Same, with HOST buffers (in, out, hop_tab, state_* are host pointers): uploads the input, runs the
+ * chain, downloads the output and the state, and returns when the result is in `out`.  Pinned host
+ * buffers make the copies asynchronous; pageable ones work too. */
+int tsb_chain_render_host(tsb_ctx *ctx, tsb_plan *plan, const tsb_chain_args *args);
+
+/* Number of kernel launches issued through this context so far (for benchmarks' bookkeeping). */
+int64_t tsb_launch_count(tsb_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

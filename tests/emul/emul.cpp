@@ -1,0 +1,121 @@
+// tests/emul/emul.cpp — TEST INFRASTRUCTURE, CPU only.
+//
+// Replays the per-thread phases of the CUDA chain kernel (tinyspec-cling_b200/csrc/tsb_chain.cuh)
+// thread by thread on the host, so that the kernel's arithmetic and indexing can be checked against
+// the oracle in a container without a GPU.  It is compiled from the SAME headers the kernel is
+// compiled from.  It is not a CPU fallback: nothing in the product loads this library.
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "tsb_chain.cuh"
+#include "tsb_plan.hpp"
+
+using namespace tsb;
+
+template <class CH>
+struct HostExec {
+    std::vector<typename CH::Regs> regs = std::vector<typename CH::Regs>(CH::T);
+    template <class F>
+    void each(F f) {
+        for (int tid = 0; tid < CH::T; tid++) f(tid, regs[tid]);
+    }
+    template <class F>
+    void each_nosync(F f) { each(f); }
+};
+
+template <typename real, int LOG2N, int PROG>
+static int run(const PlanDesc &d, const ChainArgs &a) {
+    using CH = Chain<real, LOG2N, PROG>;
+    HostTables<real> ht = build_tables<real>(d);
+    ChainTables<real> tb = ht.view();
+    auto sm = std::make_unique<typename CH::Smem>();
+    for (int lane = 0; lane < a.lanes; lane++) {
+        std::memset(sm.get(), 0, sizeof(typename CH::Smem));
+        HostExec<CH> ex;
+        run_lane<CH>(ex, lane, *sm, tb, a);
+    }
+    return 0;
+}
+
+template <typename real, int PROG>
+static int by_size(int log2n, const PlanDesc &d, const ChainArgs &a) {
+    switch (log2n) {
+        case 6: return run<real, 6, PROG>(d, a);
+        case 7: return run<real, 7, PROG>(d, a);
+        case 8: return run<real, 8, PROG>(d, a);
+        case 9: return run<real, 9, PROG>(d, a);
+        case 10: return run<real, 10, PROG>(d, a);
+        case 11: return run<real, 11, PROG>(d, a);
+        case 12: return run<real, 12, PROG>(d, a);
+        case 13: return run<real, 13, PROG>(d, a);
+    }
+    return -1;
+}
+
+extern "C" int emul_chain_render(int precision, int log2n, int program, int win_in, int win_out, double hop_d,
+                                 double rate, double ratio, const double *fn_bins, const double *gain,
+                                 const float *in, long long in_stride, long long in_len, void *out,
+                                 long long out_stride, long long out_len, long long n_frames, long long in_off0,
+                                 long long out_off0, int hop, const int *hop_tab, double *st_last_phase,
+                                 double *st_phase_sum, double *st_ola, int load_state, int lanes) {
+    PlanDesc d;
+    d.n = 1 << log2n;
+    d.program = program;
+    d.win_in = win_in;
+    d.win_out = win_out;
+    d.hop = hop_d;
+    d.rate = rate;
+    d.ratio = ratio;
+    d.fn_bins = fn_bins;
+    d.gain = gain;
+    ChainArgs a;
+    a.in = in; a.in_stride = in_stride; a.in_len = in_len;
+    a.out = out; a.out_stride = out_stride; a.out_len = out_len;
+    a.n_frames = n_frames; a.in_off0 = in_off0; a.out_off0 = out_off0;
+    a.hop = hop; a.hop_tab = hop_tab;
+    a.st_last_phase = st_last_phase; a.st_phase_sum = st_phase_sum; a.st_ola = st_ola;
+    a.load_state = load_state; a.lanes = lanes;
+    if (precision == 0)
+        return program == PROG_PV_SHIFT ? by_size<float, PROG_PV_SHIFT>(log2n, d, a) : by_size<float, PROG_GAIN>(log2n, d, a);
+    return program == PROG_PV_SHIFT ? by_size<double, PROG_PV_SHIFT>(log2n, d, a) : by_size<double, PROG_GAIN>(log2n, d, a);
+}
+
+// M-point complex forward FFT through the kernel's Stockham passes (for unit tests of tsb_math.cuh)
+template <typename real, int LOG2M>
+static void fft_only(const double *in, double *out) {
+    constexpr int M = 1 << LOG2M;
+    constexpr int T = 32;
+    std::vector<cpx<real>> a(M), b(M), tw(M);
+    std::vector<double> t = twiddle_table(M, M);
+    for (int q = 0; q < M; q++) {
+        tw[q] = mk<real>((real)t[2 * q], (real)t[2 * q + 1]);
+        a[q] = mk<real>((real)in[2 * q], (real)in[2 * q + 1]);
+    }
+    cpx<real> *src = a.data(), *dst = b.data();
+    auto pass = [&](auto P) {
+        for (int tid = 0; tid < T; tid++) stockham_pass<real, LOG2M, T, decltype(P)::value>(tid, src, dst, tw.data());
+        std::swap(src, dst);
+    };
+    using RP = RadixPlan<LOG2M>;
+    if (RP::passes > 0) pass(std::integral_constant<int, 0>{});
+    if (RP::passes > 1) pass(std::integral_constant<int, 1>{});
+    if (RP::passes > 2) pass(std::integral_constant<int, 2>{});
+    if (RP::passes > 3) pass(std::integral_constant<int, 3>{});
+    if (RP::passes > 4) pass(std::integral_constant<int, 4>{});
+    for (int q = 0; q < M; q++) {
+        out[2 * q] = src[q].x;
+        out[2 * q + 1] = src[q].y;
+    }
+}
+extern "C" int emul_fft(int precision, int log2m, const double *in, double *out) {
+#define CASE(L)                                                     \
+    case L:                                                         \
+        if (precision == 0) fft_only<float, L>(in, out);           \
+        else fft_only<double, L>(in, out);                          \
+        return 0;
+    switch (log2m) {
+        CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12)
+    }
+    return -1;
+}

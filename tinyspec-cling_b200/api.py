@@ -1,0 +1,248 @@
+"""ctypes binding of libtsb200 (include/tsb200.h).  Device buffers are torch CUDA tensors: torch is
+used for device memory and streams only."""
+import ctypes as C
+import os
+
+import numpy as np
+
+F32, F64 = 0, 1
+PROG_PV_SHIFT, PROG_GAIN = 0, 1
+WIN_NONE, WIN_HANN, WIN_SQRT_HANN = 0, 1, 2
+_WIN = {None: 0, "none": 0, "hann": 1, "sqrt_hann": 2, 0: 0, 1: 1, 2: 2}
+_PREC = {"f32": 0, "f64": 1, 0: 0, 1: 1}
+_PROG = {"pv": 0, "pv_shift": 0, "gain": 1, 0: 0, 1: 1}
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class TsbError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "libtsb200.so")
+
+
+class _PlanDesc(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("precision", C.c_int32), ("program", C.c_int32), ("win_in", C.c_int32),
+                ("win_out", C.c_int32), ("hop", C.c_double), ("rate", C.c_double), ("ratio", C.c_double),
+                ("fn_bins", C.c_void_p), ("gain", C.c_void_p)]
+
+
+class _ChainArgs(C.Structure):
+    _fields_ = [("in_", C.c_void_p), ("in_stride", C.c_int64), ("in_len", C.c_int64), ("out", C.c_void_p),
+                ("out_stride", C.c_int64), ("out_len", C.c_int64), ("n_frames", C.c_int64), ("in_off0", C.c_int64),
+                ("out_off0", C.c_int64), ("hop", C.c_int32), ("hop_tab", C.c_void_p),
+                ("state_last_phase", C.c_void_p), ("state_phase_sum", C.c_void_p), ("state_ola", C.c_void_p),
+                ("load_state", C.c_int32), ("lanes", C.c_int32)]
+
+
+_lib = None
+
+
+def _load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise TsbError(f"{path} is missing: build it with `make -C {os.path.join(_HERE, 'csrc')} -j` "
+                       "(or __graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(path)
+    P = C.c_void_p
+    L.tsb_last_error.restype = C.c_char_p
+    L.tsb_ctx_create.argtypes = [C.c_int, P, C.POINTER(P)]
+    L.tsb_ctx_destroy.argtypes = [P]
+    L.tsb_ctx_sync.argtypes = [P]
+    L.tsb_launch_count.argtypes = [P]
+    L.tsb_launch_count.restype = C.c_int64
+    L.tsb_hop_fixed.argtypes = [C.c_double, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.tsb_schedule_const.argtypes = [C.c_int64, C.c_uint32, C.c_double, C.c_double, C.c_int64, C.c_int64,
+                                     C.POINTER(C.c_int64), P, P, P, P]
+    L.tsb_shift_map.argtypes = [C.c_uint32, C.c_double, P, P]
+    L.tsb_plan_create.argtypes = [P, C.POINTER(_PlanDesc), C.POINTER(P)]
+    L.tsb_plan_destroy.argtypes = [P]
+    L.tsb_chain_render.argtypes = [P, P, C.POINTER(_ChainArgs)]
+    L.tsb_chain_render_host.argtypes = [P, P, C.POINTER(_ChainArgs)]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise TsbError(f"libtsb200 error {rc}: {_load().tsb_last_error().decode()}")
+
+
+def abi_version():
+    return _load().tsb_abi_version()
+
+
+def hop_fixed(hop):
+    """set_hop() decomposition (rtlib/control.hpp:22-29) -> (hop_samples, hop_fract)."""
+    s, f = C.c_uint64(), C.c_uint64()
+    _check(_load().tsb_hop_fixed(float(hop), C.byref(s), C.byref(f)))
+    return s.value, f.value
+
+
+def schedule_const(in_len, n, hop, rate=48000.0, max_frames=-1):
+    """Frame tables of a constant-(n, hop) render (tinyspec.cpp:135-168)."""
+    L = _load()
+    nf = C.c_int64()
+    _check(L.tsb_schedule_const(in_len, n, float(hop), rate, max_frames, 0, C.byref(nf), None, None, None, None))
+    F = nf.value
+    tabs = dict(in_off=np.zeros(F, np.int64), out_off=np.zeros(F, np.int64), hop=np.zeros(F, np.int32),
+                t=np.zeros(F, np.float64))
+    if F:
+        _check(L.tsb_schedule_const(in_len, n, float(hop), rate, max_frames, F, C.byref(nf),
+                                    tabs["in_off"].ctypes.data, tabs["out_off"].ctypes.data,
+                                    tabs["hop"].ctypes.data, tabs["t"].ctypes.data))
+    tabs["n_frames"] = F
+    return tabs
+
+
+def shift_map(n, rate, fn_bins):
+    fb = np.ascontiguousarray(fn_bins, np.float64)
+    assert fb.shape == (n // 2,)
+    dest = np.zeros(n // 2, np.int32)
+    _check(_load().tsb_shift_map(n, rate, fb.ctypes.data, dest.ctypes.data))
+    return dest
+
+
+class Context:
+    """One device + one CUDA stream (defaults to torch's current stream on that device)."""
+
+    def __init__(self, device=0, stream="torch"):
+        L = _load()
+        sp = None
+        if stream == "torch":
+            import torch
+            sp = torch.cuda.current_stream(device).cuda_stream if torch.cuda.is_available() else None
+        elif stream is not None:
+            sp = int(stream)
+        h = C.c_void_p()
+        _check(L.tsb_ctx_create(device, sp, C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def sync(self):
+        _check(_load().tsb_ctx_sync(self.h))
+
+    @property
+    def launches(self):
+        return _load().tsb_launch_count(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            _load().tsb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Plan:
+    def __init__(self, ctx, n, precision="f64", program="pv", hop=None, rate=48000.0, ratio=1.0, fn_bins=None,
+                 gain=None, win_in="sqrt_hann", win_out="sqrt_hann"):
+        self.ctx, self.n = ctx, n
+        self.precision, self.program = _PREC[precision], _PROG[program]
+        d = _PlanDesc()
+        d.n, d.precision, d.program = n, self.precision, self.program
+        d.win_in, d.win_out = _WIN[win_in], _WIN[win_out]
+        d.hop = float(n / 4 if hop is None else hop)
+        d.rate, d.ratio = rate, ratio
+        self._fb = None if fn_bins is None else np.ascontiguousarray(fn_bins, np.float64)
+        self._g = None if gain is None else np.ascontiguousarray(gain, np.float64)
+        if self._fb is not None:
+            assert self._fb.shape == (n // 2,)
+            d.fn_bins = self._fb.ctypes.data
+        if self._g is not None:
+            assert self._g.shape == (n // 2 + 1,)
+            d.gain = self._g.ctypes.data
+        h = C.c_void_p()
+        _check(_load().tsb_plan_create(ctx.h, C.byref(d), C.byref(h)))
+        self.h = h
+
+    @property
+    def out_dtype(self):
+        import torch
+        return torch.float64 if self.precision == F64 else torch.float32
+
+    def _args(self, lanes, in_ptr, in_stride, in_len, out_ptr, out_stride, out_len, n_frames, in_off0, out_off0, hop,
+              hop_tab_ptr, st, load_state):
+        a = _ChainArgs()
+        a.in_, a.in_stride, a.in_len = in_ptr, in_stride, in_len
+        a.out, a.out_stride, a.out_len = out_ptr, out_stride, out_len
+        a.n_frames, a.in_off0, a.out_off0 = n_frames, in_off0, out_off0
+        a.hop, a.hop_tab = int(hop), hop_tab_ptr
+        a.state_last_phase, a.state_phase_sum, a.state_ola = st
+        a.load_state, a.lanes = int(load_state), lanes
+        return a
+
+    def render(self, x, n_frames, hop, out=None, in_off0=2048, out_off0=0, hop_tab=None, state=None,
+               load_state=False, out_len=None):
+        """Device path.  x: CUDA float32 [lanes, L]; returns out [lanes, out_len] (plan dtype), asynchronous on
+        the context stream.  state: dict(last_phase [lanes,n/2], phase_sum [lanes,n/2], ola [lanes,n]) of CUDA
+        float64 tensors, updated in place."""
+        import torch
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous()
+        lanes, L = x.shape
+        ht = None
+        if hop_tab is not None:
+            ht = torch.as_tensor(np.asarray(hop_tab, np.int32)).to(x.device) if not torch.is_tensor(hop_tab) else hop_tab
+            assert ht.dtype == torch.int32 and ht.numel() == n_frames
+            total = int(ht.sum().item())
+        else:
+            total = n_frames * int(hop)
+        if out is None:
+            out = torch.zeros((lanes, out_len if out_len is not None else out_off0 + total), dtype=self.out_dtype,
+                              device=x.device)
+        assert out.is_cuda and out.dtype == self.out_dtype and out.is_contiguous() and out.shape[0] == lanes
+        st = (None, None, None)
+        if state is not None:
+            for k, w in (("last_phase", self.n // 2), ("phase_sum", self.n // 2), ("ola", self.n)):
+                t = state[k]
+                assert t.is_cuda and t.dtype == torch.float64 and t.shape == (lanes, w) and t.is_contiguous()
+            st = (state["last_phase"].data_ptr(), state["phase_sum"].data_ptr(), state["ola"].data_ptr())
+        a = self._args(lanes, x.data_ptr(), x.stride(0), L, out.data_ptr(), out.stride(0), out.shape[1], n_frames,
+                       in_off0, out_off0, hop, None if ht is None else ht.data_ptr(), st, load_state)
+        _check(_load().tsb_chain_render(self.ctx.h, self.h, C.byref(a)))
+        self._keep = (x, out, ht, state)
+        return out
+
+    def render_host(self, x, n_frames, hop, out=None, in_off0=2048, out_off0=0, hop_tab=None, state=None,
+                    load_state=False, out_len=None):
+        """Host path (tsb_chain_render_host): x / out are numpy arrays or CPU torch tensors (pinned or not);
+        returns when `out` holds the result."""
+        import torch
+        xt = torch.as_tensor(x)
+        assert not xt.is_cuda and xt.dtype == torch.float32 and xt.dim() == 2 and xt.is_contiguous()
+        lanes, L = xt.shape
+        ht = None if hop_tab is None else np.ascontiguousarray(hop_tab, np.int32)
+        total = int(ht.sum()) if ht is not None else n_frames * int(hop)
+        if out is None:
+            out = torch.zeros((lanes, out_len if out_len is not None else out_off0 + total), dtype=self.out_dtype)
+        ot = torch.as_tensor(out)
+        assert ot.dtype == self.out_dtype and ot.is_contiguous() and ot.shape[0] == lanes
+        st = (None, None, None)
+        if state is not None:
+            for k, w in (("last_phase", self.n // 2), ("phase_sum", self.n // 2), ("ola", self.n)):
+                assert state[k].dtype == np.float64 and state[k].shape == (lanes, w)
+            st = tuple(state[k].ctypes.data for k in ("last_phase", "phase_sum", "ola"))
+        a = self._args(lanes, xt.data_ptr(), xt.stride(0), L, ot.data_ptr(), ot.stride(0), ot.shape[1], n_frames,
+                       in_off0, out_off0, hop, None if ht is None else ht.ctypes.data, st, load_state)
+        _check(_load().tsb_chain_render_host(self.ctx.h, self.h, C.byref(a)))
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            _load().tsb_plan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,331 @@
+// tsb_api.cu — the C ABI of libtsb200 (include/tsb200.h): contexts, plans, launches.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/tsb200.h"
+#include "tsb_launch.hpp"
+#include "tsb_plan.hpp"
+
+using namespace tsb;
+
+#define TSB_API extern "C" __attribute__((visibility("default")))
+
+static thread_local std::string g_err;
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(TSB_ECUDA, "%s: %s", #call, cudaGetErrorString(e_));   \
+    } while (0)
+
+struct tsb_ctx {
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    int64_t launches;
+};
+
+struct tsb_plan {
+    tsb_ctx *ctx;
+    tsb_plan_desc desc;
+    int log2n;
+    std::vector<void *> dev;  // device allocations owned by the plan
+    ChainTables<float> t32;
+    ChainTables<double> t64;
+};
+
+TSB_API int tsb_abi_version(void) { return TSB_ABI_VERSION; }
+TSB_API const char *tsb_last_error(void) { return g_err.c_str(); }
+
+TSB_API int tsb_ctx_create(int device, void *cuda_stream, tsb_ctx **out) {
+    if (!out) return fail(TSB_EINVAL, "tsb_ctx_create: null out pointer");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(TSB_ECUDA, "no usable CUDA device (%s); libtsb200 has no CPU path",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(TSB_EINVAL, "device %d out of range (0..%d)", device, count - 1);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(TSB_EUNSUPPORTED, "device %d is sm_%d%d; libtsb200 is built for sm_100a only", device, prop.major,
+                    prop.minor);
+    tsb_ctx *c = new tsb_ctx{device, nullptr, false, 0};
+    if (cuda_stream) {
+        c->stream = (cudaStream_t)cuda_stream;
+    } else {
+        cudaError_t e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e2 != cudaSuccess) {
+            delete c;
+            return fail(TSB_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e2));
+        }
+        c->own_stream = true;
+    }
+    *out = c;
+    return TSB_OK;
+}
+TSB_API int tsb_ctx_destroy(tsb_ctx *c) {
+    if (!c) return TSB_OK;
+    cudaSetDevice(c->device);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return TSB_OK;
+}
+TSB_API int tsb_ctx_sync(tsb_ctx *c) {
+    if (!c) return fail(TSB_EINVAL, "null context");
+    CU(cudaStreamSynchronize(c->stream));
+    return TSB_OK;
+}
+TSB_API int64_t tsb_launch_count(tsb_ctx *c) { return c ? c->launches : 0; }
+
+TSB_API int tsb_malloc(tsb_ctx *c, size_t bytes, void **dptr) {
+    if (!c || !dptr) return fail(TSB_EINVAL, "tsb_malloc: null argument");
+    CU(cudaSetDevice(c->device));
+    cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) return fail(TSB_ENOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return TSB_OK;
+}
+TSB_API int tsb_free(tsb_ctx *c, void *dptr) {
+    if (!c) return fail(TSB_EINVAL, "null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaFree(dptr));
+    return TSB_OK;
+}
+TSB_API int tsb_memset(tsb_ctx *c, void *dptr, int value, size_t bytes) {
+    if (!c) return fail(TSB_EINVAL, "null context");
+    CU(cudaMemsetAsync(dptr, value, bytes, c->stream));
+    return TSB_OK;
+}
+TSB_API int tsb_upload(tsb_ctx *c, void *dptr, const void *host, size_t bytes) {
+    if (!c) return fail(TSB_EINVAL, "null context");
+    CU(cudaMemcpyAsync(dptr, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    return TSB_OK;
+}
+TSB_API int tsb_download(tsb_ctx *c, void *host, const void *dptr, size_t bytes) {
+    if (!c) return fail(TSB_EINVAL, "null context");
+    CU(cudaMemcpyAsync(host, dptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return TSB_OK;
+}
+
+// ---- host logic ----
+TSB_API int tsb_hop_fixed(double hop, uint64_t *hop_samples, uint64_t *hop_fract) {
+    if (!hop_samples || !hop_fract) return fail(TSB_EINVAL, "tsb_hop_fixed: null output");
+    if (!hop_fixed(hop, hop_samples, hop_fract)) return fail(TSB_EINVAL, "ignoring invalid hop: %g", hop);
+    return TSB_OK;
+}
+TSB_API int tsb_schedule_const(int64_t in_len, uint32_t n, double hop, double rate, int64_t max_frames, int64_t cap,
+                                  int64_t *n_frames, int64_t *in_off, int64_t *out_off, int32_t *hop_tab, double *t) {
+    if (!n_frames) return fail(TSB_EINVAL, "tsb_schedule_const: null n_frames");
+    if (hop < 0) return fail(TSB_EINVAL, "ignoring invalid hop: %g", hop);
+    if (n == 0) return fail(TSB_EINVAL, "frame size 0");
+    SchedState st;
+    st.rate = rate;
+    std::vector<FrameRec> fr = schedule_const(st, in_len, n, hop, max_frames);
+    *n_frames = (int64_t)fr.size();
+    int64_t lim = (int64_t)fr.size() < cap ? (int64_t)fr.size() : cap;
+    for (int64_t f = 0; f < lim; f++) {
+        if (in_off) in_off[f] = fr[f].in_off;
+        if (out_off) out_off[f] = fr[f].out_off;
+        if (hop_tab) hop_tab[f] = fr[f].hop;
+        if (t) t[f] = fr[f].t;
+    }
+    return TSB_OK;
+}
+TSB_API int tsb_shift_map(uint32_t n, double rate, const double *fn_bins, int32_t *dest) {
+    if (!fn_bins || !dest || n < 2) return fail(TSB_EINVAL, "tsb_shift_map: bad argument");
+    std::vector<uint32_t> map;
+    std::vector<uint16_t> src;
+    if (n > 65536) return fail(TSB_EUNSUPPORTED, "tsb_shift_map: n > 65536");
+    build_shift_map((int)n, rate, fn_bins, map, src);
+    for (uint32_t j = 0; j < n / 2; j++) dest[j] = -1;
+    for (uint32_t k = 0; k < n / 2; k++) {
+        uint32_t first = map[k] >> 16, cnt = map[k] & 0xffff;
+        for (uint32_t s = 0; s < cnt; s++) dest[src[first + s]] = (int32_t)k;
+    }
+    return TSB_OK;
+}
+
+// ---- plans ----
+template <typename T>
+static int upload_vec(tsb_plan *p, const std::vector<T> &v, const T **dst) {
+    void *d = nullptr;
+    size_t bytes = v.size() * sizeof(T);
+    cudaError_t e = cudaMalloc(&d, bytes ? bytes : 16);
+    if (e != cudaSuccess) return fail(TSB_ENOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    p->dev.push_back(d);
+    CU(cudaMemcpy(d, v.data(), bytes, cudaMemcpyHostToDevice));
+    *dst = reinterpret_cast<const T *>(d);
+    return TSB_OK;
+}
+template <typename real>
+static int upload_tables(tsb_plan *p, const PlanDesc &d, ChainTables<real> &t) {
+    HostTables<real> h = build_tables<real>(d);
+    t = h.view();
+    int r;
+    if ((r = upload_vec(p, h.tw, &t.tw))) return r;
+    if ((r = upload_vec(p, h.twn, &t.twn))) return r;
+    if ((r = upload_vec(p, h.win_a, &t.win_a))) return r;
+    if ((r = upload_vec(p, h.win_s, &t.win_s))) return r;
+    if ((r = upload_vec(p, h.expect, &t.expect))) return r;
+    if ((r = upload_vec(p, h.map, &t.map))) return r;
+    if ((r = upload_vec(p, h.map_src, &t.map_src))) return r;
+    if ((r = upload_vec(p, h.gain, &t.gain))) return r;
+    return TSB_OK;
+}
+
+TSB_API int tsb_plan_destroy(tsb_plan *p) {
+    if (!p) return TSB_OK;
+    cudaSetDevice(p->ctx->device);
+    for (void *d : p->dev) cudaFree(d);
+    delete p;
+    return TSB_OK;
+}
+TSB_API int tsb_plan_create(tsb_ctx *c, const tsb_plan_desc *desc, tsb_plan **out) {
+    if (!c || !desc || !out) return fail(TSB_EINVAL, "tsb_plan_create: null argument");
+    uint32_t n = desc->n;
+    if (n < 64 || n > 8192 || (n & (n - 1)))
+        return fail(TSB_EUNSUPPORTED, "frame size %u: the fused chain supports powers of two in 64..8192", n);
+    if (desc->precision != TSB_F32 && desc->precision != TSB_F64) return fail(TSB_EINVAL, "bad precision %d", desc->precision);
+    if (desc->program != TSB_PROG_PV_SHIFT && desc->program != TSB_PROG_GAIN) return fail(TSB_EINVAL, "bad program %d", desc->program);
+    if (desc->program == TSB_PROG_PV_SHIFT && !(desc->hop > 0)) return fail(TSB_EINVAL, "phase vocoder needs hop > 0 (got %g)", desc->hop);
+    if (!(desc->rate > 0)) return fail(TSB_EINVAL, "bad rate %g", desc->rate);
+    CU(cudaSetDevice(c->device));
+    tsb_plan *p = new tsb_plan();
+    p->ctx = c;
+    p->desc = *desc;
+    p->log2n = ilog2(n);
+    PlanDesc d;
+    d.n = (int)n;
+    d.program = desc->program;
+    bool pv = desc->program == TSB_PROG_PV_SHIFT;
+    d.win_in = pv ? (int)WIN_SQRT_HANN : desc->win_in;
+    d.win_out = pv ? (int)WIN_SQRT_HANN : desc->win_out;
+    d.hop = desc->hop > 0 ? desc->hop : 1.0;
+    d.rate = desc->rate;
+    d.ratio = desc->ratio;
+    d.fn_bins = desc->fn_bins;
+    d.gain = desc->gain;
+    int r = desc->precision == TSB_F32 ? upload_tables<float>(p, d, p->t32) : upload_tables<double>(p, d, p->t64);
+    if (r) {
+        tsb_plan_destroy(p);
+        return r;
+    }
+    p->desc.fn_bins = nullptr;
+    p->desc.gain = nullptr;
+    *out = p;
+    return TSB_OK;
+}
+
+// ---- the fused chain ----
+static chain_launch_fn launcher(int log2n) {
+    switch (log2n) {
+        case 6: return launch_chain_6;
+        case 7: return launch_chain_7;
+        case 8: return launch_chain_8;
+        case 9: return launch_chain_9;
+        case 10: return launch_chain_10;
+        case 11: return launch_chain_11;
+        case 12: return launch_chain_12;
+        case 13: return launch_chain_13;
+    }
+    return nullptr;
+}
+static int check_args(const tsb_chain_args *a) {
+    if (!a) return fail(TSB_EINVAL, "null args");
+    if (a->lanes < 0 || a->n_frames < 0) return fail(TSB_EINVAL, "negative lanes / n_frames");
+    if (a->lanes && a->n_frames && (!a->in || !a->out)) return fail(TSB_EINVAL, "null in/out");
+    if (!a->hop_tab && a->hop < 0) return fail(TSB_EINVAL, "negative hop");
+    if (a->in_off0 < 0 || a->out_off0 < 0) return fail(TSB_EINVAL, "negative offset");
+    return TSB_OK;
+}
+static ChainArgs to_args(const tsb_chain_args *a) {
+    ChainArgs k;
+    k.in = a->in; k.in_stride = a->in_stride; k.in_len = a->in_len;
+    k.out = a->out; k.out_stride = a->out_stride; k.out_len = a->out_len;
+    k.n_frames = a->n_frames; k.in_off0 = a->in_off0; k.out_off0 = a->out_off0;
+    k.hop = a->hop; k.hop_tab = a->hop_tab;
+    k.st_last_phase = a->state_last_phase; k.st_phase_sum = a->state_phase_sum; k.st_ola = a->state_ola;
+    k.load_state = a->load_state; k.lanes = a->lanes;
+    return k;
+}
+TSB_API int tsb_chain_render(tsb_ctx *c, tsb_plan *p, const tsb_chain_args *a) {
+    if (!c || !p) return fail(TSB_EINVAL, "null context / plan");
+    int r = check_args(a);
+    if (r) return r;
+    if (a->lanes == 0 || a->n_frames == 0) return TSB_OK;
+    CU(cudaSetDevice(c->device));
+    ChainArgs k = to_args(a);
+    chain_launch_fn fn = launcher(p->log2n);
+    if (!fn) return fail(TSB_EUNSUPPORTED, "no kernel for frame size 2^%d", p->log2n);
+    const void *tb = p->desc.precision == TSB_F32 ? (const void *)&p->t32 : (const void *)&p->t64;
+    cudaError_t e = fn(p->desc.precision, p->desc.program, tb, k, c->stream);
+    if (e != cudaSuccess) return fail(TSB_ECUDA, "chain kernel launch: %s", cudaGetErrorString(e));
+    c->launches++;
+    return TSB_OK;
+}
+
+TSB_API int tsb_chain_render_host(tsb_ctx *c, tsb_plan *p, const tsb_chain_args *a) {
+    if (!c || !p) return fail(TSB_EINVAL, "null context / plan");
+    int r = check_args(a);
+    if (r) return r;
+    if (a->lanes == 0 || a->n_frames == 0) return TSB_OK;
+    CU(cudaSetDevice(c->device));
+    const size_t n = p->desc.n, m = n / 2, lanes = (size_t)a->lanes;
+    const size_t osz = p->desc.precision == TSB_F32 ? 4 : 8;
+    const size_t in_bytes = lanes * (size_t)a->in_stride * 4, out_bytes = lanes * (size_t)a->out_stride * osz;
+    struct Dev {
+        std::vector<void *> ptrs;
+        ~Dev() { for (void *q : ptrs) cudaFree(q); }
+        void *get(size_t bytes) {
+            void *q = nullptr;
+            if (cudaMalloc(&q, bytes ? bytes : 16) != cudaSuccess) return nullptr;
+            ptrs.push_back(q);
+            return q;
+        }
+    } dev;
+    tsb_chain_args d = *a;
+    float *din = (float *)dev.get(in_bytes);
+    void *dout = dev.get(out_bytes);
+    if (!din || !dout) return fail(TSB_ENOMEM, "device allocation of %zu + %zu bytes failed", in_bytes, out_bytes);
+    CU(cudaMemcpyAsync(din, a->in, in_bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(dout, 0, out_bytes, c->stream));
+    d.in = din;
+    d.out = dout;
+    if (a->hop_tab) {
+        int32_t *dh = (int32_t *)dev.get((size_t)a->n_frames * 4);
+        if (!dh) return fail(TSB_ENOMEM, "device allocation failed");
+        CU(cudaMemcpyAsync(dh, a->hop_tab, (size_t)a->n_frames * 4, cudaMemcpyHostToDevice, c->stream));
+        d.hop_tab = dh;
+    }
+    double *host_state[3] = {a->state_last_phase, a->state_phase_sum, a->state_ola};
+    double **dev_state[3] = {&d.state_last_phase, &d.state_phase_sum, &d.state_ola};
+    size_t st_bytes[3] = {lanes * m * 8, lanes * m * 8, lanes * n * 8};
+    for (int i = 0; i < 3; i++) {
+        if (!host_state[i]) continue;
+        double *q = (double *)dev.get(st_bytes[i]);
+        if (!q) return fail(TSB_ENOMEM, "device allocation failed");
+        if (a->load_state) CU(cudaMemcpyAsync(q, host_state[i], st_bytes[i], cudaMemcpyHostToDevice, c->stream));
+        *dev_state[i] = q;
+    }
+    r = tsb_chain_render(c, p, &d);
+    if (r) return r;
+    CU(cudaMemcpyAsync(a->out, dout, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    for (int i = 0; i < 3; i++)
+        if (host_state[i]) CU(cudaMemcpyAsync(host_state[i], *dev_state[i], st_bytes[i], cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TSB_OK;
+}

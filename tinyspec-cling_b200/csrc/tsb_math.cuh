@@ -1,0 +1,170 @@
+// tsb_math.cuh — complex arithmetic, radix-2/4/8 butterflies and the shared-memory Stockham pass
+// used by every FFT in this library (sm_100a).  Everything here is written as per-thread code with
+// no barriers inside, so that the very same functions can also be driven thread-by-thread from a
+// host test harness (tests/emul); barriers live in the callers.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define TSB_HD __host__ __device__ __forceinline__
+#define TSB_D __device__ __forceinline__
+#else
+#define TSB_HD inline
+#define TSB_D inline
+#endif
+
+#define TSB_LDG(p) tsb::ldg(p)
+
+namespace tsb {
+
+template <typename T>
+struct alignas(2 * sizeof(T)) cpx {
+    T x, y;
+};
+
+// read-only (non-coherent) global loads for the constant tables
+template <typename T>
+TSB_HD T ldg(const T *p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+TSB_HD cpx<float> ldg(const cpx<float> *p) {
+#if defined(__CUDA_ARCH__)
+    float2 v = __ldg(reinterpret_cast<const float2 *>(p));
+    cpx<float> r;
+    r.x = v.x;
+    r.y = v.y;
+    return r;
+#else
+    return *p;
+#endif
+}
+TSB_HD cpx<double> ldg(const cpx<double> *p) {
+#if defined(__CUDA_ARCH__)
+    double2 v = __ldg(reinterpret_cast<const double2 *>(p));
+    cpx<double> r;
+    r.x = v.x;
+    r.y = v.y;
+    return r;
+#else
+    return *p;
+#endif
+}
+template <typename T>
+TSB_HD cpx<T> mk(T x, T y) {
+    cpx<T> r;
+    r.x = x;
+    r.y = y;
+    return r;
+}
+template <typename T>
+TSB_HD cpx<T> operator+(cpx<T> a, cpx<T> b) { return mk<T>(a.x + b.x, a.y + b.y); }
+template <typename T>
+TSB_HD cpx<T> operator-(cpx<T> a, cpx<T> b) { return mk<T>(a.x - b.x, a.y - b.y); }
+template <typename T>
+TSB_HD cpx<T> cmul(cpx<T> a, cpx<T> b) { return mk<T>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+template <typename T>
+TSB_HD cpx<T> conj(cpx<T> a) { return mk<T>(a.x, -a.y); }
+// multiply by -i (forward-transform quarter turn)
+template <typename T>
+TSB_HD cpx<T> mul_mi(cpx<T> a) { return mk<T>(a.y, -a.x); }
+
+constexpr int ilog2(unsigned v) { return v <= 1 ? 0 : 1 + ilog2(v >> 1); }
+
+// ---- forward DFTs of size 2, 4, 8 (kernel exp(-2*pi*i*j*k/R)), natural order in and out ----
+template <typename T>
+TSB_HD void dft2(cpx<T> &a, cpx<T> &b) {
+    cpx<T> t = a;
+    a = t + b;
+    b = t - b;
+}
+template <typename T>
+TSB_HD void dft4(cpx<T> &v0, cpx<T> &v1, cpx<T> &v2, cpx<T> &v3) {
+    cpx<T> t0 = v0 + v2, t1 = v0 - v2, t2 = v1 + v3, t3 = mul_mi(v1 - v3);
+    v0 = t0 + t2;
+    v2 = t0 - t2;
+    v1 = t1 + t3;
+    v3 = t1 - t3;
+}
+template <typename T>
+TSB_HD void dft8(cpx<T> *v) {
+    const T h = (T)0.70710678118654752440084436210485;
+    cpx<T> e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
+    cpx<T> o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];
+    dft4(e0, e1, e2, e3);
+    dft4(o0, o1, o2, o3);
+    // w8^k * O[k], w8 = exp(-i*pi/4)
+    cpx<T> p1 = mk<T>((o1.x + o1.y) * h, (o1.y - o1.x) * h);
+    cpx<T> p2 = mul_mi(o2);
+    cpx<T> p3 = mk<T>((o3.y - o3.x) * h, -(o3.x + o3.y) * h);
+    v[0] = e0 + o0;
+    v[4] = e0 - o0;
+    v[1] = e1 + p1;
+    v[5] = e1 - p1;
+    v[2] = e2 + p2;
+    v[6] = e2 - p2;
+    v[3] = e3 + p3;
+    v[7] = e3 - p3;
+}
+template <int R, typename T>
+TSB_HD void dftR(cpx<T> *v) {
+    if (R == 8) dft8(v);
+    else if (R == 4) dft4(v[0], v[1], v[2], v[3]);
+    else dft2(v[0], v[1]);
+}
+
+// Radix plan for an M-point transform: as many radix-8 passes as possible, the remainder (2 or 4)
+// taken LAST so that the twiddle-free first pass is a radix-8 one.
+template <int LOG2M>
+struct RadixPlan {
+    static constexpr int n8 = LOG2M / 3;
+    static constexpr int rem = LOG2M % 3;  // 0, 1 (radix 2) or 2 (radix 4)
+    static constexpr int passes = n8 + (rem ? 1 : 0);
+    static constexpr int radix(int p) { return p < n8 ? 8 : (1 << rem); }
+    static constexpr int ns(int p) { return p <= n8 ? (1 << (3 * p)) : (1 << (3 * n8)); }
+};
+
+// One thread's share of Stockham pass `P` of an M-point forward FFT: src -> dst (both M complex,
+// distinct buffers).  Butterfly j reads src[j + t*M/R], applies twiddle exp(-2*pi*i*(j%Ns)*t/(Ns*R)),
+// does a radix-R DFT and writes dst[(j/Ns)*Ns*R + (j%Ns) + t*Ns].  `tw` is the M-entry table
+// tw[q] = exp(-2*pi*i*q/M).
+template <typename T, int LOG2M, int THREADS, int P>
+TSB_HD void stockham_pass(int tid, const cpx<T> *src, cpx<T> *dst, const cpx<T> *tw) {
+    using RP = RadixPlan<LOG2M>;
+    constexpr int M = 1 << LOG2M;
+    constexpr int R = RP::radix(P);
+    constexpr int Ns = RP::ns(P);
+    constexpr int NB = M / R;  // butterflies in this pass
+    constexpr int ITER = (NB + THREADS - 1) / THREADS;
+#pragma unroll
+    for (int it = 0; it < ITER; it++) {
+        int j = tid + it * THREADS;
+        if (NB % THREADS != 0 && j >= NB) break;
+        cpx<T> v[R];
+#pragma unroll
+        for (int t = 0; t < R; t++) v[t] = src[j + t * NB];
+        if (Ns > 1) {
+            int jm = j & (Ns - 1);
+            constexpr int STEP = M / (Ns * R);
+#pragma unroll
+            for (int t = 1; t < R; t++) {
+                cpx<T> w = TSB_LDG(&tw[jm * t * STEP]);
+                v[t] = cmul(v[t], w);
+            }
+            dftR<R>(v);
+            int base = ((j - jm) * R) + jm;
+#pragma unroll
+            for (int t = 0; t < R; t++) dst[base + t * Ns] = v[t];
+        } else {
+            dftR<R>(v);
+#pragma unroll
+            for (int t = 0; t < R; t++) dst[j * R + t] = v[t];
+        }
+    }
+}
+
+}  // namespace tsb
