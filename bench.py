@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py — the contract benchmark (see DESIGN.md "Measurement").
+
+One step = one pass of the fused hot path (gather -> sqrt-Hann -> R2C -> phase-vocoder analyse / shift x2 /
+synthesise -> C2R -> sqrt-Hann -> overlap-add) over one batch of synthetic streams.
+
+Workload (config.workload = "cfg1x"): BASELINE.json configs[0] — hacks/pitchshift-pv.cpp, stereo 48 kHz,
+frame 1024, hop 256, 60 s per stream (11,239 frames) — replicated over S independent streams per GPU so
+that one launch fills the device (a single stereo stream is 2 lanes; SURVEY.md §8d asks for both figures,
+the single-stream one is reported as `single_stream`).  N GPUs: every rank renders its own S streams
+(stream sharding, no data-path collective) -> "scaling": "weak".
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--precision f64|f32] [--streams S] [--seconds T]
+  python bench.py --impl reference ...   # the reference's own CPU implementation on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_FRAME, HOP, CH, RATE, SHIFT = 1024, 256, 2, 48000.0, 2.0
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def b_alg(precision):
+    """Algorithmic bytes per frame-channel: hop*(s_in + s_out); the 32*N_live/F_launch state
+    term is counted from the state arrays actually read/written once per launch."""
+    return HOP * (4 + (8 if precision == "f64" else 4))
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            f = [v.strip() for v in r.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synth_input(torch, lanes, length, device, seed):
+    """0.5*sin(2*pi*f*n/48000) + 0.1*(u-0.5), f = 440 + 110*c + 0.37*s (SURVEY.md §8d shape; u from torch's
+    generator instead of the LCG — values need not match the oracle here, parity is tests/' job)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    n = torch.arange(length, device=device, dtype=torch.float64)
+    lane = torch.arange(lanes, device=device)
+    f = 440.0 + 110.0 * (lane % CH).double() + 0.37 * (lane // CH).double()
+    x = torch.empty((lanes, length), dtype=torch.float32, device=device)
+    step = 64
+    for a in range(0, lanes, step):
+        b = min(lanes, a + step)
+        ph = (2.0 * 3.141592653589793 / RATE) * f[a:b, None] * n[None, :]
+        x[a:b] = (0.5 * torch.sin(ph) + 0.1 * (torch.rand((b - a, length), generator=g, device=device,
+                                                          dtype=torch.float64) - 0.5)).float()
+    return x
+
+
+def ref_binary():
+    for name in ("ref_pv_tap_mkl", "ref_pv_tap"):
+        p = os.path.join(ROOT, "oracle", "_ref", name)
+        if os.path.exists(p):
+            try:
+                env = dict(os.environ, TSREF_SAMPLES="8192", TSREF_N=str(N_FRAME))
+                subprocess.run([p], env=env, cwd="/tmp", check=True, timeout=60, stdout=subprocess.DEVNULL,
+                               stderr=subprocess.DEVNULL)
+                return p, ("MKL DFTI standing in for FFTW" if name.endswith("_mkl") else "radix-2 FFT shim standing in for FFTW")
+            except Exception:
+                continue
+    return None, None
+
+
+def run_reference(procs, seconds):
+    """`procs` concurrent copies of the compiled, unmodified reference (oracle/_ref), one stereo stream each
+    (its own README's way to scale, README.md:85-86).  Returns (frames per process, wall seconds)."""
+    binary, fft = ref_binary()
+    samples = int(seconds * RATE)
+    if binary is None:
+        # the oracle port as a stand-in (kind "port")
+        from oracle import orc
+        x = orc.gen_signal(0, CH, samples)
+        t0 = time.perf_counter()
+        r = orc.render_pv(x, N_FRAME, HOP / N_FRAME, SHIFT)
+        return r["frames"], time.perf_counter() - t0, "port", "C oracle (oracle/oracle.c), radix-2 FFT", 1
+    import tempfile
+    env = dict(os.environ, TSREF_SAMPLES=str(samples), TSREF_N=str(N_FRAME), TSREF_HOP_RATIO=str(HOP / N_FRAME),
+               TSREF_SHIFT=str(SHIFT), TSREF_CH=str(CH), TSREF_TIMING="1", TSREF_DUMP_FIRST="0")
+    dirs = [tempfile.mkdtemp(prefix="tsref") for _ in range(procs)]
+    t0 = time.perf_counter()
+    ps = [subprocess.Popen([binary], env=dict(env, TSREF_STREAM=str(i)), cwd=d, stdout=subprocess.PIPE,
+                           stderr=subprocess.DEVNULL, text=True) for i, d in enumerate(dirs)]
+    outs = [p.communicate()[0] for p in ps]
+    wall = time.perf_counter() - t0
+    frames = 0
+    for o in outs:
+        for line in o.splitlines():
+            if line.startswith("{"):
+                frames = json.loads(line)["frames"]
+    return frames, wall, "reference", f"unmodified reference (oracle/_ref), {fft}", procs
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--streams", type=int, default=444, help="independent stereo streams per GPU")
+    ap.add_argument("--seconds", type=float, default=60.0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary figures (other precision, single stream)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    L = int(args.seconds * RATE)
+    peak, peak_src = peaks()
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cores = os.cpu_count() or 1
+        secs = min(args.seconds, 20.0)
+        times, frames = [], 0
+        for i in range(args.warmup + args.steps):
+            frames, wall, kind, what, used = run_reference(cores, secs)
+            if i >= args.warmup:
+                times.append(wall)
+        tot = sum(times)
+        fps = used * frames * len(times) / tot
+        line = {"impl": "reference", "metric": "stft_pv_istft_frames_per_s", "value": fps, "unit": "frames/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "frame_channels_per_s": fps * CH, "out_samples_per_s": fps * CH * HOP,
+                "config": {"workload": "cfg1x", "frame": N_FRAME, "hop": HOP, "channels": CH, "rate": RATE,
+                           "shift": SHIFT, "streams_per_step": used, "seconds_per_stream": secs},
+                "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": used, "kind": kind,
+                                 "sample": f"{used} concurrent processes x 1 stereo stream x {secs:g} s "
+                                           f"({frames} frames each) per step; {what}"},
+                "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import tsb200
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libtsb200 has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ctx = tsb200.Context(local)
+    sch = tsb200.schedule_const(L, N_FRAME, HOP, RATE)
+    F = sch["n_frames"]
+    S = args.streams
+    lanes = S * CH
+    x = synth_input(torch, lanes, L, dev, 1234 + rank)
+
+    def timed(plan, xin, out, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            plan.render(xin, F, HOP, out=out)
+        barrier()
+        if sampler:
+            sampler.start()
+        l0 = ctx.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            plan.render(xin, F, HOP, out=out)
+        e1.record()
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        return max_over_ranks(e0.elapsed_time(e1)), ctx.launches - l0, clocks
+
+    def device_leg(precision, steps, warmup, sampler=None):
+        plan = tsb200.Plan(ctx, N_FRAME, precision=precision, program="pv", hop=HOP, rate=RATE, ratio=SHIFT)
+        out = torch.zeros((lanes, F * HOP), dtype=plan.out_dtype, device=dev)
+        ms, launches, clocks = timed(plan, x, out, steps, warmup, sampler)
+        del out
+        return ms / steps, launches, clocks
+
+    ms_step, launches, clocks = device_leg(args.precision, args.steps, args.warmup, ClockSampler(local))
+    frames_all = world * S * F
+    fps = frames_all / (ms_step * 1e-3)
+    fcs = fps * CH
+    balg = b_alg(args.precision)
+    state_bytes = lanes * (N_FRAME // 2) * 8 * 2 * 2 * 0  # state arrays are not passed in the bench (reset start)
+    alg_bytes_launch = S * F * CH * balg + state_bytes
+    achieved = alg_bytes_launch / (ms_step * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp)).get(args.precision)
+        if tj:
+            traffic = tj["dram_bytes_per_frame_channel"] * S * F * CH
+
+    line = {"metric": "stft_pv_istft_frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "frame_channels_per_s": fcs, "out_samples_per_s": fcs * HOP,
+            "config": {"workload": "cfg1x", "what": "hacks/pitchshift-pv.cpp chain (BASELINE configs[0]) x S streams",
+                       "frame": N_FRAME, "hop": HOP, "channels": CH, "rate": RATE, "shift": SHIFT,
+                       "seconds_per_stream": args.seconds, "frames_per_stream": F, "streams_per_gpu": S,
+                       "lanes_per_gpu": lanes, "sharding": "streams across GPUs, no collective",
+                       "l2": f"inputs larger than L2 ({lanes * L * 4 / 1e9:.1f} GB in per GPU)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_frame_channel": balg,
+                         "kernel": "tsb::chain_kernel<" + ("double" if args.precision == "f64" else "float") + ",10,PV>",
+                         "note": "the fused chain is issue/latency-bound, not HBM-bound (SURVEY.md §7 hard part 1); "
+                                 "see profiles/ for the ncu SOL"},
+            "clocks": clocks, "gpu_launches": launches}
+
+    # ---- end to end through the C ABI with HOST buffers (tsb_chain_render_host) ----
+    if not args.no_e2e:
+        plan = tsb200.Plan(ctx, N_FRAME, precision=args.precision, program="pv", hop=HOP, rate=RATE, ratio=SHIFT)
+        xh = torch.empty((lanes, L), dtype=torch.float32, pin_memory=True)
+        xh.copy_(x)
+        oh = torch.empty((lanes, F * HOP), dtype=plan.out_dtype, pin_memory=True)
+        del x
+        torch.cuda.empty_cache()
+        plan.render_host(xh, F, HOP, out=oh)  # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        esteps = max(1, min(args.steps, 2))
+        for _ in range(esteps):
+            plan.render_host(xh, F, HOP, out=oh)
+        barrier()
+        ems = max_over_ranks((time.perf_counter() - t0) * 1e3) / esteps
+        line["e2e"] = {"value": frames_all / (ems * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": lanes * L * 4,
+                       "d2h_bytes_per_step": lanes * F * HOP * oh.element_size(), "ms_per_step": ems, "steps": esteps,
+                       "api": "tsb_chain_render_host (pinned host buffers; upload + kernel + download inside the timed region)"}
+        x = xh[:, :].to(dev) if not args.no_extras else None
+        del oh
+    # ---- secondary figures (rank 0 describes them; all ranks run them to stay in step) ----
+    if not args.no_extras and x is not None:
+        other = "f32" if args.precision == "f64" else "f64"
+        oms, _, _ = device_leg(other, max(1, args.steps), 1)
+        ofps = frames_all / (oms * 1e-3)
+        line["other_precision"] = {"dtype": other, "value": ofps, "unit": "frames/s", "ms_per_step": oms,
+                                   "roofline_frac": ofps * CH * b_alg(other) / 1e9 / peak}
+        if world == 1:
+            plan1 = tsb200.Plan(ctx, N_FRAME, precision=args.precision, program="pv", hop=HOP, rate=RATE, ratio=SHIFT)
+            x1 = x[:CH].contiguous()
+            o1 = torch.zeros((CH, F * HOP), dtype=plan1.out_dtype, device=dev)
+            plan1.render(x1, F, HOP, out=o1)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            plan1.render(x1, F, HOP, out=o1)
+            e1.record()
+            torch.cuda.synchronize()
+            line["single_stream"] = {"value": F / (e0.elapsed_time(e1) * 1e-3), "unit": "frames/s",
+                                     "note": "one stereo 60 s stream alone (2 lanes): latency-bound by construction"}
+    # ---- CPU baseline: rank 0, N=1 only, bounded sample ----
+    if rank == 0 and world == 1:
+        frames, wall, kind, what, used = run_reference(1, min(args.seconds, 60.0))
+        line["cpu_baseline"] = {"value": frames / wall, "unit": "frames/s", "cores": used, "kind": kind,
+                                "sample": f"1 process, 1 stereo stream x {min(args.seconds, 60.0):g} s = {frames} frames; {what}"}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

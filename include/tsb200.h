@@ -40,8 +40,9 @@ int tsb_abi_version(void);
 const char *tsb_last_error(void);
 
 /* ---- context ------------------------------------------------------------------------------- */
-/* `cuda_stream` is a cudaStream_t to run on (e.g. the caller's current stream) or NULL to create one. */
-int tsb_ctx_create(int device, void *cuda_stream, tsb_ctx **ctx);
+/* new_stream == 0: run on `cuda_stream`, a cudaStream_t of the caller (NULL = the default stream);
+ * new_stream != 0: create and own a non-blocking stream (cuda_stream is ignored). */
+int tsb_ctx_create(int device, void *cuda_stream, int new_stream, tsb_ctx **ctx);
 int tsb_ctx_destroy(tsb_ctx *ctx);
 int tsb_ctx_sync(tsb_ctx *ctx);
 /* device memory for bindings that have no CUDA runtime of their own (cgo / JNI / ctypes) */

@@ -138,10 +138,11 @@ def test_pv_segments_bit_identical(env):
 @pytest.mark.parametrize("precision", ["f64", "f32"])
 def test_gain_vs_oracle(env, n, ch, filt, precision):
     torch, tsb, orc = env["torch"], env["tsb"], env["orc"]
-    x = orc.gen_signal(0, ch, 12 * n)
+    x = orc.gen_signal(0, ch, 2048 + 12 * n)
     gain = 1.0 / (1.0 + np.arange(n // 2 + 1) / 64.0) if filt else None
     ref = orc.render_filter(x, n, 0.25, gain)
     F = ref["frames"]
+    assert F >= 8
     plan = tsb.Plan(env["ctx"], n, precision=precision, program="gain", gain=gain)
     out = plan.render(torch.from_numpy(np.ascontiguousarray(x.T)).cuda(), F, n // 4)
     torch.cuda.synchronize()

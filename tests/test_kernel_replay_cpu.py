@@ -1,0 +1,82 @@
+"""CPU replay of the CUDA chain kernel's per-thread phases (tests/emul, compiled from the same headers as
+the kernel) against the oracle: checks the kernel's arithmetic and indexing without a GPU.  The replay is
+test infrastructure, not a fallback — nothing in the product loads it."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import orc
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul"))
+import emul  # noqa: E402
+
+
+def maxrel(a, b):
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+def rmsrel(a, b):
+    return float(np.sqrt(np.mean((a - b) ** 2) / np.mean(b ** 2)))
+
+
+@pytest.mark.parametrize("lg", range(3, 13))
+def test_stockham_fft(lg):
+    import ctypes as C
+    m = 1 << lg
+    rng = np.random.default_rng(lg)
+    x = rng.standard_normal(m) + 1j * rng.standard_normal(m)
+    want = np.fft.fft(x)
+    for prec, tol in ((1, 1e-15), (0, 4e-7)):
+        y = np.empty(m, np.complex128)
+        assert emul.lib().emul_fft(prec, lg, x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p)) == 0
+        assert maxrel(y, want) < tol
+
+
+@pytest.mark.parametrize("n,hr,shift,ch,samples,stream", [
+    (1024, 0.25, 2.0, 2, 14000, 0), (256, 0.25, 1.5, 2, 8000, 0), (64, 0.25, 0.5, 1, 5000, 5),
+    (4096, 0.25, 1.5, 1, 24000, 0), (8192, 0.25, 1.5, 1, 36000, 2), (512, 0.5, 1.2, 1, 9000, 0)])
+def test_pv_chain(n, hr, shift, ch, samples, stream):
+    x = orc.gen_signal(stream, ch, samples)
+    ref = orc.render_pv(x, n, hr, shift)
+    F, hop = ref["frames"], int(n * hr)
+    want = ref["ola64"][:F * hop].T
+    out, st = emul.chain_render(x.T, n, hop, F, precision="f64", ratio=shift)
+    assert maxrel(out, want) < 1e-11
+    dps = np.abs(st["phase_sum"] - ref["phase_sum"][:, :n // 2])
+    assert dps.max() < 1e-8          # same wrap side in every bin of every frame
+    out32, st32 = emul.chain_render(x.T, n, hop, F, precision="f32", ratio=shift)
+    assert rmsrel(out32, want) < 1e-5
+    assert (np.abs(st32["phase_sum"] - ref["phase_sum"][:, :n // 2]) > 1).sum() == 0
+
+
+def test_pv_chain_fractional_hop_and_segments():
+    x = orc.gen_signal(3, 1, 12000)
+    n, hop_d, shift = 512, 512 * 0.2003, 0.75
+    ref = orc.render_pv(x, n, 0.2003, shift, want_tables=True)
+    tabs, F = ref["tables"], ref["frames"]
+    out, _ = emul.chain_render(x.T, n, 0, F, precision="f64", ratio=shift, hop_d=hop_d, hop_tab=tabs["hop"])
+    assert maxrel(out, ref["ola64"][:out.shape[1]].T) < 1e-11
+    # the same render as two launches handing the state over: bit-identical
+    a = F // 3
+    o2 = np.zeros_like(out)
+    o1, st = emul.chain_render(x.T, n, 0, a, precision="f64", ratio=shift, hop_d=hop_d, hop_tab=tabs["hop"][:a],
+                               out_len=out.shape[1])
+    o2, st = emul.chain_render(x.T, n, 0, F - a, precision="f64", ratio=shift, hop_d=hop_d, hop_tab=tabs["hop"][a:],
+                               in_off0=int(tabs["in_off"][a]), out_off0=int(tabs["out_off"][a]), state=st,
+                               out_len=out.shape[1])
+    p = int(tabs["out_off"][a])
+    assert np.array_equal(np.concatenate([o1[:, :p], o2[:, p:]], axis=1), out)
+
+
+@pytest.mark.parametrize("n,filt", [(2048, True), (64, True), (512, False)])
+def test_gain_chain(n, filt):
+    x = orc.gen_signal(0, 2, 2048 + 10 * n)
+    gain = 1.0 / (1.0 + np.arange(n // 2 + 1) / 64.0) if filt else None
+    ref = orc.render_filter(x, n, 0.25, gain)
+    F = ref["frames"]
+    out, _ = emul.chain_render(x.T, n, n // 4, F, precision="f64", program="gain", gain=gain)
+    assert maxrel(out, ref["ola64"][:out.shape[1]].T) < 1e-13
+    out, _ = emul.chain_render(x.T, n, n // 4, F, precision="f32", program="gain", gain=gain)
+    assert rmsrel(out, ref["ola64"][:out.shape[1]].T) < 1e-5

@@ -51,7 +51,7 @@ def _load():
     L = C.CDLL(path)
     P = C.c_void_p
     L.tsb_last_error.restype = C.c_char_p
-    L.tsb_ctx_create.argtypes = [C.c_int, P, C.POINTER(P)]
+    L.tsb_ctx_create.argtypes = [C.c_int, P, C.c_int, C.POINTER(P)]
     L.tsb_ctx_destroy.argtypes = [P]
     L.tsb_ctx_sync.argtypes = [P]
     L.tsb_launch_count.argtypes = [P]
@@ -109,18 +109,21 @@ def shift_map(n, rate, fn_bins):
 
 
 class Context:
-    """One device + one CUDA stream (defaults to torch's current stream on that device)."""
+    """One device + one CUDA stream: stream="torch" (default) runs on torch's current stream of that device,
+    stream="new" on a stream the context creates and owns, an int is taken as a cudaStream_t."""
 
     def __init__(self, device=0, stream="torch"):
         L = _load()
-        sp = None
+        sp, new = None, 0
         if stream == "torch":
             import torch
             sp = torch.cuda.current_stream(device).cuda_stream if torch.cuda.is_available() else None
+        elif stream == "new":
+            new = 1
         elif stream is not None:
             sp = int(stream)
         h = C.c_void_p()
-        _check(L.tsb_ctx_create(device, sp, C.byref(h)))
+        _check(L.tsb_ctx_create(device, sp, new, C.byref(h)))
         self.h = h
         self.device = device
 

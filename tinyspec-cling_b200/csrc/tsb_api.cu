@@ -50,7 +50,7 @@ struct tsb_plan {
 TSB_API int tsb_abi_version(void) { return TSB_ABI_VERSION; }
 TSB_API const char *tsb_last_error(void) { return g_err.c_str(); }
 
-TSB_API int tsb_ctx_create(int device, void *cuda_stream, tsb_ctx **out) {
+TSB_API int tsb_ctx_create(int device, void *cuda_stream, int new_stream, tsb_ctx **out) {
     if (!out) return fail(TSB_EINVAL, "tsb_ctx_create: null out pointer");
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -65,7 +65,7 @@ TSB_API int tsb_ctx_create(int device, void *cuda_stream, tsb_ctx **out) {
         return fail(TSB_EUNSUPPORTED, "device %d is sm_%d%d; libtsb200 is built for sm_100a only", device, prop.major,
                     prop.minor);
     tsb_ctx *c = new tsb_ctx{device, nullptr, false, 0};
-    if (cuda_stream) {
+    if (!new_stream) {
         c->stream = (cudaStream_t)cuda_stream;
     } else {
         cudaError_t e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);

@@ -17,7 +17,7 @@
 //     ola[N]   real    overlap-add accumulator, slot = absolute output position mod N
 //     bufA[M], bufB[M] complex<real>, ping-pong FFT buffers (M = N/2); the idle one doubles as the
 //                      phase-increment exchange array of the PV stage
-//     amp[M]   real    PV amplitude exchange array (PV program only)
+//     amp[M]   real    PV amplitude exchange array (fp32 PV only; fp64 keeps it in the idle buffer)
 //
 // Real-FFT mapping: the reference runs complex FFTs of real data.  Here the N
 // real samples are packed into M = N/2 complex points, transformed once, and split; with
@@ -215,7 +215,9 @@ struct Chain {
         real ola[N];
         C bufA[M];
         C bufB[M];
-        real amp[PROG == PROG_PV_SHIFT ? M : 1];
+        // PV amplitude exchange array: fp32 needs its own (the spare FFT buffer is filled by the M fp64
+        // increments); in fp64 the spare buffer (16*M bytes) holds both, so nothing extra is reserved.
+        real amp_own[(PROG == PROG_PV_SHIFT && sizeof(real) == 4) ? M : 1];
     };
     // Per-thread state that lives in registers for the whole launch.
     struct Regs {
@@ -226,6 +228,11 @@ struct Chain {
     // where the forward transform of data that started in bufA ends up
     static TSB_HD C *fwd_result(Smem &sm) { return (PASSES & 1) ? sm.bufB : sm.bufA; }
     static TSB_HD C *fwd_spare(Smem &sm) { return (PASSES & 1) ? sm.bufA : sm.bufB; }
+    // PV exchange arrays (between the analysis and the synthesis phase)
+    static TSB_HD double *xch_inc(Smem &sm) { return reinterpret_cast<double *>(fwd_spare(sm)); }
+    static TSB_HD real *xch_amp(Smem &sm) {
+        return sizeof(real) == 4 ? sm.amp_own : reinterpret_cast<real *>(xch_inc(sm) + M);
+    }
 
     // ------------------------------------------------------------------ state in / out
     static TSB_HD void load_state(int tid, int lane, Smem &sm, Regs &rg, const ChainArgs &a) {
@@ -355,7 +362,8 @@ struct Chain {
     // (rtlib/pv.hpp:17-28 over the live bins 0..N/2-1; results go to the exchange arrays)
     static TSB_HD void phase_pv_analyze(int tid, Smem &sm, Regs &rg, const Tables &tb) {
         const C *Zc = fwd_result(sm);
-        double *inc_x = reinterpret_cast<double *>(fwd_spare(sm));
+        double *inc_x = xch_inc(sm);
+        real *amp_x = xch_amp(sm);
 #pragma unroll
         for (int i = 0; i < S; i++) {
             int k = tid + T * i;
@@ -366,23 +374,23 @@ struct Chain {
             real amp;
             double inc;
             PvMath<real>::analyze(k, Xa, rg.last_phase[2 * i], tb, N, amp, inc);
-            sm.amp[k] = amp;
+            amp_x[k] = amp;
             inc_x[k] = inc;
             PvMath<real>::analyze(kb, Xb, rg.last_phase[2 * i + 1], tb, N, amp, inc);
-            sm.amp[kb] = amp;
+            amp_x[kb] = amp;
             inc_x[kb] = inc;
         }
     }
     // shift gather for destination bin k (rtlib/pv.hpp:70-78: amplitudes add in ascending source
     // order, the frequency of the last source wins; bins with no source are silent with freq 0)
-    static TSB_HD void gather_bin(const Smem &sm, const double *inc_x, const Tables &tb, int k, real &amp, double &inc) {
+    static TSB_HD void gather_bin(const real *amp_x, const double *inc_x, const Tables &tb, int k, real &amp, double &inc) {
         uint32_t e = TSB_LDG(&tb.map[k]);
         int first = (int)(e >> 16), cnt = (int)(e & 0xffff);
         amp = 0;
         inc = 0;
         for (int s = 0; s < cnt; s++) {
             int j = TSB_LDG(&tb.map_src[first + s]);
-            amp = amp + sm.amp[j];
+            amp = amp + amp_x[j];
             inc = inc_x[j];
         }
     }
@@ -390,7 +398,8 @@ struct Chain {
     // (rtlib/pv.hpp:29-38 on the shifted bins, then Z = conj(Y) [1/2 folded into win_s])
     static TSB_HD void phase_pv_synth(int tid, Smem &sm, Regs &rg, const Tables &tb) {
         C *H = fwd_result(sm);  // the packed spectrum has been consumed; reuse its buffer
-        const double *inc_x = reinterpret_cast<const double *>(fwd_spare(sm));
+        const double *inc_x = xch_inc(sm);
+        const real *amp_x = xch_amp(sm);
 #pragma unroll
         for (int i = 0; i < S; i++) {
             int k = tid + T * i;
@@ -398,9 +407,9 @@ struct Chain {
             int kb = k == 0 ? HALF : M - k;
             real amp;
             double inc;
-            gather_bin(sm, inc_x, tb, k, amp, inc);
+            gather_bin(amp_x, inc_x, tb, k, amp, inc);
             C Ya = PvMath<real>::synth(amp, inc, rg.phase_sum[2 * i]);
-            gather_bin(sm, inc_x, tb, kb, amp, inc);
+            gather_bin(amp_x, inc_x, tb, kb, amp, inc);
             C Yb = PvMath<real>::synth(amp, inc, rg.phase_sum[2 * i + 1]);
             if (k != 0) {
                 merge_pair(H, tb, k, conj(Ya), conj(Yb));
