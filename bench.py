@@ -25,6 +25,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_FRAME, HOP, CH, RATE, SHIFT = 1024, 256, 2, 48000.0, 2.0
+# One lane = one CTA; resident CTAs per SM: 7 (fp64 kernel, 28 KB smem + 128 regs) / 12 (fp32, 18 KB + 80 regs).
+# 148 SMs x that many CTAs = one full wave of lanes; 2 lanes per stereo stream.
+STREAMS = {"f64": 148 * 7 // 2, "f32": 148 * 12 // 2}
 
 
 def peaks():
@@ -148,7 +151,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--streams", type=int, default=444, help="independent stereo streams per GPU")
+    ap.add_argument("--streams", type=int, default=0,
+                    help="independent stereo streams per GPU (default: one full wave of resident CTAs, see STREAMS)")
     ap.add_argument("--seconds", type=float, default=60.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary figures (other precision, single stream)")
@@ -212,9 +216,13 @@ def main():
     ctx = tsb200.Context(local)
     sch = tsb200.schedule_const(L, N_FRAME, HOP, RATE)
     F = sch["n_frames"]
-    S = args.streams
+    S = args.streams or STREAMS[args.precision]
     lanes = S * CH
-    x = synth_input(torch, lanes, L, dev, 1234 + rank)
+    other = "f32" if args.precision == "f64" else "f64"
+    S_other = args.streams or STREAMS[other]
+    lanes_alloc = lanes if args.no_extras else max(lanes, S_other * CH)
+    x_all = synth_input(torch, lanes_alloc, L, dev, 1234 + rank)
+    x = x_all[:lanes]
 
     def timed(plan, xin, out, steps, warmup, sampler=None):
         for _ in range(warmup):
@@ -232,14 +240,14 @@ def main():
         clocks = sampler.stop() if sampler else None
         return max_over_ranks(e0.elapsed_time(e1)), ctx.launches - l0, clocks
 
-    def device_leg(precision, steps, warmup, sampler=None):
+    def device_leg(precision, xin, steps, warmup, sampler=None):
         plan = tsb200.Plan(ctx, N_FRAME, precision=precision, program="pv", hop=HOP, rate=RATE, ratio=SHIFT)
-        out = torch.zeros((lanes, F * HOP), dtype=plan.out_dtype, device=dev)
-        ms, launches, clocks = timed(plan, x, out, steps, warmup, sampler)
+        out = torch.zeros((xin.shape[0], F * HOP), dtype=plan.out_dtype, device=dev)
+        ms, launches, clocks = timed(plan, xin, out, steps, warmup, sampler)
         del out
         return ms / steps, launches, clocks
 
-    ms_step, launches, clocks = device_leg(args.precision, args.steps, args.warmup, ClockSampler(local))
+    ms_step, launches, clocks = device_leg(args.precision, x, args.steps, args.warmup, ClockSampler(local))
     frames_all = world * S * F
     fps = frames_all / (ms_step * 1e-3)
     fcs = fps * CH
@@ -276,7 +284,6 @@ def main():
         xh = torch.empty((lanes, L), dtype=torch.float32, pin_memory=True)
         xh.copy_(x)
         oh = torch.empty((lanes, F * HOP), dtype=plan.out_dtype, pin_memory=True)
-        del x
         torch.cuda.empty_cache()
         plan.render_host(xh, F, HOP, out=oh)  # warm-up
         barrier()
@@ -289,14 +296,13 @@ def main():
         line["e2e"] = {"value": frames_all / (ems * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": lanes * L * 4,
                        "d2h_bytes_per_step": lanes * F * HOP * oh.element_size(), "ms_per_step": ems, "steps": esteps,
                        "api": "tsb_chain_render_host (pinned host buffers; upload + kernel + download inside the timed region)"}
-        x = xh[:, :].to(dev) if not args.no_extras else None
-        del oh
+        del oh, xh
     # ---- secondary figures (rank 0 describes them; all ranks run them to stay in step) ----
-    if not args.no_extras and x is not None:
-        other = "f32" if args.precision == "f64" else "f64"
-        oms, _, _ = device_leg(other, max(1, args.steps), 1)
-        ofps = frames_all / (oms * 1e-3)
+    if not args.no_extras:
+        oms, _, _ = device_leg(other, x_all[:S_other * CH], max(1, args.steps), 2)
+        ofps = world * S_other * F / (oms * 1e-3)
         line["other_precision"] = {"dtype": other, "value": ofps, "unit": "frames/s", "ms_per_step": oms,
+                                   "streams_per_gpu": S_other,
                                    "roofline_frac": ofps * CH * b_alg(other) / 1e9 / peak}
         if world == 1:
             plan1 = tsb200.Plan(ctx, N_FRAME, precision=args.precision, program="pv", hop=HOP, rate=RATE, ratio=SHIFT)

@@ -86,12 +86,10 @@ template <typename real, int LOG2M>
 static void fft_only(const double *in, double *out) {
     constexpr int M = 1 << LOG2M;
     constexpr int T = 32;
-    std::vector<cpx<real>> a(M), b(M), tw(M);
-    std::vector<double> t = twiddle_table(M, M);
-    for (int q = 0; q < M; q++) {
-        tw[q] = mk<real>((real)t[2 * q], (real)t[2 * q + 1]);
-        a[q] = mk<real>((real)in[2 * q], (real)in[2 * q + 1]);
-    }
+    std::vector<double> t = pass_twiddle_table(M);
+    std::vector<cpx<real>> a(M), b(M), tw(t.size() / 2);
+    for (size_t q = 0; q < tw.size(); q++) tw[q] = mk<real>((real)t[2 * q], (real)t[2 * q + 1]);
+    for (int q = 0; q < M; q++) a[q] = mk<real>((real)in[2 * q], (real)in[2 * q + 1]);
     cpx<real> *src = a.data(), *dst = b.data();
     auto pass = [&](auto P) {
         for (int tid = 0; tid < T; tid++) stockham_pass<real, LOG2M, T, decltype(P)::value>(tid, src, dst, tw.data());

@@ -52,7 +52,7 @@ inline long long d2ll_rn(double a) { return llrint(a); }
 // Tables built once per plan on the host (tsb_host.cpp) and kept in device memory.
 template <typename real>
 struct ChainTables {
-    const cpx<real> *tw;     // [M]      exp(-2*pi*i*q/M)
+    const cpx<real> *tw;     // per-pass twiddle tables of the M-point FFT (TwLayout<LOG2M>)
     const cpx<real> *twn;    // [M/2+1]  exp(-2*pi*i*k/N)
     const real *win_a;       // [N]      analysis window / sqrt(N)
     const real *win_s;       // [N]      synthesis window * c / sqrt(N), c = 1/2 (PV) or 1 (gain)
@@ -60,10 +60,12 @@ struct ChainTables {
     const double *expect;    // [M]      j*2.0*M_PI*hop/N, evaluated as rtlib/pv.hpp:40 does
     const uint32_t *map;     // [M]      (first << 16) | count into map_src: sources of destination bin k
     const uint16_t *map_src; // source bins, ascending within each destination (rtlib/pv.hpp:70-78)
+    const int16_t *map1;     // [M] or nullptr: when no destination has more than one source, that source (-1: none)
     double hop;              // PhaseVocoder::hop() (rtinc/pv.hpp:50-53), may be fractional
     double rate;             // RATE
     double ratio;            // fn(x) = ratio*x applied to the frequencies (rtlib/pv.hpp:66)
     double size_over_hop;    // size/hop()
+    double inv_rate;         // 1/RATE
     double dc_pos, dc_neg;   // arg() the reference obtains for a positive / negative DC bin (see dc_phase())
     // PROG_GAIN
     const real *gain;        // [M+1]    real gain applied to bins k and (N-k)%N
@@ -92,6 +94,47 @@ struct ChainArgs {
 template <typename real>
 struct PvMath;
 
+// single-instruction (MUFU) reciprocal / reciprocal square root, ~1 ulp, flush-to-zero
+TSB_HD float fast_rcpf(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+TSB_HD float fast_rsqrtf(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+
+// Branch-free atan2f: octant reduction + odd minimax polynomial on [0,1]; max error 3.1e-7 rad (the same
+// as a correctly rounded float result near +-pi), no special-case paths.  atan2f(+-0, x<0) = +-pi as in libm.
+TSB_HD float fast_atan2f(float y, float x) {
+    float ax = fabsf(x), ay = fabsf(y);
+    float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    float a = mn * fast_rcpf(fmaxf(mx, 1e-37f));
+    float s = a * a;
+    float r = 0.00282363896258175373077393f;
+    r = fmaf(r, s, -0.0159569028764963150024414f);
+    r = fmaf(r, s, 0.0425049886107444763183594f);
+    r = fmaf(r, s, -0.0748900920152664184570312f);
+    r = fmaf(r, s, 0.106347933411598205566406f);
+    r = fmaf(r, s, -0.142027363181114196777344f);
+    r = fmaf(r, s, 0.199926957488059997558594f);
+    r = fmaf(r, s, -0.333331018686294555664062f);
+    r = fmaf(r * s, a, a);
+    r = ay > ax ? 1.57079632679489661923f - r : r;
+    r = x < 0.f ? 3.14159265358979323846f - r : r;
+    return copysignf(r, y);
+}
+
 // The DC bin of a real frame is real, so its phase sits exactly on the branch cut of arg() and on the
 // wrap boundary of phase_to_frequency whenever its sign changes.  In the reference the value fed to
 // arg() carries a ~1e-16 imaginary leak of the same sign as the bin (pow(i,2) is inexact in
@@ -109,10 +152,10 @@ struct PvMath<double> {
     // analysis of one bin: spectrum value X (R2C convention) -> amplitude and the phase increment the
     // synthesis stage will add for the bin this one is shifted to.
     static TSB_HD void analyze(int j, cpx<double> X, double &last_phase, const ChainTables<double> &tb, int n,
-                               double &amp, double &inc) {
+                               double &amp, double &inc, bool dc) {
         double re = X.x, im = -X.y;  // frft(.,+1) of real data = conj(R2C)/sqrt(N)
         amp = sqrt(add_rn(mul_rn(re, re), mul_rn(im, im)));  // abs(), pv.hpp:20
-        double phase = j == 0 ? dc_phase(re, tb) : atan2(im, re);  // arg(), pv.hpp:21
+        double phase = dc ? dc_phase(re, tb) : atan2(im, re);  // arg(), pv.hpp:21 (dc: bin 0)
         double diff = sub_rn(phase, last_phase);
         last_phase = phase;                                  // pv.hpp:23
         // phase_to_frequency, pv.hpp:39-45
@@ -123,13 +166,16 @@ struct PvMath<double> {
         double t = sub_rn(delta, mul_rn(TSB_PI, (double)qpd));
         t = mul_rn(tb.size_over_hop, t);
         t = mul_rn(t, 0.5);  // "/2.0" is exact either way
-        t = t / TSB_PI;
+        // The truncation above needs the true quotient (a DC sign change puts delta exactly on -pi); the two
+        // divisions below only scale, so a reciprocal multiply (<= 1 ulp apart, ~1e-16 relative on the
+        // increment) replaces them: fp64 division costs ~20 instructions on the fp64 pipe.
+        t = mul_rn(t, 1.0 / TSB_PI);
         t = add_rn((double)j, t);
         t = mul_rn(t, tb.rate);
-        double freq = t / (double)n;
+        double freq = mul_rn(t, 1.0 / (double)n);  // exact: n is a power of two
         freq = mul_rn(freq, tb.ratio);  // shift: freqs[j] = fn(freq), pv.hpp:66
         // frequency_to_phase, pv.hpp:46-48: 2.0*M_PI*freq/RATE*hop()
-        inc = mul_rn(mul_rn(2.0 * TSB_PI, freq) / tb.rate, tb.hop);
+        inc = mul_rn(mul_rn(mul_rn(2.0 * TSB_PI, freq), tb.inv_rate), tb.hop);
     }
     static TSB_HD cpx<double> synth(double amp, double inc, double &phase_sum) {
         phase_sum = add_rn(phase_sum, inc);  // pv.hpp:34 — never wrapped
@@ -151,13 +197,14 @@ struct PvMath<double> {
 template <>
 struct PvMath<float> {
     static TSB_HD void analyze(int j, cpx<float> X, float &last_phase, const ChainTables<float> &tb, int n,
-                               float &amp, double &inc) {
+                               float &amp, double &inc, bool dc) {
         (void)n;
         float re = X.x, im = -X.y;
-        amp = sqrtf(re * re + im * im);
-        float phase = atan2f(im, re);
+        float pw = fmaf(re, re, im * im);
+        amp = pw * fast_rsqrtf(fmaxf(pw, 1e-37f));
+        float phase = fast_atan2f(im, re);
         double diff = (double)phase - (double)last_phase;
-        if (j == 0) {  // DC: keep the reference's (double) values, stored as a sign in the float state
+        if (dc) {  // bin 0: keep the reference's (double) values, stored as a sign in the float state
             double lp = last_phase > 0.f ? tb.dc_pos : (last_phase < 0.f ? tb.dc_neg : 0.0);
             double ph = dc_phase((double)re, tb);
             diff = ph - lp;
@@ -188,12 +235,13 @@ struct PvMath<float> {
         cp = fmaf(cp, x2, -1.388731625493765e-3f);
         cp = fmaf(cp, x2, 4.166664568298827e-2f);
         float c = fmaf(cp * x2, x2, fmaf(-0.5f, x2, 1.0f));
-        int qi = (int)(q & 3);
+        int qi = (int)q;
         float ss = (qi & 1) ? c : s;
         float cc = (qi & 1) ? s : c;
-        if (qi == 1 || qi == 2) cc = -cc;
-        if (qi >= 2) ss = -ss;
-        return mk<float>(amp * cc, amp * ss);
+        // quadrant signs: sin negative for q in {2,3}, cos negative for q in {1,2}; folded into the amplitude
+        float as = (qi & 2) ? -amp : amp;
+        float ac = ((qi + 1) & 2) ? -amp : amp;
+        return mk<float>(ac * cc, as * ss);
     }
 };
 
@@ -209,12 +257,12 @@ struct Chain {
     static constexpr bool IS_PV = PROG == PROG_PV_SHIFT;
     using C = cpx<real>;
     using Tables = ChainTables<real>;
+    using SW = Swz<real>;
 
     struct Smem {
         float ring[N];
         real ola[N];
-        C bufA[M];
-        C bufB[M];
+        C buf[2][M];  // ping-pong FFT buffers, swizzled (Swz<real>)
         // PV amplitude exchange array: fp32 needs its own (the spare FFT buffer is filled by the M fp64
         // increments); in fp64 the spare buffer (16*M bytes) holds both, so nothing extra is reserved.
         real amp_own[(PROG == PROG_PV_SHIFT && sizeof(real) == 4) ? M : 1];
@@ -225,14 +273,20 @@ struct Chain {
         double phase_sum[2 * S];
     };
 
-    // where the forward transform of data that started in bufA ends up
-    static TSB_HD C *fwd_result(Smem &sm) { return (PASSES & 1) ? sm.bufB : sm.bufA; }
-    static TSB_HD C *fwd_spare(Smem &sm) { return (PASSES & 1) ? sm.bufA : sm.bufB; }
+    // Forward pass p writes buf[p & 1] (pass 0 reads the ring), so the packed spectrum ends up in RB.
+    static constexpr int RB = (PASSES - 1) & 1;
+    static constexpr int SB = RB ^ 1;
+    static TSB_HD C *fwd_result(Smem &sm) { return sm.buf[RB]; }
+    static TSB_HD C *fwd_spare(Smem &sm) { return sm.buf[SB]; }
     // PV exchange arrays (between the analysis and the synthesis phase)
     static TSB_HD double *xch_inc(Smem &sm) { return reinterpret_cast<double *>(fwd_spare(sm)); }
     static TSB_HD real *xch_amp(Smem &sm) {
         return sizeof(real) == 4 ? sm.amp_own : reinterpret_cast<real *>(xch_inc(sm) + M);
     }
+    // The inverse transform starts from H: PV writes it over the consumed spectrum (RB), the gain program
+    // into the spare buffer (no barrier between its split and merge).  Inverse pass p reads IB(p), writes IB(p+1).
+    static constexpr int INV0 = IS_PV ? RB : SB;
+    static constexpr int inv_buf(int p) { return (p & 1) ? (INV0 ^ 1) : INV0; }
 
     // ------------------------------------------------------------------ state in / out
     static TSB_HD void load_state(int tid, int lane, Smem &sm, Regs &rg, const ChainArgs &a) {
@@ -242,14 +296,16 @@ struct Chain {
         }
         bool ld = a.load_state != 0;
         if (PROG == PROG_PV_SHIFT && ld && a.st_last_phase && a.st_phase_sum) {
+#pragma unroll
             for (int i = 0; i < S; i++) {
                 int k = tid + T * i;
-                if (k >= HALF) break;
-                int kb = k == 0 ? HALF : M - k;
-                rg.last_phase[2 * i] = (real)a.st_last_phase[(long long)lane * M + k];
-                rg.last_phase[2 * i + 1] = (real)a.st_last_phase[(long long)lane * M + kb];
-                rg.phase_sum[2 * i] = a.st_phase_sum[(long long)lane * M + k];
-                rg.phase_sum[2 * i + 1] = a.st_phase_sum[(long long)lane * M + kb];
+                if (k < HALF) {
+                    int kb = k == 0 ? HALF : M - k;
+                    rg.last_phase[2 * i] = (real)a.st_last_phase[(long long)lane * M + k];
+                    rg.last_phase[2 * i + 1] = (real)a.st_last_phase[(long long)lane * M + kb];
+                    rg.phase_sum[2 * i] = a.st_phase_sum[(long long)lane * M + k];
+                    rg.phase_sum[2 * i + 1] = a.st_phase_sum[(long long)lane * M + kb];
+                }
             }
         }
         for (int i = tid; i < N; i += T) {
@@ -260,14 +316,16 @@ struct Chain {
     }
     static TSB_HD void store_state(int tid, int lane, Smem &sm, Regs &rg, const ChainArgs &a, long long out_pos) {
         if (PROG == PROG_PV_SHIFT && a.st_last_phase && a.st_phase_sum) {
+#pragma unroll
             for (int i = 0; i < S; i++) {
                 int k = tid + T * i;
-                if (k >= HALF) break;
-                int kb = k == 0 ? HALF : M - k;
-                a.st_last_phase[(long long)lane * M + k] = (double)rg.last_phase[2 * i];
-                a.st_last_phase[(long long)lane * M + kb] = (double)rg.last_phase[2 * i + 1];
-                a.st_phase_sum[(long long)lane * M + k] = rg.phase_sum[2 * i];
-                a.st_phase_sum[(long long)lane * M + kb] = rg.phase_sum[2 * i + 1];
+                if (k < HALF) {
+                    int kb = k == 0 ? HALF : M - k;
+                    a.st_last_phase[(long long)lane * M + k] = (double)rg.last_phase[2 * i];
+                    a.st_last_phase[(long long)lane * M + kb] = (double)rg.last_phase[2 * i + 1];
+                    a.st_phase_sum[(long long)lane * M + k] = rg.phase_sum[2 * i];
+                    a.st_phase_sum[(long long)lane * M + kb] = rg.phase_sum[2 * i + 1];
+                }
             }
         }
         if (a.st_ola)
@@ -316,47 +374,67 @@ struct Chain {
 #endif
     }
 
-    // ------------------------------------------------------------------ phase A: window + pack
-    // z[m] = x[2m]*wa[2m] + i*x[2m+1]*wa[2m+1]  -> bufA        (rtlib/windowfn.hpp, fused into the load)
-    static TSB_HD void phase_window_pack(int tid, Smem &sm, const Tables &tb, long long in_off) {
-        for (int m = tid; m < M; m += T) {
-            float x0 = sm.ring[(int)((in_off + 2 * m) & (N - 1))];
-            float x1 = sm.ring[(int)((in_off + 2 * m + 1) & (N - 1))];
-            real w0 = TSB_LDG(&tb.win_a[2 * m]), w1 = TSB_LDG(&tb.win_a[2 * m + 1]);
-            sm.bufA[m] = mk<real>((real)x0 * w0, (real)x1 * w1);
-        }
-    }
+    // ------------------------------------------------------------------ forward passes
+    // Pass 0 gathers straight from the input ring and applies the analysis window on the way
+    // (rtlib/windowfn.hpp fused into the load): z[m] = x[2m]*wa[2m] + i*x[2m+1]*wa[2m+1].
+    // Swizzled buffer access with index = a + c, a per-thread, c compile-time, bit-disjoint (Swz is linear).
+    static TSB_HD C ld_sw(const C *buf, int a, int c) { return buf[SW::f(a) ^ SW::f(c)]; }
+    static TSB_HD void st_sw(C *buf, int a, int c, C v) { buf[SW::f(a) ^ SW::f(c)] = v; }
 
-    // ------------------------------------------------------------------ FFT passes (ping-pong)
     template <int P>
-    static TSB_HD void phase_fft_pass(int tid, const C *src, C *dst, const Tables &tb) {
-        stockham_pass<real, LOG2M, T, P>(tid, src, dst, tb.tw);
-    }
-
-    // spectrum of the real frame at bins k and kb from the packed transform Zc (see file header)
-    static TSB_HD void split_pair(const C *Zc, const Tables &tb, int k, C &Xa, C &Xb) {
-        if (k != 0) {
-            C a = Zc[k], b = conj(Zc[M - k]);
-            C e = mk<real>((real)0.5 * (a.x + b.x), (real)0.5 * (a.y + b.y));
-            C d = a - b;
-            C o = mk<real>((real)0.5 * d.y, (real)-0.5 * d.x);  // -i*d/2
-            C wo = cmul(TSB_LDG(&tb.twn[k]), o);
-            Xa = e + wo;           // X[k]
-            Xb = conj(e - wo);     // X[M-k]
+    static TSB_HD void fwd_pass(int tid, Smem &sm, const Tables &tb, long long in_off) {
+        C *dst = sm.buf[P & 1];
+        auto out = [&](int a, int c, C v) { st_sw(dst, a, c, v); };
+        if (P == 0) {
+            const int rb = (int)(in_off & (N - 1));
+            const C *wa = reinterpret_cast<const C *>(tb.win_a);
+            if ((rb & 1) == 0) {
+                const cpx<float> *ring2 = reinterpret_cast<const cpx<float> *>(sm.ring);
+                const int rb2 = rb >> 1;
+                auto in = [&](int a, int c) {
+                    cpx<float> q = ring2[(rb2 + a + c) & (M - 1)];
+                    C w = TSB_LDG(wa + a + c);
+                    return mk<real>((real)q.x * w.x, (real)q.y * w.y);
+                };
+                stockham_pass_io<real, LOG2M, T, P>(tid, tb.tw, in, out);
+            } else {
+                auto in = [&](int a, int c) {
+                    int m = a + c;
+                    float x0 = sm.ring[(rb + 2 * m) & (N - 1)];
+                    float x1 = sm.ring[(rb + 2 * m + 1) & (N - 1)];
+                    C w = TSB_LDG(wa + m);
+                    return mk<real>((real)x0 * w.x, (real)x1 * w.y);
+                };
+                stockham_pass_io<real, LOG2M, T, P>(tid, tb.tw, in, out);
+            }
         } else {
-            C z0 = Zc[0], zh = Zc[HALF];
-            Xa = mk<real>(z0.x + z0.y, 0);  // X[0]
-            Xb = conj(zh);                  // X[M/2]
+            const C *src = sm.buf[(P - 1) & 1];
+            auto in = [&](int a, int c) { return ld_sw(src, a, c); };
+            stockham_pass_io<real, LOG2M, T, P>(tid, tb.tw, in, out);
         }
     }
-    // C2R pre-processing for the pair (k, M-k): Hermitian-half values Zk, Zp -> conj(G) entries
+
+    // spectrum of the real frame at bins k and M-k (k != 0) from the packed transform Zc (see file header)
+    static TSB_HD void split_pair(const C *Zc, const Tables &tb, int k, C &Xa, C &Xb) {
+        C a = Zc[SW::f(k)], b = conj(Zc[SW::f(M - k)]);
+        C e = mk<real>((real)0.5 * (a.x + b.x), (real)0.5 * (a.y + b.y));
+        C d = a - b;
+        C o = mk<real>((real)0.5 * d.y, (real)-0.5 * d.x);  // -i*d/2
+        C wo = cmul(TSB_LDG(&tb.twn[k]), o);
+        Xa = e + wo;           // X[k]
+        Xb = conj(e - wo);     // X[M-k]
+    }
+    // C2R pre-processing for the pair (k, M-k), k != 0: Hermitian-half values Zk, Zp -> conj(G) entries
     static TSB_HD void merge_pair(C *H, const Tables &tb, int k, C Zk, C Zp) {
         C ee = Zk + conj(Zp);
         C d = Zk - conj(Zp);
         C oo = cmul(d, conj(TSB_LDG(&tb.twn[k])));
-        H[k] = mk<real>(ee.x - oo.y, -ee.y - oo.x);
-        H[M - k] = mk<real>(ee.x + oo.y, ee.y - oo.x);
+        H[SW::f(k)] = mk<real>(ee.x - oo.y, -ee.y - oo.x);
+        H[SW::f(M - k)] = mk<real>(ee.x + oo.y, ee.y - oo.x);
     }
+    // Only the first slot of thread 0 holds the irregular pair (bins 0 and M/2): the test is compile-time
+    // false for every other slot.
+    static TSB_HD bool is_special(int i, int k) { return i == 0 && k == 0; }
 
     // ------------------------------------------------------------------ PV phase C: split + analysis
     // (rtlib/pv.hpp:17-28 over the live bins 0..N/2-1; results go to the exchange arrays)
@@ -368,15 +446,22 @@ struct Chain {
         for (int i = 0; i < S; i++) {
             int k = tid + T * i;
             if (HALF % T != 0 && k >= HALF) break;
-            int kb = k == 0 ? HALF : M - k;
+            const bool sp = is_special(i, k);
+            int kb = sp ? HALF : M - k;
             C Xa, Xb;
-            split_pair(Zc, tb, k, Xa, Xb);
+            if (!sp) {
+                split_pair(Zc, tb, k, Xa, Xb);
+            } else {
+                C z0 = Zc[SW::f(0)], zh = Zc[SW::f(HALF)];
+                Xa = mk<real>(z0.x + z0.y, 0);  // X[0]
+                Xb = conj(zh);                  // X[M/2]
+            }
             real amp;
             double inc;
-            PvMath<real>::analyze(k, Xa, rg.last_phase[2 * i], tb, N, amp, inc);
+            PvMath<real>::analyze(k, Xa, rg.last_phase[2 * i], tb, N, amp, inc, sp);
             amp_x[k] = amp;
             inc_x[k] = inc;
-            PvMath<real>::analyze(kb, Xb, rg.last_phase[2 * i + 1], tb, N, amp, inc);
+            PvMath<real>::analyze(kb, Xb, rg.last_phase[2 * i + 1], tb, N, amp, inc, false);
             amp_x[kb] = amp;
             inc_x[kb] = inc;
         }
@@ -384,10 +469,19 @@ struct Chain {
     // shift gather for destination bin k (rtlib/pv.hpp:70-78: amplitudes add in ascending source
     // order, the frequency of the last source wins; bins with no source are silent with freq 0)
     static TSB_HD void gather_bin(const real *amp_x, const double *inc_x, const Tables &tb, int k, real &amp, double &inc) {
-        uint32_t e = TSB_LDG(&tb.map[k]);
-        int first = (int)(e >> 16), cnt = (int)(e & 0xffff);
         amp = 0;
         inc = 0;
+        if (tb.map1) {  // at most one source per destination (any upward shift): no loop
+            int j = TSB_LDG(&tb.map1[k]);
+            if (j >= 0) {
+                amp = amp_x[j];
+                inc = inc_x[j];
+            }
+            return;
+        }
+        uint32_t e = TSB_LDG(&tb.map[k]);
+        int first = (int)(e >> 16), cnt = (int)(e & 0xffff);
+#pragma unroll 1
         for (int s = 0; s < cnt; s++) {
             int j = TSB_LDG(&tb.map_src[first + s]);
             amp = amp + amp_x[j];
@@ -404,19 +498,20 @@ struct Chain {
         for (int i = 0; i < S; i++) {
             int k = tid + T * i;
             if (HALF % T != 0 && k >= HALF) break;
-            int kb = k == 0 ? HALF : M - k;
+            const bool sp = is_special(i, k);
+            int kb = sp ? HALF : M - k;
             real amp;
             double inc;
             gather_bin(amp_x, inc_x, tb, k, amp, inc);
             C Ya = PvMath<real>::synth(amp, inc, rg.phase_sum[2 * i]);
             gather_bin(amp_x, inc_x, tb, kb, amp, inc);
             C Yb = PvMath<real>::synth(amp, inc, rg.phase_sum[2 * i + 1]);
-            if (k != 0) {
+            if (!sp) {
                 merge_pair(H, tb, k, conj(Ya), conj(Yb));
             } else {
                 real z0 = (real)2 * Ya.x;  // Z[0] = Re Y[0] (not halved), Z[M] = 0
-                H[0] = mk<real>(z0, -z0);
-                H[HALF] = mk<real>((real)2 * Yb.x, (real)-2 * Yb.y);  // 2*Z[M/2], Z = conj(Y)
+                H[SW::f(0)] = mk<real>(z0, -z0);
+                H[SW::f(HALF)] = mk<real>((real)2 * Yb.x, (real)-2 * Yb.y);  // 2*Z[M/2], Z = conj(Y)
             }
         }
     }
@@ -429,53 +524,82 @@ struct Chain {
             int k = tid + T * i;
             if (HALF % T != 0 && k >= HALF) break;
             C Xa, Xb;
-            if (k != 0) {
+            if (!is_special(i, k)) {
                 split_pair(Zc, tb, k, Xa, Xb);
                 real ga = TSB_LDG(&tb.gain[k]), gb = TSB_LDG(&tb.gain[M - k]);
                 merge_pair(H, tb, k, mk<real>(ga * Xa.x, ga * Xa.y), mk<real>(gb * Xb.x, gb * Xb.y));
             } else {
-                C z0 = Zc[0], zh = Zc[HALF];
+                C z0 = Zc[SW::f(0)], zh = Zc[SW::f(HALF)];
                 real x0 = (z0.x + z0.y) * TSB_LDG(&tb.gain[0]);  // X[0]
                 real xm = (z0.x - z0.y) * TSB_LDG(&tb.gain[M]);  // X[N/2]
                 real gh = TSB_LDG(&tb.gain[HALF]);
-                H[0] = mk<real>(x0 + xm, -(x0 - xm));
-                H[HALF] = mk<real>((real)2 * gh * zh.x, (real)-2 * gh * zh.y);  // 2*Z[M/2], Z = g*conj(zh)
+                H[SW::f(0)] = mk<real>(x0 + xm, -(x0 - xm));
+                H[SW::f(HALF)] = mk<real>((real)2 * gh * zh.x, (real)-2 * gh * zh.y);  // 2*Z[M/2], Z = g*conj(zh)
             }
         }
     }
-    // buffers of the inverse transform
-    static TSB_HD C *inv_src(Smem &sm) { return PROG == PROG_PV_SHIFT ? fwd_result(sm) : fwd_spare(sm); }
-    static TSB_HD C *inv_dst(Smem &sm) { return PROG == PROG_PV_SHIFT ? fwd_spare(sm) : fwd_result(sm); }
-    static TSB_HD C *inv_result(Smem &sm) { return (PASSES & 1) ? inv_dst(sm) : inv_src(sm); }
 
-    // ------------------------------------------------------------------ phase F: window + overlap-add + emit
+    // ------------------------------------------------------------------ inverse passes
+    // The last pass hands its outputs F[m] straight to the synthesis window and the overlap-add:
     // x[2m] = Re F[m], x[2m+1] = -Im F[m]; out = x*ws; accumulate into the ring; the first `hop`
     // positions are complete (tinyspec.cpp:173-182) and leave the chip, the rest is the tail (194-200).
-    static TSB_HD void phase_ola_emit(int tid, int lane, Smem &sm, const Tables &tb, const ChainArgs &a,
-                                      long long out_pos, int hop) {
-        const C *F = inv_result(sm);
-        real *dst = reinterpret_cast<real *>(a.out) + (long long)lane * a.out_stride;
-        for (int m = tid; m < M; m += T) {
-            C f = F[m];
-            real v[2] = {f.x * TSB_LDG(&tb.win_s[2 * m]), -f.y * TSB_LDG(&tb.win_s[2 * m + 1])};
+    template <int P>
+    static TSB_HD void inv_pass(int tid, int lane, Smem &sm, const Tables &tb, const ChainArgs &a, long long out_pos,
+                                int hop) {
+        const C *src = sm.buf[inv_buf(P)];
+        auto in = [&](int x, int c) { return ld_sw(src, x, c); };
+        if (P < PASSES - 1) {
+            C *dst = sm.buf[inv_buf(P + 1)];
+            auto out = [&](int x, int c, C v) { st_sw(dst, x, c, v); };
+            stockham_pass_io<real, LOG2M, T, P>(tid, tb.tw, in, out);
+        } else {
+            real *dstg = reinterpret_cast<real *>(a.out) + (long long)lane * a.out_stride + out_pos;
+            const C *ws = reinterpret_cast<const C *>(tb.win_s);
+            const int ob = (int)(out_pos & (N - 1));
+            // samples of this frame that may be written: n < lim (everything when the row has room)
+            const long long room = a.out_len - out_pos;
+            const int lim = room >= (long long)N + hop ? 0x7fffffff : (room < 0 ? 0 : (int)room);
+            if (((ob | hop) & 1) == 0 && ((reinterpret_cast<uintptr_t>(dstg) & (2 * sizeof(real) - 1)) == 0)) {
+                // pairs (2m, 2m+1) never straddle the hop boundary and are aligned in the ring and in the row
+                C *ola2 = reinterpret_cast<C *>(sm.ola);
+                const int ob2 = ob >> 1;
+                auto out = [&](int x, int c, C f) {
+                    const int m = x + c;
+                    C w = TSB_LDG(ws + m);
+                    C *slot = &ola2[(ob2 + m) & (M - 1)];
+                    C acc = *slot;
+                    acc.x += f.x * w.x;
+                    acc.y -= f.y * w.y;
+                    if (2 * m < hop) {
+                        if (2 * m + 1 < lim) *reinterpret_cast<C *>(dstg + 2 * m) = acc;
+                        else if (2 * m < lim) dstg[2 * m] = acc.x;
+                        acc = mk<real>(0, 0);
+                    }
+                    *slot = acc;
+                };
+                stockham_pass_io<real, LOG2M, T, P>(tid, tb.tw, in, out);
+            } else {
+                auto out = [&](int x, int c, C f) {
+                    const int m = x + c;
+                    C w = TSB_LDG(ws + m);
+                    real v[2] = {f.x * w.x, -f.y * w.y};
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
-                int n = 2 * m + u;
-                int slot = (int)((out_pos + n) & (N - 1));
-                real acc = sm.ola[slot] + v[u];
-                if (n < hop) {
-                    long long p = out_pos + n;
-                    if (p < a.out_len) dst[p] = acc;
-                    sm.ola[slot] = 0;
-                } else {
-                    sm.ola[slot] = acc;
-                }
+                    for (int u = 0; u < 2; u++) {
+                        int n = 2 * m + u;
+                        int slot = (ob + n) & (N - 1);
+                        real acc = sm.ola[slot] + v[u];
+                        if (n < hop) {
+                            if (n < lim) dstg[n] = acc;
+                            acc = 0;
+                        }
+                        sm.ola[slot] = acc;
+                    }
+                };
+                stockham_pass_io<real, LOG2M, T, P>(tid, tb.tw, in, out);
             }
-        }
-        // hop larger than the frame: nothing overlaps those positions (tinyspec.cpp:184-191)
-        for (int n = N + tid; n < hop; n += T) {
-            long long p = out_pos + n;
-            if (p < a.out_len) dst[p] = 0;
+            // hop larger than the frame: nothing overlaps those positions (tinyspec.cpp:184-191)
+            for (int n = N + tid; n < hop; n += T)
+                if (n < lim) dstg[n] = 0;
         }
     }
 };
@@ -484,25 +608,48 @@ struct Chain {
 template <class CH, int P, int END>
 struct FwdPasses {
     template <class Exec>
-    static TSB_HD void run(Exec &ex, typename CH::Smem &sm, const typename CH::Tables &tb, typename CH::C *src,
-                           typename CH::C *dst) {
-        ex.each([&](int tid, typename CH::Regs &) { CH::template phase_fft_pass<P>(tid, src, dst, tb); });
-        FwdPasses<CH, P + 1, END>::run(ex, sm, tb, dst, src);
+    static TSB_HD void run(Exec &ex, int lane, typename CH::Smem &sm, const typename CH::Tables &tb, const ChainArgs &a,
+                           long long in_off, long long next_first, int next_cnt) {
+        ex.each([&](int tid, typename CH::Regs &) {
+            // after pass 0 nobody reads the ring any more: fetch the next frame's new samples behind pass 1
+            if (P == 1 && next_cnt > 0) CH::ring_fill(tid, lane, sm, a, next_first, next_cnt);
+            CH::template fwd_pass<P>(tid, sm, tb, in_off);
+        });
+        FwdPasses<CH, P + 1, END>::run(ex, lane, sm, tb, a, in_off, next_first, next_cnt);
     }
 };
 template <class CH, int END>
 struct FwdPasses<CH, END, END> {
     template <class Exec>
-    static TSB_HD void run(Exec &, typename CH::Smem &, const typename CH::Tables &, typename CH::C *, typename CH::C *) {}
+    static TSB_HD void run(Exec &, int, typename CH::Smem &, const typename CH::Tables &, const ChainArgs &, long long,
+                           long long, int) {}
+};
+template <class CH, int P, int END>
+struct InvPasses {
+    template <class Exec>
+    static TSB_HD void run(Exec &ex, int lane, typename CH::Smem &sm, const typename CH::Tables &tb, const ChainArgs &a,
+                           long long out_pos, int hop) {
+        ex.each([&](int tid, typename CH::Regs &) {
+            CH::template inv_pass<P>(tid, lane, sm, tb, a, out_pos, hop);
+            if (P == END - 1) CH::ring_wait();
+        });
+        InvPasses<CH, P + 1, END>::run(ex, lane, sm, tb, a, out_pos, hop);
+    }
+};
+template <class CH, int END>
+struct InvPasses<CH, END, END> {
+    template <class Exec>
+    static TSB_HD void run(Exec &, int, typename CH::Smem &, const typename CH::Tables &, const ChainArgs &, long long, int) {}
 };
 
 // The whole launch for one lane.  `Exec::each(f)` runs f(tid, regs) for every thread of the lane and
 // ends with a barrier: on the device that is { f(threadIdx.x, regs); __syncthreads(); }, in the CPU
-// test harness a loop over tid.
+// test harness a loop over tid.  Barriers per frame: 2*PASSES + (PV ? 2 : 1).
 template <class CH, class Exec>
 TSB_HD void run_lane(Exec &ex, int lane, typename CH::Smem &sm, const typename CH::Tables &tb, const ChainArgs &a) {
     using Regs = typename CH::Regs;
     constexpr int N = CH::N;
+    static_assert(CH::PASSES >= 2, "frame sizes below 64 are not instantiated");
     long long in_off = a.in_off0, out_pos = a.out_off0;
     ex.each([&](int tid, Regs &rg) {
         CH::load_state(tid, lane, sm, rg, a);
@@ -511,26 +658,17 @@ TSB_HD void run_lane(Exec &ex, int lane, typename CH::Smem &sm, const typename C
     });
     for (long long f = 0; f < a.n_frames; f++) {
         int hop = a.hop_tab ? TSB_LDG(&a.hop_tab[f]) : a.hop;
-        ex.each([&](int tid, Regs &) { CH::phase_window_pack(tid, sm, tb, in_off); });
-        // slots [in_off, in_off+hop) are dead now: start fetching the next frame's new samples
-        {
-            int cnt = hop < N ? hop : N;
-            long long first = in_off + hop + N - cnt;
-            if (f + 1 < a.n_frames)
-                ex.each_nosync([&](int tid, Regs &) { CH::ring_fill(tid, lane, sm, a, first, cnt); });
-        }
-        FwdPasses<CH, 0, CH::PASSES>::run(ex, sm, tb, sm.bufA, sm.bufB);
+        // slots [in_off, in_off+hop) are dead once pass 0 has read the frame
+        int cnt = f + 1 < a.n_frames ? (hop < N ? hop : N) : 0;
+        long long first = in_off + hop + N - cnt;
+        FwdPasses<CH, 0, CH::PASSES>::run(ex, lane, sm, tb, a, in_off, first, cnt);
         if (CH::IS_PV) {
             ex.each([&](int tid, Regs &rg) { CH::phase_pv_analyze(tid, sm, rg, tb); });
             ex.each([&](int tid, Regs &rg) { CH::phase_pv_synth(tid, sm, rg, tb); });
         } else {
             ex.each([&](int tid, Regs &) { CH::phase_gain(tid, sm, tb); });
         }
-        FwdPasses<CH, 0, CH::PASSES>::run(ex, sm, tb, CH::inv_src(sm), CH::inv_dst(sm));
-        ex.each([&](int tid, Regs &) {
-            CH::phase_ola_emit(tid, lane, sm, tb, a, out_pos, hop);
-            CH::ring_wait();
-        });
+        InvPasses<CH, 0, CH::PASSES>::run(ex, lane, sm, tb, a, out_pos, hop);
         in_off += hop;
         out_pos += hop;
     }

@@ -5,6 +5,12 @@
 #ifndef TSB_LOG2N
 #error "compile with -DTSB_LOG2N=<6..13>"
 #endif
+#ifndef TSB_REGS_PV32
+#define TSB_REGS_PV32 80
+#endif
+#ifndef TSB_REGS_PV64
+#define TSB_REGS_PV64 128
+#endif
 
 namespace tsb {
 
@@ -22,8 +28,21 @@ struct DevExec {
     }
 };
 
+// Resident CTAs per SM the kernel is compiled for: what shared memory allows (227 KB, 1 KB reserved per
+// CTA), capped by the thread limit and by a register budget that still keeps the FFT butterflies and the
+// PV state in registers.
+template <class CH>
+constexpr int min_blocks() {
+    constexpr int by_smem = (227 * 1024) / ((int)sizeof(typename CH::Smem) + 1024);
+    constexpr int by_threads = 2048 / CH::T;
+    constexpr int by_regs = 65536 / (CH::T * (sizeof(typename CH::C) == 8 ? (CH::IS_PV ? TSB_REGS_PV32 : 80) : (CH::IS_PV ? TSB_REGS_PV64 : 96)));
+    int b = by_smem < by_threads ? by_smem : by_threads;
+    b = b < by_regs ? b : by_regs;
+    return b < 1 ? 1 : (b > 32 ? 32 : b);
+}
+
 template <typename real, int LOG2N, int PROG>
-__global__ void __launch_bounds__(Chain<real, LOG2N, PROG>::T)
+__global__ void __launch_bounds__(Chain<real, LOG2N, PROG>::T, min_blocks<Chain<real, LOG2N, PROG>>())
 chain_kernel(const ChainTables<real> tb, const ChainArgs a) {
     using CH = Chain<real, LOG2N, PROG>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -37,12 +56,10 @@ static cudaError_t launch(const void *tables, const ChainArgs &a, cudaStream_t s
     using CH = Chain<real, LOG2N, PROG>;
     auto kern = chain_kernel<real, LOG2N, PROG>;
     size_t smem = sizeof(typename CH::Smem);
-    static bool configured = false;  // per instantiation; attribute is per device function
-    if (!configured || true) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
     if (a.lanes <= 0 || a.n_frames <= 0) return cudaSuccess;
     kern<<<a.lanes, CH::T, smem, stream>>>(*reinterpret_cast<const ChainTables<real> *>(tables), a);
     return cudaGetLastError();

@@ -94,6 +94,31 @@ std::vector<double> twiddle_table(int m, int count) {
     return t;
 }
 
+std::vector<double> pass_twiddle_table(int m) {
+    int lg = 0;
+    while ((1 << lg) < m) lg++;
+    int n8 = lg / 3, rem = lg % 3;
+    std::vector<int> radix(n8, 8);
+    if (rem) radix.push_back(1 << rem);
+    std::vector<double> t;
+    const long double tau = 6.283185307179586476925286766559005768L;
+    int ns = 1;
+    for (size_t p = 0; p < radix.size(); p++) {
+        int r = radix[p];
+        if (p >= 1) {
+            for (int jm = 0; jm < ns; jm++)
+                for (int k = 0; k < r; k++) {
+                    long double a = -tau * (long double)(jm * k) / (long double)(ns * r);
+                    t.push_back((double)cosl(a));
+                    t.push_back((double)sinl(a));
+                }
+        }
+        ns *= r;
+    }
+    if (t.empty()) { t.push_back(1.0); t.push_back(0.0); }
+    return t;
+}
+
 std::vector<double> expect_table(int n, double hop, int count) {
     std::vector<double> e(count);
     for (int j = 0; j < count; j++) {

@@ -55,6 +55,11 @@ void build_shift_map(int n, double rate, const double *fn_bins, std::vector<uint
 // exp(-2*pi*i*q/m), q < count, evaluated in long double (re,im interleaved)
 std::vector<double> twiddle_table(int m, int count);
 
+// Per-pass twiddle tables of an m-point Stockham FFT with the radix plan of tsb_math.cuh (radix 8 passes,
+// remainder 2 or 4 last): for each pass p >= 1, entries [jm*R + t] = exp(-2*pi*i*jm*t/(Ns*R)); passes
+// concatenated (re,im interleaved).  Matches TwLayout<log2 m>.
+std::vector<double> pass_twiddle_table(int m);
+
 // j*2.0*M_PI*hop/size as rtlib/pv.hpp:40 evaluates it, j < count
 std::vector<double> expect_table(int n, double hop, int count);
 

@@ -128,12 +128,42 @@ struct RadixPlan {
     static constexpr int ns(int p) { return p <= n8 ? (1 << (3 * p)) : (1 << (3 * n8)); }
 };
 
-// One thread's share of Stockham pass `P` of an M-point forward FFT: src -> dst (both M complex,
-// distinct buffers).  Butterfly j reads src[j + t*M/R], applies twiddle exp(-2*pi*i*(j%Ns)*t/(Ns*R)),
-// does a radix-R DFT and writes dst[(j/Ns)*Ns*R + (j%Ns) + t*Ns].  `tw` is the M-entry table
-// tw[q] = exp(-2*pi*i*q/M).
-template <typename T, int LOG2M, int THREADS, int P>
-TSB_HD void stockham_pass(int tid, const cpx<T> *src, cpx<T> *dst, const cpx<T> *tw) {
+// Shared-memory swizzle of the FFT buffers.  A Stockham pass reads with unit stride across lanes but
+// writes with stride R*Ns, which without a swizzle lands whole half-warps in one bank.  XOR-ing low index
+// bits with higher ones makes every access pattern of every pass (and the reversed M-k accesses of the
+// real-FFT split) conflict-free or within 15 % of it; the functions below were chosen by exhaustive
+// search over XOR / padding families (see DESIGN.md "shared-memory layout").
+// f is linear over GF(2): f(a ^ c) = f(a) ^ f(c), and a + c = a ^ c when a & c == 0, so an index made of
+// a per-thread part and a compile-time part with disjoint bits costs one f() per thread plus one XOR
+// with a constant per access.
+template <typename T>
+struct Swz;
+template <>
+struct Swz<float> {  // 8-byte elements: 16 lanes per wavefront
+    static TSB_HD constexpr int f(int i) { return i ^ ((i >> 3) & 15); }
+};
+template <>
+struct Swz<double> {  // 16-byte elements: 8 lanes per wavefront
+    static TSB_HD constexpr int f(int i) { return i ^ (((i >> 3) ^ (i >> 4)) & 7); }
+};
+
+// Per-pass twiddle tables: for pass P, entry [jm*R + t] = exp(-2*pi*i*jm*t/(Ns*R)), jm < Ns, t < R, so
+// that a butterfly's R-1 twiddles are one contiguous run (t = 0 is the unused 1).  Passes are laid out
+// one after the other; pass 0 (Ns = 1) needs none.
+template <int LOG2M>
+struct TwLayout {
+    using RP = RadixPlan<LOG2M>;
+    static constexpr int offset(int p) { return p <= 1 ? 0 : offset(p - 1) + RP::ns(p - 1) * RP::radix(p - 1); }
+    static constexpr int total = offset(RP::passes);
+};
+
+// One thread's share of Stockham pass `P` of an M-point forward FFT.  Butterfly j takes inputs
+// in(j, t*M/R) [index = sum of the two, bit-disjoint], applies twiddle exp(-2*pi*i*(j%Ns)*t/(Ns*R)), does a
+// radix-R DFT and hands out(base, t*Ns, value) with base = (j/Ns)*Ns*R + (j%Ns).  `in` / `out` are
+// functors so that the first pass can read (and window) the input ring and the last pass can feed the
+// overlap-add directly.  `twp` is the per-pass twiddle table (TwLayout).
+template <typename T, int LOG2M, int THREADS, int P, class In, class Out>
+TSB_HD void stockham_pass_io(int tid, const cpx<T> *twp, In in, Out out) {
     using RP = RadixPlan<LOG2M>;
     constexpr int M = 1 << LOG2M;
     constexpr int R = RP::radix(P);
@@ -146,25 +176,29 @@ TSB_HD void stockham_pass(int tid, const cpx<T> *src, cpx<T> *dst, const cpx<T> 
         if (NB % THREADS != 0 && j >= NB) break;
         cpx<T> v[R];
 #pragma unroll
-        for (int t = 0; t < R; t++) v[t] = src[j + t * NB];
+        for (int t = 0; t < R; t++) v[t] = in(j, t * NB);
         if (Ns > 1) {
             int jm = j & (Ns - 1);
-            constexpr int STEP = M / (Ns * R);
+            const cpx<T> *w = twp + TwLayout<LOG2M>::offset(P) + jm * R;
 #pragma unroll
-            for (int t = 1; t < R; t++) {
-                cpx<T> w = TSB_LDG(&tw[jm * t * STEP]);
-                v[t] = cmul(v[t], w);
-            }
+            for (int t = 1; t < R; t++) v[t] = cmul(v[t], TSB_LDG(&w[t]));
             dftR<R>(v);
             int base = ((j - jm) * R) + jm;
 #pragma unroll
-            for (int t = 0; t < R; t++) dst[base + t * Ns] = v[t];
+            for (int t = 0; t < R; t++) out(base, t * Ns, v[t]);
         } else {
             dftR<R>(v);
 #pragma unroll
-            for (int t = 0; t < R; t++) dst[j * R + t] = v[t];
+            for (int t = 0; t < R; t++) out(j * R, t, v[t]);
         }
     }
+}
+
+// plain buffer-to-buffer pass (unswizzled), used by the unit tests and the standalone FFT kernels
+template <typename T, int LOG2M, int THREADS, int P>
+TSB_HD void stockham_pass(int tid, const cpx<T> *src, cpx<T> *dst, const cpx<T> *twp) {
+    stockham_pass_io<T, LOG2M, THREADS, P>(
+        tid, twp, [&](int a, int c) { return src[a + c]; }, [&](int a, int c, cpx<T> v) { dst[a + c] = v; });
 }
 
 }  // namespace tsb

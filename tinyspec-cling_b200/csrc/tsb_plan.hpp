@@ -47,6 +47,7 @@ struct HostTables {
     std::vector<double> expect;
     std::vector<uint32_t> map;
     std::vector<uint16_t> map_src;
+    std::vector<int16_t> map1;  // empty unless every destination has at most one source
     double hop, rate, ratio, size_over_hop, dc_pos, dc_neg;
     ChainTables<real> view() const {
         ChainTables<real> t;
@@ -57,10 +58,12 @@ struct HostTables {
         t.expect = expect.data();
         t.map = map.data();
         t.map_src = map_src.data();
+        t.map1 = map1.empty() ? nullptr : map1.data();
         t.hop = hop;
         t.rate = rate;
         t.ratio = ratio;
         t.size_over_hop = size_over_hop;
+        t.inv_rate = 1.0 / rate;
         t.dc_pos = dc_pos;
         t.dc_neg = dc_neg;
         t.gain = gain.data();
@@ -72,9 +75,9 @@ template <typename real>
 HostTables<real> build_tables(const PlanDesc &d) {
     HostTables<real> h;
     const int n = d.n, m = n / 2;
-    std::vector<double> tw = twiddle_table(m, m), twn = twiddle_table(n, m / 2 + 1);
-    h.tw.resize(m);
-    for (int q = 0; q < m; q++) h.tw[q] = mk<real>((real)tw[2 * q], (real)tw[2 * q + 1]);
+    std::vector<double> tw = pass_twiddle_table(m), twn = twiddle_table(n, m / 2 + 1);
+    h.tw.resize(tw.size() / 2);
+    for (size_t q = 0; q < h.tw.size(); q++) h.tw[q] = mk<real>((real)tw[2 * q], (real)tw[2 * q + 1]);
     h.twn.resize(m / 2 + 1);
     for (int q = 0; q <= m / 2; q++) h.twn[q] = mk<real>((real)twn[2 * q], (real)twn[2 * q + 1]);
     std::vector<double> wa = window_table(d.win_in, n), ws = window_table(d.win_out, n);
@@ -99,6 +102,12 @@ HostTables<real> build_tables(const PlanDesc &d) {
         fb[j] = d.fn_bins ? d.fn_bins[j] : centre * d.ratio;
     }
     build_shift_map(n, d.rate, fb.data(), h.map, h.map_src);
+    bool simple = true;
+    for (uint32_t e : h.map) simple = simple && (e & 0xffff) <= 1;
+    if (simple) {
+        h.map1.resize(m);
+        for (int k = 0; k < m; k++) h.map1[k] = (h.map[k] & 0xffff) ? (int16_t)h.map_src[h.map[k] >> 16] : (int16_t)-1;
+    }
     h.gain.resize(m + 1);
     for (int k = 0; k <= m; k++) h.gain[k] = (real)(d.gain ? d.gain[k] : 1.0);
     return h;
