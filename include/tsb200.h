@@ -123,6 +123,37 @@ int tsb_chain_render(tsb_ctx *ctx, tsb_plan *plan, const tsb_chain_args *args);
  * buffers make the copies asynchronous; pageable ones work too. */
 int tsb_chain_render_host(tsb_ctx *ctx, tsb_plan *plan, const tsb_chain_args *args);
 
+/* ---- the helpers one by one ("immediate mode") ------------------------------------------------ */
+/* One call = one helper of the reference's rtinc/ library, on DEVICE buffers laid out like Buf<T>
+ * (planar [channel][size]; FFTBuf interleaved re,im; PVBuf interleaved amp,freq), double precision,
+ * asynchronous on the context's stream.  They serve hacks that mix helper calls with their own loops;
+ * chains made only of helpers are fused (tsb_chain_render). */
+
+/* window_hann / window_sqrt_hann (rtlib/windowfn.hpp:1-14): data[c][i] *= w[i], in place. */
+int tsb_window(tsb_ctx *ctx, double *data, int64_t nch, int64_t size, int32_t kind);
+
+/* What FFTW does for the reference (fftw_plan_many_dft(FFTW_FORWARD), rtlib/fft.hpp:13-17): `rows` forward
+ * DFTs of length n, kernel exp(-2*pi*i*j*k/n), unnormalised, any n >= 1, in place allowed. */
+int tsb_fft_forward(tsb_ctx *ctx, const double *in, double *out, int64_t rows, int64_t n);
+
+/* frft(in, out, exponent) (rtlib/fft.hpp:3-42), any size, any exponent; in == out reproduces the reference's
+ * in-place aliasing.  nch*n == 0 returns silently (fft.hpp:8-9). */
+int tsb_frft(tsb_ctx *ctx, double *in, double *out, int64_t nch, int64_t n, double exponent);
+
+/* PhaseVocoder::analyze(FFTBuf&) (rtlib/pv.hpp:17-28,39-45): all `size` bins of every channel.
+ * last_phase [nch][size] is read and updated, pvdata [nch][size][2] receives (amp, freq). */
+int tsb_pv_analyze(tsb_ctx *ctx, const double *spec, double *last_phase, double *pvdata, int64_t nch, int64_t size,
+                   double hop, double rate);
+/* PhaseVocoder::synthesize(FFTBuf&) (rtlib/pv.hpp:29-38,46-48): phase_sum += 2*pi*freq/RATE*hop; spec = polar. */
+int tsb_pv_synthesize(tsb_ctx *ctx, double *spec, double *phase_sum, const double *pvdata, int64_t nch, int64_t size,
+                      double hop, double rate);
+/* PhaseVocoder::shift (rtlib/pv.hpp:56-79).  The caller evaluates the user's fn on the host — it is
+ * arbitrary user code — and passes fn_bins[c][j] = fn(j/size*RATE) and fn_freqs[c][j] = fn(data[c][j].freq),
+ * j < size/2 (HOST arrays; tsb_pv_freqs fetches the frequencies).  The device zeroes and scatters. */
+int tsb_pv_freqs(tsb_ctx *ctx, const double *pvdata, int64_t nch, int64_t size, double *host_freqs);
+int tsb_pv_shift(tsb_ctx *ctx, double *pvdata, int64_t nch, int64_t size, double rate, const double *host_fn_bins,
+                 const double *host_fn_freqs);
+
 /* Number of kernel launches issued through this context so far (for benchmarks' bookkeeping). */
 int64_t tsb_launch_count(tsb_ctx *ctx);
 

@@ -1,0 +1,124 @@
+"""GPU parity of the one-helper-per-call device operators (tsb200.h "immediate mode") against the C oracle
+and the golden fixtures of the compiled reference."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+    import tsb200
+    from oracle import orc
+    return dict(torch=torch, tsb=tsb200, orc=orc, ctx=tsb200.Context(0))
+
+
+def dev(env, a):
+    return env["torch"].from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("n", [1, 2, 8, 64, 100, 512, 1000, 1800, 4096, 8192, 65536, 262144])
+def test_fft_forward_any_n(env, n):
+    rng = np.random.default_rng(n)
+    rows = 3 if n <= 8192 else 2
+    x = rng.standard_normal((rows, n)) + 1j * rng.standard_normal((rows, n))
+    got = env["ctx"].fft_forward(dev(env, x)).cpu().numpy()
+    want = np.fft.fft(x, axis=-1)
+    assert np.abs(got - want).max() <= 2e-14 * np.abs(want).max() * max(1.0, np.log2(max(n, 2)))
+
+
+def test_fft_in_place_and_large_batch(env):
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((700, 2048)) + 1j * rng.standard_normal((700, 2048))
+    xd = dev(env, x)
+    env["ctx"].fft_forward(xd, out=xd)
+    assert np.abs(xd.cpu().numpy() - np.fft.fft(x, axis=-1)).max() < 1e-11
+
+
+@pytest.mark.parametrize("kind", ["hann", "sqrt_hann"])
+@pytest.mark.parametrize("n", [8, 100, 1024])
+def test_window_bit_exact(env, kind, n):
+    x = np.random.default_rng(0).standard_normal((2, n))
+    got = env["ctx"].window(dev(env, x), kind).cpu().numpy()
+    assert np.array_equal(got, env["orc"].window(x, kind))
+
+
+def test_frft_vs_golden(env, golden):
+    """frft for exponents 1, -1, 2, 0.5 on sizes 8, 64, 100, 512: out of place and in place."""
+    g = golden("helpers")
+    off_in = off_out = 0
+    for n in g["frft_sizes"]:
+        x = g["frft_in"][off_in:off_in + 2 * n].reshape(2, n)
+        for e in g["frft_exps"]:
+            want = g["frft_out"][off_out:off_out + 2 * n].reshape(2, n)
+            off_out += 2 * n
+            xd = dev(env, x)
+            out = env["torch"].zeros_like(xd)
+            env["ctx"].frft(xd, float(e), out=out)
+            assert np.abs(out.cpu().numpy() - want).max() <= 1e-13 * max(1.0, np.abs(want).max()), (n, e)
+        want = g["frft_inplace"][off_in:off_in + 2 * n].reshape(2, n)
+        xd = dev(env, x)
+        env["ctx"].frft(xd, 1.0)
+        assert np.abs(xd.cpu().numpy() - want).max() <= 1e-13 * np.abs(want).max()
+        off_in += 2 * n
+
+
+@pytest.mark.parametrize("n,e", [(1800, 1.0), (1800, -1.0), (4096, 0.3), (131072, -1.0)])
+def test_frft_vs_oracle(env, n, e):
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((2, n)) + 1j * rng.standard_normal((2, n))
+    want = env["orc"].frft(x, e, inplace=True)
+    xd = dev(env, x)
+    env["ctx"].frft(xd, e)
+    assert np.abs(xd.cpu().numpy() - want).max() <= 1e-12 * np.abs(want).max()
+
+
+def test_frft_round_trip_and_empty(env):
+    x = np.random.default_rng(2).standard_normal((4, 2048)) + 0j
+    xd = dev(env, x)
+    env["ctx"].frft(xd, 1.0)
+    env["ctx"].frft(xd, -1.0)
+    assert np.abs(xd.cpu().numpy() - x).max() < 1e-12
+    empty = env["torch"].zeros((0, 16), dtype=env["torch"].complex128, device="cuda")
+    env["ctx"].frft(empty, 1.0)  # N*C == 0 returns silently (rtlib/fft.hpp:8-9)
+
+
+def test_pv_steps_vs_golden(env, golden):
+    """PhaseVocoder::analyze(WaveBuf) -> shift -> synthesize(WaveBuf) rebuilt from the device helpers, three
+    frames at sizes 64/256 and ratios 2, 1.5, 0.5, against the compiled reference's dumps (all N bins)."""
+    torch, ctx = env["torch"], env["ctx"]
+    g = golden("helpers")
+    off = 0
+    for n in g["pv_sizes"]:
+        n = int(n)
+        for ratio in g["pv_ratios"]:
+            hop = n / 4.0
+            last = torch.zeros((2, n), dtype=torch.float64, device="cuda")
+            psum = torch.zeros((2, n), dtype=torch.float64, device="cuda")
+            pvd = torch.zeros((2, n, 2), dtype=torch.float64, device="cuda")
+            for _ in range(3):
+                sl, sl2 = slice(off, off + 2 * n), slice(2 * off, 2 * off + 4 * n)
+                wave = dev(env, g["pv_in"][sl].reshape(2, n))
+                ctx.window(wave, "sqrt_hann")                       # rtlib/pv.hpp:5
+                spec = torch.complex(wave, torch.zeros_like(wave))  # fill_from, :6
+                ctx.frft(spec, 1.0)                                 # :7
+                ctx.pv_analyze(spec, last, pvd, hop)                # :8
+                want = g["pv_analyzed"][sl2].reshape(2, n, 2)
+                got = pvd.cpu().numpy()
+                assert np.abs(got[..., 0] - want[..., 0]).max() < 1e-13
+                assert np.abs(got[..., 1] - want[..., 1]).max() < 1e-6   # Hz; 1e-9 rad of phase ~ 3e-8 Hz
+                ctx.pv_shift(pvd, lambda v: v * float(ratio))
+                want = g["pv_shifted"][sl2].reshape(2, n, 2)
+                got = pvd.cpu().numpy()
+                assert np.abs(got[..., 0] - want[..., 0]).max() < 1e-13
+                assert np.abs(got[..., 1] - want[..., 1]).max() < 1e-6
+                ctx.pv_synthesize(spec, psum, pvd, hop)             # :12
+                ctx.frft(spec, -1.0)                                # :13
+                out = spec.real.contiguous()                        # :14
+                ctx.window(out, "sqrt_hann")                        # :15
+                want = g["pv_out"][sl].reshape(2, n)
+                assert np.abs(out.cpu().numpy() - want).max() <= 1e-9 * np.abs(want).max()
+                assert np.abs(psum.cpu().numpy() - g["pv_phase_sum"][sl].reshape(2, n)).max() < 1e-8
+                assert np.abs(last.cpu().numpy() - g["pv_last_phase"][sl].reshape(2, n)).max() < 1e-12
+                off += 2 * n

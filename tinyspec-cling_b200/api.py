@@ -64,6 +64,14 @@ def _load():
     L.tsb_plan_destroy.argtypes = [P]
     L.tsb_chain_render.argtypes = [P, P, C.POINTER(_ChainArgs)]
     L.tsb_chain_render_host.argtypes = [P, P, C.POINTER(_ChainArgs)]
+    I64, D = C.c_int64, C.c_double
+    L.tsb_window.argtypes = [P, P, I64, I64, C.c_int32]
+    L.tsb_fft_forward.argtypes = [P, P, P, I64, I64]
+    L.tsb_frft.argtypes = [P, P, P, I64, I64, D]
+    L.tsb_pv_analyze.argtypes = [P, P, P, P, I64, I64, D, D]
+    L.tsb_pv_synthesize.argtypes = [P, P, P, P, I64, I64, D, D]
+    L.tsb_pv_freqs.argtypes = [P, P, I64, I64, P]
+    L.tsb_pv_shift.argtypes = [P, P, I64, I64, D, P, P]
     _lib = L
     return L
 
@@ -133,6 +141,50 @@ class Context:
     @property
     def launches(self):
         return _load().tsb_launch_count(self.h)
+
+    # ---- the helpers one by one (tsb200.h "immediate mode"); tensors are CUDA float64 / complex128 ----
+    def window(self, data, kind):
+        """window_hann / window_sqrt_hann in place on a float64 [nch, size] tensor."""
+        assert data.is_cuda and data.is_contiguous() and data.dim() == 2
+        _check(_load().tsb_window(self.h, data.data_ptr(), data.shape[0], data.shape[1], _WIN[kind]))
+        return data
+
+    def fft_forward(self, x, out=None):
+        """rows of unnormalised forward DFTs (the FFTW contract), complex128 [rows, n], any n."""
+        import torch
+        assert x.is_cuda and x.dtype == torch.complex128 and x.is_contiguous() and x.dim() == 2
+        out = torch.empty_like(x) if out is None else out
+        _check(_load().tsb_fft_forward(self.h, x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1]))
+        return out
+
+    def frft(self, x, exponent, out=None):
+        """frft(in, out, exponent); out=None or out is x -> in place, like every reference call site."""
+        import torch
+        assert x.is_cuda and x.dtype == torch.complex128 and x.is_contiguous() and x.dim() == 2
+        out = x if out is None else out
+        _check(_load().tsb_frft(self.h, x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], float(exponent)))
+        return out
+
+    def pv_analyze(self, spec, last_phase, pvdata, hop, rate=48000.0):
+        nch, size = spec.shape
+        _check(_load().tsb_pv_analyze(self.h, spec.data_ptr(), last_phase.data_ptr(), pvdata.data_ptr(), nch, size,
+                                      float(hop), float(rate)))
+
+    def pv_synthesize(self, spec, phase_sum, pvdata, hop, rate=48000.0):
+        nch, size = spec.shape
+        _check(_load().tsb_pv_synthesize(self.h, spec.data_ptr(), phase_sum.data_ptr(), pvdata.data_ptr(), nch, size,
+                                         float(hop), float(rate)))
+
+    def pv_shift(self, pvdata, fn, rate=48000.0):
+        """PhaseVocoder::shift with a Python fn applied elementwise on the host (it is user code)."""
+        nch, size, _ = pvdata.shape
+        half = size // 2
+        freqs = np.zeros((nch, half))
+        _check(_load().tsb_pv_freqs(self.h, pvdata.data_ptr(), nch, size, freqs.ctypes.data))
+        bins = np.tile(np.arange(half) / float(size) * rate, (nch, 1))
+        fb = np.ascontiguousarray(fn(bins), np.float64)
+        ff = np.ascontiguousarray(fn(freqs), np.float64)
+        _check(_load().tsb_pv_shift(self.h, pvdata.data_ptr(), nch, size, float(rate), fb.ctypes.data, ff.ctypes.data))
 
     def close(self):
         if getattr(self, "h", None):

@@ -9,7 +9,9 @@
 
 #include "../../include/tsb200.h"
 #include "tsb_launch.hpp"
+#include "tsb_ops.hpp"
 #include "tsb_plan.hpp"
+#include <map>
 
 using namespace tsb;
 
@@ -36,6 +38,9 @@ struct tsb_ctx {
     cudaStream_t stream;
     bool own_stream;
     int64_t launches;
+    std::map<std::pair<int64_t, int>, double *> windows;  // (size, kind) -> device table
+    double *scratch = nullptr;                            // frft's FFT output / shift's copy
+    size_t scratch_bytes = 0;
 };
 
 struct tsb_plan {
@@ -64,7 +69,11 @@ TSB_API int tsb_ctx_create(int device, void *cuda_stream, int new_stream, tsb_ct
     if (prop.major != 10)
         return fail(TSB_EUNSUPPORTED, "device %d is sm_%d%d; libtsb200 is built for sm_100a only", device, prop.major,
                     prop.minor);
-    tsb_ctx *c = new tsb_ctx{device, nullptr, false, 0};
+    tsb_ctx *c = new tsb_ctx();
+    c->device = device;
+    c->stream = nullptr;
+    c->own_stream = false;
+    c->launches = 0;
     if (!new_stream) {
         c->stream = (cudaStream_t)cuda_stream;
     } else {
@@ -82,6 +91,8 @@ TSB_API int tsb_ctx_destroy(tsb_ctx *c) {
     if (!c) return TSB_OK;
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamDestroy(c->stream);
+    for (auto &kv : c->windows) cudaFree(kv.second);
+    if (c->scratch) cudaFree(c->scratch);
     delete c;
     return TSB_OK;
 }
@@ -328,5 +339,133 @@ TSB_API int tsb_chain_render_host(tsb_ctx *c, tsb_plan *p, const tsb_chain_args 
     for (int i = 0; i < 3; i++)
         if (host_state[i]) CU(cudaMemcpyAsync(host_state[i], *dev_state[i], st_bytes[i], cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    return TSB_OK;
+}
+
+// ---- the helpers one by one ----
+static int ctx_scratch(tsb_ctx *c, size_t bytes, double **out) {
+    if (c->scratch_bytes < bytes) {
+        // the stream may still be using the old block
+        CU(cudaStreamSynchronize(c->stream));
+        if (c->scratch) cudaFree(c->scratch);
+        c->scratch = nullptr;
+        c->scratch_bytes = 0;
+        cudaError_t e = cudaMalloc(&c->scratch, bytes);
+        if (e != cudaSuccess) return fail(TSB_ENOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+        c->scratch_bytes = bytes;
+    }
+    *out = c->scratch;
+    return TSB_OK;
+}
+TSB_API int tsb_window(tsb_ctx *c, double *data, int64_t nch, int64_t size, int32_t kind) {
+    if (!c) return fail(TSB_EINVAL, "null context");
+    if (nch < 0 || size < 0) return fail(TSB_EINVAL, "negative shape");
+    if (kind != TSB_WIN_HANN && kind != TSB_WIN_SQRT_HANN && kind != TSB_WIN_NONE) return fail(TSB_EINVAL, "bad window kind %d", kind);
+    if (nch * size == 0 || kind == TSB_WIN_NONE) return TSB_OK;
+    CU(cudaSetDevice(c->device));
+    auto key = std::make_pair(size, (int)kind);
+    auto it = c->windows.find(key);
+    if (it == c->windows.end()) {
+        std::vector<double> w = window_table(kind, (int)size);
+        double *d = nullptr;
+        cudaError_t e = cudaMalloc(&d, w.size() * sizeof(double));
+        if (e != cudaSuccess) return fail(TSB_ENOMEM, "cudaMalloc: %s", cudaGetErrorString(e));
+        CU(cudaMemcpyAsync(d, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        it = c->windows.emplace(key, d).first;
+    }
+    CU(op_window(data, it->second, nch, size, c->stream));
+    c->launches++;
+    return TSB_OK;
+}
+TSB_API int tsb_fft_forward(tsb_ctx *c, const double *in, double *out, int64_t rows, int64_t n) {
+    if (!c) return fail(TSB_EINVAL, "null context");
+    if (rows < 0 || n < 0) return fail(TSB_EINVAL, "negative shape");
+    if (n > (1LL << 24)) return fail(TSB_EUNSUPPORTED, "FFT length %lld > 2^24", (long long)n);
+    CU(cudaSetDevice(c->device));
+    long long l = 0;
+    CU(op_fft_forward(c->device, in, out, rows, n, c->stream, &l));
+    c->launches += l;
+    return TSB_OK;
+}
+TSB_API int tsb_frft(tsb_ctx *c, double *in, double *out, int64_t nch, int64_t n, double exponent) {
+    if (!c) return fail(TSB_EINVAL, "null context");
+    if (nch < 0 || n < 0) return fail(TSB_EINVAL, "negative shape");
+    if (nch * n == 0) return TSB_OK;  // rtlib/fft.hpp:8-9
+    if (n > (1LL << 23)) return fail(TSB_EUNSUPPORTED, "frft length %lld > 2^23", (long long)n);
+    CU(cudaSetDevice(c->device));
+    double *g;
+    int r = ctx_scratch(c, (size_t)(nch * n) * 16, &g);
+    if (r) return r;
+    long long l = 0;
+    CU(op_frft(c->device, in, out, g, nch, n, exponent, c->stream, &l));
+    c->launches += l;
+    return TSB_OK;
+}
+TSB_API int tsb_pv_analyze(tsb_ctx *c, const double *spec, double *last_phase, double *pvdata, int64_t nch, int64_t size,
+                           double hop, double rate) {
+    if (!c) return fail(TSB_EINVAL, "null context");
+    CU(cudaSetDevice(c->device));
+    CU(op_pv_analyze(spec, last_phase, pvdata, nch, size, hop, rate, c->stream));
+    c->launches++;
+    return TSB_OK;
+}
+TSB_API int tsb_pv_synthesize(tsb_ctx *c, double *spec, double *phase_sum, const double *pvdata, int64_t nch, int64_t size,
+                              double hop, double rate) {
+    if (!c) return fail(TSB_EINVAL, "null context");
+    CU(cudaSetDevice(c->device));
+    CU(op_pv_synthesize(spec, phase_sum, pvdata, nch, size, hop, rate, c->stream));
+    c->launches++;
+    return TSB_OK;
+}
+TSB_API int tsb_pv_freqs(tsb_ctx *c, const double *pvdata, int64_t nch, int64_t size, double *host_freqs) {
+    if (!c || !host_freqs) return fail(TSB_EINVAL, "null argument");
+    CU(cudaSetDevice(c->device));
+    int64_t half = size / 2;
+    for (int64_t ch = 0; ch < nch; ch++)  // freq is the second double of each PVBin
+        CU(cudaMemcpy2DAsync(host_freqs + ch * half, 8, pvdata + 2 * ch * size + 1, 16, 8, (size_t)half,
+                             cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TSB_OK;
+}
+TSB_API int tsb_pv_shift(tsb_ctx *c, double *pvdata, int64_t nch, int64_t size, double rate, const double *host_fn_bins,
+                         const double *host_fn_freqs) {
+    if (!c || !host_fn_bins || !host_fn_freqs) return fail(TSB_EINVAL, "null argument");
+    if (nch * size == 0) return TSB_OK;
+    CU(cudaSetDevice(c->device));
+    const int64_t half = size / 2;
+    std::vector<unsigned> off(nch * half + 1, 0), src;
+    for (int64_t ch = 0; ch < nch; ch++) {
+        std::vector<std::vector<unsigned>> per(half);
+        for (int64_t j = 0; j < half; j++) {
+            double q = host_fn_bins[ch * half + j] / rate * (size_t)size;  // rtlib/pv.hpp:72
+            if (!(q > -2147483648.0 && q < 2147483648.0)) continue;
+            int k = (int)q;
+            if (k >= 0 && k < (int)half) per[k].push_back((unsigned)j);
+        }
+        for (int64_t k = 0; k < half; k++) {
+            off[ch * half + k] = (unsigned)src.size();
+            for (unsigned j : per[k]) src.push_back(j);
+        }
+    }
+    off[nch * half] = (unsigned)src.size();
+    if (src.empty()) src.push_back(0);
+    // scratch: [copy of pvdata | fn_freqs | off | src]
+    size_t b_tmp = (size_t)(nch * size) * 16, b_fr = (size_t)(nch * half) * 8, b_off = off.size() * 4, b_src = src.size() * 4;
+    double *scr;
+    int r = ctx_scratch(c, b_tmp + b_fr + b_off + b_src + 64, &scr);
+    if (r) return r;
+    char *p = reinterpret_cast<char *>(scr);
+    double *d_tmp = reinterpret_cast<double *>(p);
+    double *d_fr = reinterpret_cast<double *>(p + b_tmp);
+    unsigned *d_off = reinterpret_cast<unsigned *>(p + b_tmp + b_fr);
+    unsigned *d_src = reinterpret_cast<unsigned *>(p + b_tmp + b_fr + b_off);
+    CU(cudaMemcpyAsync(d_tmp, pvdata, b_tmp, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_fr, host_fn_freqs, b_fr, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_off, off.data(), b_off, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_src, src.data(), b_src, cudaMemcpyHostToDevice, c->stream));
+    CU(op_pv_shift(d_tmp, pvdata, d_fr, d_off, d_src, nch, size, c->stream));
+    CU(cudaStreamSynchronize(c->stream));  // off/src/host arrays go out of scope
+    c->launches++;
     return TSB_OK;
 }

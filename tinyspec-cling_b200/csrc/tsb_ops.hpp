@@ -1,0 +1,19 @@
+// tsb_ops.hpp — launchers of the generic (one reference helper = one call) device operators, tsb_ops.cu.
+// All pointers are device pointers, all data double precision, layouts as the reference's Buf<T>:
+// planar [channel][size]; FFTBuf = interleaved (re, im); PVBuf = interleaved (amp, freq).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace tsb {
+cudaError_t op_fft_forward(int device, const double *in, double *out, long long rows, long long n, cudaStream_t st,
+                           long long *launches);
+cudaError_t op_frft(int device, const double *in, double *out, double *scratch_g, long long nch, long long n,
+                    double exponent, cudaStream_t st, long long *launches);
+cudaError_t op_window(double *data, const double *wtab, long long nch, long long size, cudaStream_t st);
+cudaError_t op_pv_analyze(const double *spec, double *last_phase, double *pvdata, long long nch, long long size,
+                          double hop, double rate, cudaStream_t st);
+cudaError_t op_pv_synthesize(double *spec, double *phase_sum, const double *pvdata, long long nch, long long size,
+                             double hop, double rate, cudaStream_t st);
+cudaError_t op_pv_shift(const double *tmp, double *pvdata, const double *fn_freqs, const unsigned *off,
+                        const unsigned *src, long long nch, long long size, cudaStream_t st);
+}  // namespace tsb
