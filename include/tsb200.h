@@ -154,6 +154,17 @@ int tsb_pv_freqs(tsb_ctx *ctx, const double *pvdata, int64_t nch, int64_t size, 
 int tsb_pv_shift(tsb_ctx *ctx, double *pvdata, int64_t nch, int64_t size, double rate, const double *host_fn_bins,
                  const double *host_fn_freqs);
 
+/* Frame gather (tinyspec.cpp:151-157): frame[l][i] = (double) in[l][in_off + i], i < w, zero past in_len. */
+int tsb_gather_frame(tsb_ctx *ctx, const float *in, int64_t in_stride, int64_t in_len, int64_t in_off, double *frame,
+                     int64_t lanes, int64_t w);
+/* Overlap-add of one frame exactly as tinyspec.cpp:170-200 does it, float32 tail and float32 narrowing
+ * included: emits `hop` samples at out[l][out_off ..], keeps max(tail_len, osize) - hop samples of overlap.
+ * tail_in / tail_out are distinct float32 [lanes][tail_cap] buffers (swap them frame to frame); tail_len is the
+ * overlap length before this frame; the new length is returned in *new_tail_len. */
+int tsb_overlap_add(tsb_ctx *ctx, const double *frame, int64_t lanes, int64_t osize, int64_t hop, float *out,
+                    int64_t out_stride, int64_t out_len, int64_t out_off, const float *tail_in, float *tail_out,
+                    int64_t tail_cap, int64_t tail_len, int64_t *new_tail_len);
+
 /* Number of kernel launches issued through this context so far (for benchmarks' bookkeeping). */
 int64_t tsb_launch_count(tsb_ctx *ctx);
 

@@ -1,0 +1,115 @@
+"""The source-compatible C++ header set (tinyspec-cling_b200/rtinc) and the offline render driver.
+
+CPU: the reference's own hacks compile UNCHANGED against our headers (where /root/reference exists) and the
+example hacks build.  GPU: rendered output against the oracle, in fused and in immediate mode."""
+import json
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DRV = os.path.join(ROOT, "tinyspec-cling_b200", "driver")
+EX = os.path.join(ROOT, "tinyspec-cling_b200", "examples")
+REF_HACKS = "/root/reference/hacks"
+
+
+def build(hack, out=None):
+    args = ["make", "-C", DRV, "HACK=" + hack]
+    if out:
+        args.append("OUT=" + out)
+    r = subprocess.run(args, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return out or os.path.join(DRV, "ts_render_" + os.path.splitext(os.path.basename(hack))[0])
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_HACKS), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("hack", ["pitchshift-pv", "readme", "pitchshift-simple", "karplus-strong", "sinosc", "bytebeat",
+                                  "osc", "tidal", "pwm", "pwm_bb", "connect", "spectral_bytebeat/voidbubbles",
+                                  "spectral_bytebeat/andshuffle", "spectral_bytebeat/knead"])
+def test_reference_hacks_compile_unchanged(hack, tmp_path):
+    build(os.path.join(REF_HACKS, hack + ".cpp"), out=str(tmp_path / "r"))
+
+
+def test_examples_build():
+    for h in ("pitchshift_cfg1", "passthrough_cfg2", "lowpass_raw"):
+        assert os.path.exists(build(os.path.join(EX, h + ".cpp")))
+
+
+def render(binary, *args, lanes=1, f64=False):
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, "o.bin")
+        cmd = [binary, "--out", out, "--timing"] + [str(a) for a in args] + (["--out-f64"] if f64 else [])
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            return r, None, None
+        info = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+        y = np.fromfile(out, np.float64 if f64 else np.float32).reshape(lanes, -1)
+        return r, info, y
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_fused_pitchshift(precision):
+    from oracle import orc
+    b = build(os.path.join(EX, "pitchshift_cfg1.cpp"))
+    streams, secs = 3, 0.5
+    r, info, y = render(b, "--seconds", secs, "--streams", streams, "--precision", precision, lanes=2 * streams,
+                        f64=precision == "f64")
+    assert r.returncode == 0, r.stderr
+    assert info["mode"] == "fused" and info["gpu_launches"] == 1      # all frames x all lanes in one launch
+    for s in range(streams):
+        x = orc.gen_signal(s, 2, int(secs * 48000))
+        ref = orc.render_pv(x, 1024, 0.25, 2.0)
+        assert info["frames"] == ref["frames"]
+        want = ref["ola64"][:y.shape[1]].T
+        got = y[2 * s:2 * s + 2]
+        if precision == "f64":
+            assert np.abs(got - want).max() <= 1e-9 * np.abs(want).max()
+        else:
+            assert np.sqrt(np.mean((got - want) ** 2) / np.mean(want ** 2)) <= 1e-5
+
+
+@pytest.mark.gpu
+def test_immediate_pitchshift_matches_reference_stream():
+    """Immediate mode runs the reference's loop with device operators, float32 overlap tail included: the output
+    is the reference's float32 stream up to the last bit of float rounding."""
+    from oracle import orc
+    b = build(os.path.join(EX, "pitchshift_cfg1.cpp"))
+    r, info, y = render(b, "--seconds", 0.25, "--mode", "immediate", lanes=2)
+    assert r.returncode == 0, r.stderr
+    x = orc.gen_signal(0, 2, 12000)
+    ref = orc.render_pv(x, 1024, 0.25, 2.0)
+    assert info["frames"] == ref["frames"] and y.shape[1] == ref["stream"].shape[0]
+    d = np.abs(y.T - ref["stream"])
+    assert d.max() <= 1.2e-7 * np.abs(ref["stream"]).max()
+    assert (d == 0).mean() > 0.99
+
+
+@pytest.mark.gpu
+def test_fused_passthrough_and_immediate_lowpass():
+    from oracle import orc
+    x = orc.gen_signal(0, 1, 24000)
+    b = build(os.path.join(EX, "passthrough_cfg2.cpp"))
+    r, info, y = render(b, "--seconds", 0.5, f64=True)
+    assert r.returncode == 0, r.stderr
+    ref = orc.render_filter(x, 2048, 0.25, None)
+    assert info["frames"] == ref["frames"] and info["gpu_launches"] == 1
+    assert np.abs(y[0] - ref["ola64"][:y.shape[1], 0]).max() < 1e-12
+    b = build(os.path.join(EX, "lowpass_raw.cpp"))
+    r, info, y = render(b, "--seconds", 0.5, "--mode", "immediate")
+    assert r.returncode == 0, r.stderr
+    gain = 1.0 / (1.0 + np.arange(1025) / 64.0)
+    ref = orc.render_filter(x, 2048, 0.25, gain)
+    assert info["frames"] == ref["frames"]
+    d = np.abs(y[0] - ref["stream"][:, 0])
+    assert d.max() <= 1.2e-7 * np.abs(ref["stream"]).max() and (d == 0).mean() > 0.99
+
+
+@pytest.mark.gpu
+def test_fused_mode_refuses_raw_access_loudly():
+    b = build(os.path.join(EX, "lowpass_raw.cpp"))
+    r, _, _ = render(b, "--seconds", 0.2)
+    assert r.returncode != 0 and "immediate" in r.stderr

@@ -469,3 +469,29 @@ TSB_API int tsb_pv_shift(tsb_ctx *c, double *pvdata, int64_t nch, int64_t size, 
     c->launches++;
     return TSB_OK;
 }
+
+TSB_API int tsb_gather_frame(tsb_ctx *c, const float *in, int64_t in_stride, int64_t in_len, int64_t in_off, double *frame,
+                             int64_t lanes, int64_t w) {
+    if (!c) return fail(TSB_EINVAL, "null context");
+    if (lanes < 0 || w < 0) return fail(TSB_EINVAL, "negative shape");
+    CU(cudaSetDevice(c->device));
+    CU(op_gather(in, in_stride, in_len, in_off, frame, lanes, w, c->stream));
+    c->launches++;
+    return TSB_OK;
+}
+TSB_API int tsb_overlap_add(tsb_ctx *c, const double *frame, int64_t lanes, int64_t osize, int64_t hop, float *out,
+                            int64_t out_stride, int64_t out_len, int64_t out_off, const float *tail_in, float *tail_out,
+                            int64_t tail_cap, int64_t tail_len, int64_t *new_tail_len) {
+    if (!c || !new_tail_len) return fail(TSB_EINVAL, "null argument");
+    if (lanes < 0 || osize < 0 || hop < 0 || tail_len < 0) return fail(TSB_EINVAL, "negative shape");
+    int64_t keep = (tail_len > osize ? tail_len : osize) - hop;
+    if (keep < 0) keep = 0;
+    if (keep > tail_cap || tail_len > tail_cap) return fail(TSB_EINVAL, "overlap of %lld samples exceeds tail_cap %lld", (long long)keep, (long long)tail_cap);
+    if (tail_in == tail_out && keep > 0) return fail(TSB_EINVAL, "tail_in and tail_out must be distinct buffers");
+    CU(cudaSetDevice(c->device));
+    CU(op_overlap_add(frame, osize, hop, out, out_stride, out_len, out_off, tail_in, tail_out, tail_cap, tail_len, keep, lanes,
+                      c->stream));
+    *new_tail_len = keep;
+    c->launches++;
+    return TSB_OK;
+}

@@ -413,4 +413,72 @@ cudaError_t op_pv_shift(const double *tmp, double *pvdata, const double *fn_freq
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ frame gather, tinyspec.cpp:151-157
+// frame[l][i] = (double) in[l][in_off + i], zero past the end of the input (planar float rows -> planar double).
+__global__ void gather_kernel(const float *in, long long in_stride, long long in_len, long long in_off, double *frame,
+                              long long lanes, long long w) {
+    long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= lanes * w) return;
+    long long l = idx / w, i = idx % w, s = in_off + i;
+    frame[idx] = (s >= 0 && s < in_len) ? (double)in[l * in_stride + s] : 0.0;
+}
+cudaError_t op_gather(const float *in, long long in_stride, long long in_len, long long in_off, double *frame,
+                      long long lanes, long long w, cudaStream_t st) {
+    if (lanes * w == 0) return cudaSuccess;
+    const int TB = 256;
+    gather_kernel<<<(unsigned)((lanes * w + TB - 1) / TB), TB, 0, st>>>(in, in_stride, in_len, in_off, frame, lanes, w);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ overlap-add, tinyspec.cpp:170-200
+// The reference keeps the overlap in a deque<float> `atmp` and narrows to float when it emits:
+//   emit  i <  min(hop, osize):  out = float(double(tail[i] or 0) + frame[i])          (:173-182)
+//   emit  osize <= i < hop:      out = tail[i] or 0                                    (:184-191)
+//   keep  i <  osize - hop:      tail'[i] = (tail[hop+i] exists ? tail[hop+i] + float(frame[hop+i]) : float(frame[hop+i]))
+//   keep  beyond that:           tail'[i] = tail[hop+i]                                (:194-200)
+// tail_in / tail_out are distinct buffers [lanes][tail_cap]; tail_len is the deque's length before this frame.
+__global__ void ola_kernel(const double *frame, long long osize, long long hop, float *out, long long out_stride,
+                           long long out_len, long long out_off, const float *tail_in, float *tail_out, long long tail_cap,
+                           long long tail_len, long long new_tail_len, long long lanes) {
+    long long span = hop > new_tail_len ? hop : new_tail_len;
+    long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= lanes * span) return;
+    long long l = idx / span, i = idx % span;
+    const double *fr = frame + l * osize;
+    const float *ti = tail_in + l * tail_cap;
+    if (i < hop) {
+        float v;
+        if (i < osize) {
+            float overlap = i < tail_len ? ti[i] : 0.f;
+            v = (float)((double)overlap + fr[i]);
+        } else {
+            v = i < tail_len ? ti[i] : 0.f;
+        }
+        long long p = out_off + i;
+        if (p < out_len) out[l * out_stride + p] = v;
+    }
+    if (i < new_tail_len) {
+        float t;
+        bool have = hop + i < tail_len;
+        if (hop + i < osize) {
+            float out_val = (float)fr[hop + i];
+            t = have ? ti[hop + i] + out_val : out_val;
+        } else {
+            t = ti[hop + i];
+        }
+        tail_out[l * tail_cap + i] = t;
+    }
+}
+cudaError_t op_overlap_add(const double *frame, long long osize, long long hop, float *out, long long out_stride,
+                           long long out_len, long long out_off, const float *tail_in, float *tail_out, long long tail_cap,
+                           long long tail_len, long long new_tail_len, long long lanes, cudaStream_t st) {
+    long long span = hop > new_tail_len ? hop : new_tail_len;
+    if (lanes * span == 0) return cudaSuccess;
+    const int TB = 256;
+    ola_kernel<<<(unsigned)((lanes * span + TB - 1) / TB), TB, 0, st>>>(frame, osize, hop, out, out_stride, out_len, out_off,
+                                                                         tail_in, tail_out, tail_cap, tail_len, new_tail_len,
+                                                                         lanes);
+    return cudaGetLastError();
+}
+
 }  // namespace tsb

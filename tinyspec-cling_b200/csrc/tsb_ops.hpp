@@ -16,4 +16,9 @@ cudaError_t op_pv_synthesize(double *spec, double *phase_sum, const double *pvda
                              double hop, double rate, cudaStream_t st);
 cudaError_t op_pv_shift(const double *tmp, double *pvdata, const double *fn_freqs, const unsigned *off,
                         const unsigned *src, long long nch, long long size, cudaStream_t st);
+cudaError_t op_gather(const float *in, long long in_stride, long long in_len, long long in_off, double *frame,
+                      long long lanes, long long w, cudaStream_t st);
+cudaError_t op_overlap_add(const double *frame, long long osize, long long hop, float *out, long long out_stride,
+                           long long out_len, long long out_off, const float *tail_in, float *tail_out, long long tail_cap,
+                           long long tail_len, long long new_tail_len, long long lanes, cudaStream_t st);
 }  // namespace tsb
