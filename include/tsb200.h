@@ -123,6 +123,38 @@ int tsb_chain_render(tsb_ctx *ctx, tsb_plan *plan, const tsb_chain_args *args);
  * buffers make the copies asynchronous; pageable ones work too. */
 int tsb_chain_render_host(tsb_ctx *ctx, tsb_plan *plan, const tsb_chain_args *args);
 
+/* ---- time-parallel rendering ------------------------------------------------------------------ */
+/* The only things a frame needs from earlier frames of its lane are last_phase (the previous frame's phases),
+ * phase_sum (a running sum of per-frame increments) and the overlap tail.  A render of n_frames frames is cut
+ * into time segments that run concurrently (one CTA per segment and lane):
+ *   pre-pass  every segment analyses its frames (plus one warm-up frame before it, to obtain last_phase) and
+ *             sums its phase increments per bin — no synthesis, no output;
+ *   scan      segment s starts from phase_sum = carry-in + the totals of segments 0..s-1, added in order;
+ *   main      the full chain per segment from that state, each segment starting with an empty overlap tail;
+ *   fix-up    segment s-1's overlap tail is added onto the head of segment s's output, in a fixed order.
+ * The result equals tsb_chain_render's up to the regrouping of those floating-point additions (~ulp(phase_sum)).
+ * This is what lets ONE long stream fill a GPU, and what a multi-GPU time split is built from: rank g renders a
+ * block of frames (its input must start one warm-up frame earlier: `warmup` = 1 and args->in_off0 - warm_hop >= 0),
+ * pre-passes it, exchanges block totals (tsb_timepar_prepass gives the block's total and final last_phase),
+ * sets args' state_phase_sum to the sum of earlier blocks and renders; the final overlap tail (state_ola) goes to
+ * rank g+1, which adds it at the head of its output with tsb_add_tail. */
+typedef struct tsb_timepar tsb_timepar;
+/* args is copied (device pointers must stay valid); host_hop_tab = host copy of args->hop_tab (NULL iff hop_tab is NULL) */
+int tsb_timepar_create(tsb_ctx *ctx, tsb_plan *plan, const tsb_chain_args *args, const int32_t *host_hop_tab,
+                       int32_t n_segments, int32_t warmup, int32_t warm_hop, tsb_timepar **tp);
+int tsb_timepar_segments(tsb_timepar *tp);   /* segments actually used (each must emit at least n samples) */
+/* block_total / block_last_phase: device [lanes][n/2] float64, may be NULL */
+int tsb_timepar_prepass(tsb_timepar *tp, double *block_total, double *block_last_phase);
+/* initial state = args->state_* (NULL or load_state 0: reset state); they receive the final state */
+int tsb_timepar_render(tsb_timepar *tp);
+int tsb_timepar_destroy(tsb_timepar *tp);
+/* create + prepass + render + destroy */
+int tsb_chain_render_timepar(tsb_ctx *ctx, tsb_plan *plan, const tsb_chain_args *args, const int32_t *host_hop_tab,
+                             int32_t n_segments);
+/* out[l][pos + i] += tail[l][i], i < n (tail: device float64 [lanes][n], e.g. another block's final state_ola) */
+int tsb_add_tail(tsb_ctx *ctx, tsb_plan *plan, void *out, int64_t out_stride, int64_t out_len, int64_t pos,
+                 const double *tail, int64_t lanes);
+
 /* ---- the helpers one by one ("immediate mode") ------------------------------------------------ */
 /* One call = one helper of the reference's rtinc/ library, on DEVICE buffers laid out like Buf<T>
  * (planar [channel][size]; FFTBuf interleaved re,im; PVBuf interleaved amp,freq), double precision,

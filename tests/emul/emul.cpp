@@ -33,7 +33,7 @@ static int run(const PlanDesc &d, const ChainArgs &a) {
     for (int lane = 0; lane < a.lanes; lane++) {
         std::memset(sm.get(), 0, sizeof(typename CH::Smem));
         HostExec<CH> ex;
-        run_lane<CH>(ex, lane, *sm, tb, a);
+        run_lane<CH>(ex, lane, 0, *sm, tb, a);
     }
     return 0;
 }
@@ -76,6 +76,7 @@ extern "C" int emul_chain_render(int precision, int log2n, int program, int win_
     a.hop = hop; a.hop_tab = hop_tab;
     a.st_last_phase = st_last_phase; a.st_phase_sum = st_phase_sum; a.st_ola = st_ola;
     a.load_state = load_state; a.lanes = lanes;
+    a.n_seg = 0; a.seg_tab = nullptr; a.mode = 0; a.st_warm_phase = nullptr;
     if (precision == 0)
         return program == PROG_PV_SHIFT ? by_size<float, PROG_PV_SHIFT>(log2n, d, a) : by_size<float, PROG_GAIN>(log2n, d, a);
     return program == PROG_PV_SHIFT ? by_size<double, PROG_PV_SHIFT>(log2n, d, a) : by_size<double, PROG_GAIN>(log2n, d, a);

@@ -208,3 +208,72 @@ def test_errors_are_loud(env):
         tsb.Plan(env["ctx"], 16384, program="pv", hop=4096)    # beyond the fused range
     with pytest.raises(tsb.TsbError):
         tsb.hop_fixed(-1.0)                                    # rtlib/control.hpp:23
+
+
+# ---------------------------------------------------------------- time-parallel rendering (tsb_timepar_*)
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+@pytest.mark.parametrize("n,hr,shift,ch,samples,nseg", [(1024, 0.25, 2.0, 2, 96000, 37), (1024, 0.25, 1.5, 1, 480000, 444),
+                                                        (4096, 0.25, 1.5, 8, 120000, 5), (512, 0.2003, 0.75, 1, 40000, 16)])
+def test_timepar_matches_sequential_and_oracle(env, precision, n, hr, shift, ch, samples, nseg):
+    """Segments of one stream rendered concurrently (pre-pass, scan, main, tail fix-up) give the sequential
+    result up to the regrouping of the phase and overlap additions, and stay within the oracle tolerance."""
+    torch, tsb, orc = env["torch"], env["tsb"], env["orc"]
+    x = orc.gen_signal(1, ch, samples)
+    sch = tsb.schedule_const(samples, n, n * hr)
+    F = sch["n_frames"]
+    const = bool(np.all(sch["hop"] == sch["hop"][0]))
+    hop_tab = None if const else sch["hop"]
+    xd = torch.from_numpy(np.ascontiguousarray(x.T)).cuda()
+    plan = tsb.Plan(env["ctx"], n, precision=precision, program="pv", hop=n * hr, ratio=shift)
+    mk = lambda: {k: torch.zeros((ch, w), dtype=torch.float64, device="cuda") for k, w in
+                  (("last_phase", n // 2), ("phase_sum", n // 2), ("ola", n))}
+    s_seq, s_par = mk(), mk()
+    seq = plan.render(xd, F, int(sch["hop"][0]), hop_tab=hop_tab, state=s_seq).clone()
+    par = plan.render_timepar(xd, F, int(sch["hop"][0]), nseg, hop_tab=hop_tab, state=s_par)
+    torch.cuda.synchronize()
+    seq, par = seq.cpu().numpy(), par.cpu().numpy()
+    peak = np.abs(seq).max()
+    if precision == "f64":
+        assert np.abs(par - seq).max() <= 1e-9 * peak   # regrouped fp64 sums: ~ulp(phase_sum) x bin amplitude
+        assert np.abs(s_par["phase_sum"].cpu().numpy() - s_seq["phase_sum"].cpu().numpy()).max() < 1e-7
+        assert np.abs(s_par["last_phase"].cpu().numpy() - s_seq["last_phase"].cpu().numpy()).max() == 0
+        assert np.abs(s_par["ola"].cpu().numpy() - s_seq["ola"].cpu().numpy()).max() <= 1e-9 * peak
+        if samples <= 120000:
+            ref = orc.render_pv(x, n, hr, shift)
+            assert maxrel(par, ref["ola64"][:par.shape[1]].T) <= F64_MAXREL
+    else:
+        assert rmsrel(par, seq) <= 2e-6
+        assert (np.abs(s_par["phase_sum"].cpu().numpy() - s_seq["phase_sum"].cpu().numpy()) > 1).sum() == 0
+    again = plan.render_timepar(xd, F, int(sch["hop"][0]), nseg, hop_tab=hop_tab)
+    torch.cuda.synchronize()
+    assert np.array_equal(again.cpu().numpy(), par)  # deterministic
+
+
+def test_timepar_two_blocks_like_two_gpus(env):
+    """The multi-GPU time split, run as two blocks on one device: block 1 starts mid-render with a warm-up frame
+    from its input halo, a phase carry equal to block 0's total, and receives block 0's overlap tail."""
+    torch, tsb, orc = env["torch"], env["tsb"], env["orc"]
+    n, hop, ch, samples = 1024, 256, 2, 200000
+    x = orc.gen_signal(0, ch, samples)
+    sch = tsb.schedule_const(samples, n, hop)
+    F = sch["n_frames"]
+    xd = torch.from_numpy(np.ascontiguousarray(x.T)).cuda()
+    plan = tsb.Plan(env["ctx"], n, precision="f64", program="pv", hop=hop, ratio=1.5)
+    whole = plan.render(xd, F, hop).clone()
+    zeros = lambda w: torch.zeros((ch, w), dtype=torch.float64, device="cuda")
+    F0 = F // 2
+    out = torch.zeros_like(whole)
+    # block 0: frames [0, F0)
+    st0 = dict(last_phase=zeros(n // 2), phase_sum=zeros(n // 2), ola=zeros(n))
+    tp0 = plan.timepar(xd, F0, hop, 24, out=out, state=st0)
+    tot0, _ = tp0.prepass()
+    # block 1: frames [F0, F): needs input from I_F0 - hop on (the halo), carry-in = block 0's total
+    st1 = dict(last_phase=zeros(n // 2), phase_sum=tot0.clone(), ola=zeros(n))
+    tp1 = plan.timepar(xd, F - F0, hop, 24, out=out, in_off0=int(sch["in_off"][F0]), out_off0=int(sch["out_off"][F0]),
+                       state=st1, load_state=True, warmup=True, warm_hop=hop)
+    tp1.prepass()
+    tp1.render()
+    tp0.render()
+    plan.add_tail(out, int(sch["out_off"][F0]), st0["ola"])
+    torch.cuda.synchronize()
+    assert np.abs(out.cpu().numpy() - whole.cpu().numpy()).max() <= 1e-9 * float(whole.abs().max())

@@ -72,6 +72,14 @@ def _load():
     L.tsb_pv_synthesize.argtypes = [P, P, P, P, I64, I64, D, D]
     L.tsb_pv_freqs.argtypes = [P, P, I64, I64, P]
     L.tsb_pv_shift.argtypes = [P, P, I64, I64, D, P, P]
+    I32 = C.c_int32
+    L.tsb_timepar_create.argtypes = [P, P, C.POINTER(_ChainArgs), P, I32, I32, I32, C.POINTER(P)]
+    L.tsb_timepar_segments.argtypes = [P]
+    L.tsb_timepar_prepass.argtypes = [P, P, P]
+    L.tsb_timepar_render.argtypes = [P]
+    L.tsb_timepar_destroy.argtypes = [P]
+    L.tsb_chain_render_timepar.argtypes = [P, P, C.POINTER(_ChainArgs), P, I32]
+    L.tsb_add_tail.argtypes = [P, P, P, I64, I64, I64, P, I64]
     _lib = L
     return L
 
@@ -267,6 +275,58 @@ class Plan:
         self._keep = (x, out, ht, state)
         return out
 
+    def _device_args(self, x, n_frames, hop, out, in_off0, out_off0, hop_tab, state, load_state, out_len):
+        import torch
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous()
+        lanes, L = x.shape
+        ht_host = None
+        ht = None
+        if hop_tab is not None:
+            ht_host = np.ascontiguousarray(hop_tab.cpu().numpy() if torch.is_tensor(hop_tab) else hop_tab, np.int32)
+            ht = torch.from_numpy(ht_host).to(x.device)
+            assert ht_host.size == n_frames
+            total = int(ht_host.sum())
+        else:
+            total = n_frames * int(hop)
+        if out is None:
+            out = torch.zeros((lanes, out_len if out_len is not None else out_off0 + total), dtype=self.out_dtype,
+                              device=x.device)
+        assert out.is_cuda and out.dtype == self.out_dtype and out.is_contiguous() and out.shape[0] == lanes
+        st = (None, None, None)
+        if state is not None:
+            for k, w in (("last_phase", self.n // 2), ("phase_sum", self.n // 2), ("ola", self.n)):
+                t = state[k]
+                assert t.is_cuda and t.dtype == torch.float64 and t.shape == (lanes, w) and t.is_contiguous()
+            st = (state["last_phase"].data_ptr(), state["phase_sum"].data_ptr(), state["ola"].data_ptr())
+        a = self._args(lanes, x.data_ptr(), x.stride(0), L, out.data_ptr(), out.stride(0), out.shape[1], n_frames,
+                       in_off0, out_off0, hop, None if ht is None else ht.data_ptr(), st, load_state)
+        return a, out, ht, ht_host
+
+    def render_timepar(self, x, n_frames, hop, n_segments, out=None, in_off0=2048, out_off0=0, hop_tab=None,
+                       state=None, load_state=False, out_len=None):
+        """Same result as render() up to floating-point regrouping, with the frames of every lane cut into
+        `n_segments` concurrent time segments (tsb_chain_render_timepar)."""
+        a, out, ht, ht_host = self._device_args(x, n_frames, hop, out, in_off0, out_off0, hop_tab, state, load_state,
+                                                out_len)
+        _check(_load().tsb_chain_render_timepar(self.ctx.h, self.h, C.byref(a),
+                                                None if ht_host is None else ht_host.ctypes.data, int(n_segments)))
+        self._keep = (x, out, ht, state)
+        return out
+
+    def timepar(self, x, n_frames, hop, n_segments, out=None, in_off0=2048, out_off0=0, hop_tab=None, state=None,
+                load_state=False, out_len=None, warmup=False, warm_hop=0):
+        """Two-step form (pre-pass, then render) for renders split across GPUs: returns a TimePar."""
+        a, out, ht, ht_host = self._device_args(x, n_frames, hop, out, in_off0, out_off0, hop_tab, state, load_state,
+                                                out_len)
+        return TimePar(self, a, out, ht_host, n_segments, warmup, warm_hop, keep=(x, ht, state))
+
+    def add_tail(self, out, pos, tail):
+        """out[l][pos + i] += tail[l][i]: another block's final overlap tail onto the head of this block's output."""
+        import torch
+        assert tail.is_cuda and tail.dtype == torch.float64 and tail.is_contiguous() and tail.shape == (out.shape[0], self.n)
+        _check(_load().tsb_add_tail(self.ctx.h, self.h, out.data_ptr(), out.stride(0), out.shape[1], int(pos),
+                                    tail.data_ptr(), out.shape[0]))
+
     def render_host(self, x, n_frames, hop, out=None, in_off0=2048, out_off0=0, hop_tab=None, state=None,
                     load_state=False, out_len=None):
         """Host path (tsb_chain_render_host): x / out are numpy arrays or CPU torch tensors (pinned or not);
@@ -294,6 +354,45 @@ class Plan:
     def close(self):
         if getattr(self, "h", None):
             _load().tsb_plan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class TimePar:
+    """tsb_timepar_*: pre-pass (block totals) and render of one block of frames cut into time segments."""
+
+    def __init__(self, plan, args, out, ht_host, n_segments, warmup, warm_hop, keep):
+        self.plan, self.args, self.out, self._keep, self._ht = plan, args, out, keep, ht_host
+        h = C.c_void_p()
+        _check(_load().tsb_timepar_create(plan.ctx.h, plan.h, C.byref(args), None if ht_host is None else ht_host.ctypes.data,
+                                          int(n_segments), int(bool(warmup)), int(warm_hop), C.byref(h)))
+        self.h = h
+
+    @property
+    def segments(self):
+        return _load().tsb_timepar_segments(self.h)
+
+    def prepass(self):
+        """-> (block_total, block_last_phase), CUDA float64 [lanes, n/2]"""
+        import torch
+        lanes, m = self.out.shape[0], self.plan.n // 2
+        tot = torch.zeros((lanes, m), dtype=torch.float64, device=self.out.device)
+        last = torch.zeros((lanes, m), dtype=torch.float64, device=self.out.device)
+        _check(_load().tsb_timepar_prepass(self.h, tot.data_ptr(), last.data_ptr()))
+        return tot, last
+
+    def render(self):
+        _check(_load().tsb_timepar_render(self.h))
+        return self.out
+
+    def close(self):
+        if getattr(self, "h", None):
+            _load().tsb_timepar_destroy(self.h)
             self.h = None
 
     def __del__(self):

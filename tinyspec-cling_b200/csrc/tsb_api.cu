@@ -272,6 +272,7 @@ static ChainArgs to_args(const tsb_chain_args *a) {
     k.hop = a->hop; k.hop_tab = a->hop_tab;
     k.st_last_phase = a->state_last_phase; k.st_phase_sum = a->state_phase_sum; k.st_ola = a->state_ola;
     k.load_state = a->load_state; k.lanes = a->lanes;
+    k.n_seg = 0; k.seg_tab = nullptr; k.mode = 0; k.st_warm_phase = nullptr;
     return k;
 }
 TSB_API int tsb_chain_render(tsb_ctx *c, tsb_plan *p, const tsb_chain_args *a) {
@@ -492,6 +493,202 @@ TSB_API int tsb_overlap_add(tsb_ctx *c, const double *frame, int64_t lanes, int6
     CU(op_overlap_add(frame, osize, hop, out, out_stride, out_len, out_off, tail_in, tail_out, tail_cap, tail_len, keep, lanes,
                       c->stream));
     *new_tail_len = keep;
+    c->launches++;
+    return TSB_OK;
+}
+
+// ---- time-parallel rendering ----
+struct tsb_timepar {
+    tsb_ctx *ctx;
+    tsb_plan *plan;
+    tsb_chain_args args;
+    int n_seg, warmup, warm_hop;
+    size_t lanes, n, m;
+    std::vector<long long> seg;  // [n_seg][6]
+    long long *d_seg = nullptr, *d_pos = nullptr;
+    double *d_last = nullptr, *d_sum = nullptr, *d_warm = nullptr, *d_ola = nullptr;
+    bool prepassed = false;
+};
+TSB_API int tsb_timepar_destroy(tsb_timepar *tp) {
+    if (!tp) return TSB_OK;
+    cudaSetDevice(tp->ctx->device);
+    cudaStreamSynchronize(tp->ctx->stream);
+    cudaFree(tp->d_seg);
+    cudaFree(tp->d_pos);
+    cudaFree(tp->d_last);
+    cudaFree(tp->d_sum);
+    cudaFree(tp->d_warm);
+    cudaFree(tp->d_ola);
+    delete tp;
+    return TSB_OK;
+}
+TSB_API int tsb_timepar_segments(tsb_timepar *tp) { return tp ? tp->n_seg : 0; }
+TSB_API int tsb_timepar_create(tsb_ctx *c, tsb_plan *p, const tsb_chain_args *a, const int32_t *host_hop_tab,
+                               int32_t n_segments, int32_t warmup, int32_t warm_hop, tsb_timepar **out) {
+    if (!c || !p || !out) return fail(TSB_EINVAL, "null argument");
+    int r = check_args(a);
+    if (r) return r;
+    if ((a->hop_tab == nullptr) != (host_hop_tab == nullptr)) return fail(TSB_EINVAL, "host_hop_tab must mirror args->hop_tab");
+    if (p->desc.program != TSB_PROG_PV_SHIFT && warmup) return fail(TSB_EINVAL, "warm-up frames only exist for the phase vocoder");
+    if (warmup && (warm_hop < 0 || a->in_off0 - warm_hop < 0)) return fail(TSB_EINVAL, "warm-up frame would start before the input");
+    CU(cudaSetDevice(c->device));
+    tsb_timepar *tp = new tsb_timepar();
+    tp->ctx = c;
+    tp->plan = p;
+    tp->args = *a;
+    tp->warmup = warmup;
+    tp->warm_hop = warm_hop;
+    tp->lanes = (size_t)a->lanes;
+    tp->n = p->desc.n;
+    tp->m = tp->n / 2;
+    const int64_t F = a->n_frames;
+    // every segment must emit at least n samples, so that a tail never reaches past the next segment
+    int64_t hop_min = a->hop;
+    if (host_hop_tab) {
+        hop_min = host_hop_tab[0];
+        for (int64_t f = 0; f < F; f++) hop_min = host_hop_tab[f] < hop_min ? host_hop_tab[f] : hop_min;
+    }
+    int64_t min_frames = hop_min > 0 ? ((int64_t)tp->n + hop_min - 1) / hop_min : F;
+    if (min_frames < 1) min_frames = 1;
+    int64_t nseg = n_segments < 1 ? 1 : n_segments;
+    if (F > 0 && nseg > F / min_frames) nseg = F / min_frames;
+    if (nseg < 1) nseg = 1;
+    tp->n_seg = (int)nseg;
+    tp->seg.assign(6 * nseg, 0);
+    std::vector<long long> pos(nseg, 0);
+    int64_t in_off = a->in_off0, out_off = a->out_off0, f = 0;
+    for (int64_t s = 0; s < nseg; s++) {
+        int64_t cnt = F / nseg + (s < F % nseg ? 1 : 0);
+        long long *t = &tp->seg[6 * s];
+        t[0] = f;
+        t[1] = cnt;
+        t[2] = in_off;
+        t[3] = out_off;
+        t[4] = s == 0 ? (warmup ? 1 : 0) : 1;
+        t[5] = s == 0 ? warm_hop : (host_hop_tab ? host_hop_tab[f - 1] : a->hop);
+        pos[s] = out_off;
+        for (int64_t i = 0; i < cnt; i++) {
+            int64_t h = host_hop_tab ? host_hop_tab[f + i] : a->hop;
+            in_off += h;
+            out_off += h;
+        }
+        f += cnt;
+    }
+    size_t rows = (size_t)nseg * tp->lanes;
+    cudaError_t e = cudaMalloc(&tp->d_seg, tp->seg.size() * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&tp->d_pos, (size_t)nseg * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&tp->d_last, rows * tp->m * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&tp->d_sum, rows * tp->m * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&tp->d_warm, rows * tp->m * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&tp->d_ola, rows * tp->n * 8);
+    if (e != cudaSuccess) {
+        tsb_timepar_destroy(tp);
+        return fail(TSB_ENOMEM, "time-parallel scratch: %s", cudaGetErrorString(e));
+    }
+    CU(cudaMemcpyAsync(tp->d_seg, tp->seg.data(), tp->seg.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(tp->d_pos, pos.data(), (size_t)nseg * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *out = tp;
+    return TSB_OK;
+}
+static int timepar_launch(tsb_timepar *tp, int mode) {
+    tsb_ctx *c = tp->ctx;
+    tsb_plan *p = tp->plan;
+    ChainArgs k = to_args(&tp->args);
+    k.n_seg = tp->n_seg;
+    k.seg_tab = tp->d_seg;
+    k.mode = mode;
+    k.st_last_phase = tp->d_last;
+    k.st_phase_sum = tp->d_sum;
+    k.st_ola = tp->d_ola;
+    k.st_warm_phase = tp->d_warm;
+    k.load_state = 1;
+    chain_launch_fn fn = launcher(p->log2n);
+    if (!fn) return fail(TSB_EUNSUPPORTED, "no kernel for frame size 2^%d", p->log2n);
+    const void *tb = p->desc.precision == TSB_F32 ? (const void *)&p->t32 : (const void *)&p->t64;
+    cudaError_t e = fn(p->desc.precision, p->desc.program, tb, k, c->stream);
+    if (e != cudaSuccess) return fail(TSB_ECUDA, "chain kernel launch: %s", cudaGetErrorString(e));
+    c->launches++;
+    return TSB_OK;
+}
+// row block 0 of a scratch array <- the caller's state (or zeros)
+static int seed_rows(tsb_timepar *tp, double *dst, const double *user, size_t width) {
+    size_t bytes = tp->lanes * width * 8;
+    if (user && tp->args.load_state) CU(cudaMemcpyAsync(dst, user, bytes, cudaMemcpyDeviceToDevice, tp->ctx->stream));
+    else CU(cudaMemsetAsync(dst, 0, bytes, tp->ctx->stream));
+    return TSB_OK;
+}
+TSB_API int tsb_timepar_prepass(tsb_timepar *tp, double *block_total, double *block_last_phase) {
+    if (!tp) return fail(TSB_EINVAL, "null argument");
+    tsb_ctx *c = tp->ctx;
+    CU(cudaSetDevice(c->device));
+    const size_t rows = (size_t)tp->n_seg * tp->lanes;
+    if (tp->plan->desc.program != TSB_PROG_PV_SHIFT || tp->args.n_frames == 0 || tp->lanes == 0) {
+        // nothing crosses frames but the overlap tail: no pre-pass needed
+        if (block_total) CU(cudaMemsetAsync(block_total, 0, tp->lanes * tp->m * 8, c->stream));
+        if (block_last_phase) CU(cudaMemsetAsync(block_last_phase, 0, tp->lanes * tp->m * 8, c->stream));
+        CU(cudaMemsetAsync(tp->d_sum, 0, rows * tp->m * 8, c->stream));
+        tp->prepassed = true;
+        return TSB_OK;
+    }
+    CU(cudaMemsetAsync(tp->d_last, 0, rows * tp->m * 8, c->stream));
+    int r = seed_rows(tp, tp->d_last, tp->args.state_last_phase, tp->m);
+    if (r) return r;
+    if ((r = timepar_launch(tp, 1))) return r;
+    if (block_total) CU(op_timepar_scan(tp->d_sum, nullptr, block_total, (long long)tp->lanes, (long long)tp->m, tp->n_seg, c->stream));
+    if (block_last_phase)
+        CU(cudaMemcpyAsync(block_last_phase, tp->d_last + (rows - tp->lanes) * tp->m, tp->lanes * tp->m * 8,
+                           cudaMemcpyDeviceToDevice, c->stream));
+    tp->prepassed = true;
+    return TSB_OK;
+}
+TSB_API int tsb_timepar_render(tsb_timepar *tp) {
+    if (!tp) return fail(TSB_EINVAL, "null argument");
+    if (!tp->prepassed) return fail(TSB_EINVAL, "tsb_timepar_render before tsb_timepar_prepass");
+    tsb_ctx *c = tp->ctx;
+    CU(cudaSetDevice(c->device));
+    if (tp->args.n_frames == 0 || tp->lanes == 0) return TSB_OK;
+    const size_t rows = (size_t)tp->n_seg * tp->lanes;
+    const tsb_chain_args &a = tp->args;
+    const double *base = (a.state_phase_sum && a.load_state) ? a.state_phase_sum : nullptr;
+    CU(op_timepar_scan(tp->d_sum, base, nullptr, (long long)tp->lanes, (long long)tp->m, tp->n_seg, c->stream));
+    int r = seed_rows(tp, tp->d_last, a.state_last_phase, tp->m);  // segment 0 without warm-up starts from the caller's phases
+    if (r) return r;
+    CU(cudaMemsetAsync(tp->d_ola, 0, rows * tp->n * 8, c->stream));
+    if ((r = seed_rows(tp, tp->d_ola, a.state_ola, tp->n))) return r;
+    if ((r = timepar_launch(tp, 0))) return r;
+    if (tp->n_seg > 1)
+        CU(op_add_tails(a.out, tp->plan->desc.precision == TSB_F64, a.out_stride, a.out_len, tp->d_pos + 1, tp->n_seg - 1,
+                        tp->d_ola, (long long)tp->lanes, (long long)tp->n, c->stream));
+    c->launches += tp->n_seg > 1 ? 2 : 1;
+    const size_t lastrow = rows - tp->lanes;
+    if (a.state_last_phase) CU(cudaMemcpyAsync(a.state_last_phase, tp->d_last + lastrow * tp->m, tp->lanes * tp->m * 8, cudaMemcpyDeviceToDevice, c->stream));
+    if (a.state_phase_sum) CU(cudaMemcpyAsync(a.state_phase_sum, tp->d_sum + lastrow * tp->m, tp->lanes * tp->m * 8, cudaMemcpyDeviceToDevice, c->stream));
+    if (a.state_ola) CU(cudaMemcpyAsync(a.state_ola, tp->d_ola + lastrow * tp->n, tp->lanes * tp->n * 8, cudaMemcpyDeviceToDevice, c->stream));
+    tp->prepassed = false;
+    return TSB_OK;
+}
+TSB_API int tsb_chain_render_timepar(tsb_ctx *c, tsb_plan *p, const tsb_chain_args *a, const int32_t *host_hop_tab,
+                                     int32_t n_segments) {
+    tsb_timepar *tp = nullptr;
+    int r = tsb_timepar_create(c, p, a, host_hop_tab, n_segments, 0, 0, &tp);
+    if (r) return r;
+    r = tsb_timepar_prepass(tp, nullptr, nullptr);
+    if (!r) r = tsb_timepar_render(tp);
+    tsb_timepar_destroy(tp);
+    return r;
+}
+TSB_API int tsb_add_tail(tsb_ctx *c, tsb_plan *p, void *out, int64_t out_stride, int64_t out_len, int64_t pos,
+                         const double *tail, int64_t lanes) {
+    if (!c || !p || !out || !tail) return fail(TSB_EINVAL, "null argument");
+    CU(cudaSetDevice(c->device));
+    long long *d_pos = nullptr;
+    CU(cudaMallocAsync((void **)&d_pos, 8, c->stream));
+    long long hp = pos;
+    CU(cudaMemcpyAsync(d_pos, &hp, 8, cudaMemcpyHostToDevice, c->stream));
+    CU(op_add_tails(out, p->desc.precision == TSB_F64, out_stride, out_len, d_pos, 1, tail, lanes, (long long)p->desc.n, c->stream));
+    CU(cudaFreeAsync(d_pos, c->stream));
+    CU(cudaStreamSynchronize(c->stream));  // &hp
     c->launches++;
     return TSB_OK;
 }

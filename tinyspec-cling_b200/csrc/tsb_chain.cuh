@@ -89,6 +89,21 @@ struct ChainArgs {
     double *st_ola;        // [lanes][N]   overlap tail relative to the next output position
     int load_state;        // 0: start from zero (PhaseVocoder::reset, empty atmp)
     int lanes;
+    // ---- time segments (tsb_timepar_*): CTA b works on segment b / lanes of lane b % lanes; state rows are
+    // [segment * lanes + lane].  seg_tab[s] = {first frame (index into hop_tab), frames, I of the first frame,
+    // P of the first frame, warm-up}: with warm-up the CTA first analyses the frame BEFORE the segment
+    // (input offset I - prev_hop) only to obtain last_phase.
+    int n_seg;                 // 0 or 1: the whole launch is one segment described by the fields above
+    const long long *seg_tab;  // [n_seg][6]: first_frame, n_frames, in_off0, out_off0, warm-up flag, hop of the frame before
+    int mode;                  // 0: full chain; 1: pre-pass (analysis + shift + increment accumulation only, no output)
+    double *st_warm_phase;     // pre-pass out / main in: [rows][M] last_phase after the warm-up frame (segments with warm-up)
+};
+
+// What one CTA works on.
+struct SegInfo {
+    long long first_frame, n_frames, in_off0, out_off0;
+    int warm, warm_hop;
+    long long row;  // state row = segment * lanes + lane
 };
 
 template <typename real>
@@ -177,6 +192,7 @@ struct PvMath<double> {
         // frequency_to_phase, pv.hpp:46-48: 2.0*M_PI*freq/RATE*hop()
         inc = mul_rn(mul_rn(mul_rn(2.0 * TSB_PI, freq), tb.inv_rate), tb.hop);
     }
+    static TSB_HD double accumulate(double phase_sum, double inc) { return add_rn(phase_sum, inc); }
     static TSB_HD cpx<double> synth(double amp, double inc, double &phase_sum) {
         phase_sum = add_rn(phase_sum, inc);  // pv.hpp:34 — never wrapped
         double s, c;
@@ -219,6 +235,7 @@ struct PvMath<float> {
         double wrapped = fma(-TSB_PI, (double)qpd, delta);
         inc = tb.ratio * (expect + wrapped);
     }
+    static TSB_HD double accumulate(double phase_sum, double inc) { return phase_sum + inc; }
     static TSB_HD cpx<float> synth(float amp, double inc, double &phase_sum) {
         phase_sum += inc;
         // fp64 range reduction to [-pi/4, pi/4] + quadrant, then fp32 polynomials
@@ -289,48 +306,82 @@ struct Chain {
     static constexpr int inv_buf(int p) { return (p & 1) ? (INV0 ^ 1) : INV0; }
 
     // ------------------------------------------------------------------ state in / out
-    static TSB_HD void load_state(int tid, int lane, Smem &sm, Regs &rg, const ChainArgs &a) {
+    // state rows: registers <-> [row][M] arrays, thread `tid` owning bins (k, M-k) of its slots
+    static TSB_HD void regs_from(int tid, const double *arr, long long row, real *dst_real, double *dst_dbl) {
+#pragma unroll
+        for (int i = 0; i < S; i++) {
+            int k = tid + T * i;
+            if (k < HALF) {
+                int kb = k == 0 ? HALF : M - k;
+                if (dst_real) {
+                    dst_real[2 * i] = (real)arr[row * M + k];
+                    dst_real[2 * i + 1] = (real)arr[row * M + kb];
+                } else {
+                    dst_dbl[2 * i] = arr[row * M + k];
+                    dst_dbl[2 * i + 1] = arr[row * M + kb];
+                }
+            }
+        }
+    }
+    static TSB_HD void regs_to(int tid, double *arr, long long row, const real *src_real, const double *src_dbl) {
+#pragma unroll
+        for (int i = 0; i < S; i++) {
+            int k = tid + T * i;
+            if (k < HALF) {
+                int kb = k == 0 ? HALF : M - k;
+                arr[row * M + k] = src_real ? (double)src_real[2 * i] : src_dbl[2 * i];
+                arr[row * M + kb] = src_real ? (double)src_real[2 * i + 1] : src_dbl[2 * i + 1];
+            }
+        }
+    }
+    static TSB_HD void load_state(int tid, Smem &sm, Regs &rg, const ChainArgs &a, const SegInfo &sg) {
         for (int i = 0; i < 2 * S; i++) {
             rg.last_phase[i] = 0;
             rg.phase_sum[i] = 0;
         }
         bool ld = a.load_state != 0;
-        if (PROG == PROG_PV_SHIFT && ld && a.st_last_phase && a.st_phase_sum) {
-#pragma unroll
-            for (int i = 0; i < S; i++) {
-                int k = tid + T * i;
-                if (k < HALF) {
-                    int kb = k == 0 ? HALF : M - k;
-                    rg.last_phase[2 * i] = (real)a.st_last_phase[(long long)lane * M + k];
-                    rg.last_phase[2 * i + 1] = (real)a.st_last_phase[(long long)lane * M + kb];
-                    rg.phase_sum[2 * i] = a.st_phase_sum[(long long)lane * M + k];
-                    rg.phase_sum[2 * i + 1] = a.st_phase_sum[(long long)lane * M + kb];
-                }
+        if (PROG == PROG_PV_SHIFT && ld) {
+            if (a.mode == 1) {
+                // pre-pass: increments are summed from zero; last_phase comes from the caller only for a
+                // segment that starts the render (no warm-up frame)
+                if (!sg.warm && a.st_last_phase) regs_from(tid, a.st_last_phase, sg.row, rg.last_phase, nullptr);
+            } else {
+                if (sg.warm && a.st_warm_phase) regs_from(tid, a.st_warm_phase, sg.row, rg.last_phase, nullptr);
+                else if (a.st_last_phase) regs_from(tid, a.st_last_phase, sg.row, rg.last_phase, nullptr);
+                if (a.st_phase_sum) regs_from(tid, a.st_phase_sum, sg.row, nullptr, rg.phase_sum);
             }
         }
         for (int i = tid; i < N; i += T) {
             real v = 0;
-            if (ld && a.st_ola) v = (real)a.st_ola[(long long)lane * N + i];
-            sm.ola[(int)((a.out_off0 + i) & (N - 1))] = v;
+            if (ld && a.st_ola && a.mode == 0) v = (real)a.st_ola[sg.row * N + i];
+            sm.ola[(int)((sg.out_off0 + i) & (N - 1))] = v;
         }
     }
-    static TSB_HD void store_state(int tid, int lane, Smem &sm, Regs &rg, const ChainArgs &a, long long out_pos) {
+    static TSB_HD void store_state(int tid, Smem &sm, Regs &rg, const ChainArgs &a, const SegInfo &sg, long long out_pos) {
         if (PROG == PROG_PV_SHIFT && a.st_last_phase && a.st_phase_sum) {
-#pragma unroll
-            for (int i = 0; i < S; i++) {
-                int k = tid + T * i;
-                if (k < HALF) {
-                    int kb = k == 0 ? HALF : M - k;
-                    a.st_last_phase[(long long)lane * M + k] = (double)rg.last_phase[2 * i];
-                    a.st_last_phase[(long long)lane * M + kb] = (double)rg.last_phase[2 * i + 1];
-                    a.st_phase_sum[(long long)lane * M + k] = rg.phase_sum[2 * i];
-                    a.st_phase_sum[(long long)lane * M + kb] = rg.phase_sum[2 * i + 1];
-                }
-            }
+            regs_to(tid, a.st_last_phase, sg.row, rg.last_phase, nullptr);
+            regs_to(tid, a.st_phase_sum, sg.row, nullptr, rg.phase_sum);
         }
-        if (a.st_ola)
-            for (int i = tid; i < N; i += T)
-                a.st_ola[(long long)lane * N + i] = (double)sm.ola[(int)((out_pos + i) & (N - 1))];
+        if (a.st_ola && a.mode == 0)
+            for (int i = tid; i < N; i += T) a.st_ola[sg.row * N + i] = (double)sm.ola[(int)((out_pos + i) & (N - 1))];
+    }
+    // pre-pass "synthesis": only the phase accumulation of rtlib/pv.hpp:34 (same order of additions as the
+    // full kernel), so that a segment's total increment per bin is known before anything is synthesised
+    static TSB_HD void phase_pv_accumulate(int tid, Smem &sm, Regs &rg, const Tables &tb) {
+        const double *inc_x = xch_inc(sm);
+        const real *amp_x = xch_amp(sm);
+#pragma unroll
+        for (int i = 0; i < S; i++) {
+            int k = tid + T * i;
+            if (HALF % T != 0 && k >= HALF) break;
+            int kb = is_special(i, k) ? HALF : M - k;
+            real amp;
+            double inc;
+            gather_bin(amp_x, inc_x, tb, k, amp, inc);
+            rg.phase_sum[2 * i] = PvMath<real>::accumulate(rg.phase_sum[2 * i], inc);
+            gather_bin(amp_x, inc_x, tb, kb, amp, inc);
+            rg.phase_sum[2 * i + 1] = PvMath<real>::accumulate(rg.phase_sum[2 * i + 1], inc);
+        }
     }
 
     // ------------------------------------------------------------------ input ring
@@ -642,28 +693,63 @@ struct InvPasses<CH, END, END> {
     static TSB_HD void run(Exec &, int, typename CH::Smem &, const typename CH::Tables &, const ChainArgs &, long long, int) {}
 };
 
-// The whole launch for one lane.  `Exec::each(f)` runs f(tid, regs) for every thread of the lane and
+// The whole launch for one (segment, lane).  `Exec::each(f)` runs f(tid, regs) for every thread of the lane and
 // ends with a barrier: on the device that is { f(threadIdx.x, regs); __syncthreads(); }, in the CPU
 // test harness a loop over tid.  Barriers per frame: 2*PASSES + (PV ? 2 : 1).
 template <class CH, class Exec>
-TSB_HD void run_lane(Exec &ex, int lane, typename CH::Smem &sm, const typename CH::Tables &tb, const ChainArgs &a) {
+TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const typename CH::Tables &tb, const ChainArgs &a) {
     using Regs = typename CH::Regs;
     constexpr int N = CH::N;
     static_assert(CH::PASSES >= 2, "frame sizes below 64 are not instantiated");
-    long long in_off = a.in_off0, out_pos = a.out_off0;
+    SegInfo sg;
+    if (a.n_seg > 1 || a.seg_tab) {
+        const long long *t = a.seg_tab + 6 * (long long)seg;
+        sg.first_frame = TSB_LDG(&t[0]);
+        sg.n_frames = TSB_LDG(&t[1]);
+        sg.in_off0 = TSB_LDG(&t[2]);
+        sg.out_off0 = TSB_LDG(&t[3]);
+        sg.warm = (int)TSB_LDG(&t[4]);
+        sg.warm_hop = (int)TSB_LDG(&t[5]);
+    } else {
+        sg.first_frame = 0;
+        sg.n_frames = a.n_frames;
+        sg.in_off0 = a.in_off0;
+        sg.out_off0 = a.out_off0;
+        sg.warm = 0;
+        sg.warm_hop = 0;
+    }
+    sg.row = (long long)seg * a.lanes + lane;
+    const bool prepass = CH::IS_PV && a.mode == 1;
+    const bool warm = prepass && sg.warm;
+    // a warm-up frame is the frame before the segment: it only primes last_phase
+    long long in_off = warm ? sg.in_off0 - sg.warm_hop : sg.in_off0, out_pos = sg.out_off0;
     ex.each([&](int tid, Regs &rg) {
-        CH::load_state(tid, lane, sm, rg, a);
+        CH::load_state(tid, sm, rg, a, sg);
         CH::ring_fill(tid, lane, sm, a, in_off, N);
         CH::ring_wait();
     });
-    for (long long f = 0; f < a.n_frames; f++) {
-        int hop = a.hop_tab ? TSB_LDG(&a.hop_tab[f]) : a.hop;
+    const long long total = sg.n_frames + (warm ? 1 : 0);
+    for (long long ff = 0; ff < total; ff++) {
+        const bool is_warm = warm && ff == 0;
+        const long long f = sg.first_frame + ff - (warm ? 1 : 0);  // index into hop_tab (the warm-up frame uses warm_hop)
+        int hop = is_warm ? sg.warm_hop : (a.hop_tab ? TSB_LDG(&a.hop_tab[f]) : a.hop);
         // slots [in_off, in_off+hop) are dead once pass 0 has read the frame
-        int cnt = f + 1 < a.n_frames ? (hop < N ? hop : N) : 0;
+        int cnt = ff + 1 < total ? (hop < N ? hop : N) : 0;
         long long first = in_off + hop + N - cnt;
         FwdPasses<CH, 0, CH::PASSES>::run(ex, lane, sm, tb, a, in_off, first, cnt);
         if (CH::IS_PV) {
             ex.each([&](int tid, Regs &rg) { CH::phase_pv_analyze(tid, sm, rg, tb); });
+            if (prepass) {
+                if (is_warm) {
+                    if (a.st_warm_phase)
+                        ex.each([&](int tid, Regs &rg) { CH::regs_to(tid, a.st_warm_phase, sg.row, rg.last_phase, nullptr); });
+                } else {
+                    ex.each([&](int tid, Regs &rg) { CH::phase_pv_accumulate(tid, sm, rg, tb); });
+                }
+                ex.each([&](int, Regs &) { CH::ring_wait(); });
+                in_off += hop;
+                continue;
+            }
             ex.each([&](int tid, Regs &rg) { CH::phase_pv_synth(tid, sm, rg, tb); });
         } else {
             ex.each([&](int tid, Regs &) { CH::phase_gain(tid, sm, tb); });
@@ -672,7 +758,7 @@ TSB_HD void run_lane(Exec &ex, int lane, typename CH::Smem &sm, const typename C
         in_off += hop;
         out_pos += hop;
     }
-    ex.each([&](int tid, Regs &rg) { CH::store_state(tid, lane, sm, rg, a, out_pos); });
+    ex.each([&](int tid, Regs &rg) { CH::store_state(tid, sm, rg, a, sg, out_pos); });
 }
 
 }  // namespace tsb

@@ -48,7 +48,9 @@ chain_kernel(const ChainTables<real> tb, const ChainArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typename CH::Smem &sm = *reinterpret_cast<typename CH::Smem *>(smem_raw);
     DevExec<CH> ex;
-    for (int lane = blockIdx.x; lane < a.lanes; lane += gridDim.x) run_lane<CH>(ex, lane, sm, tb, a);
+    const int nseg = a.n_seg > 1 ? a.n_seg : 1;
+    for (long long b = blockIdx.x; b < (long long)a.lanes * nseg; b += gridDim.x)
+        run_lane<CH>(ex, (int)(b % a.lanes), (int)(b / a.lanes), sm, tb, a);
 }
 
 template <typename real, int LOG2N, int PROG>
@@ -61,7 +63,8 @@ static cudaError_t launch(const void *tables, const ChainArgs &a, cudaStream_t s
     e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     if (a.lanes <= 0 || a.n_frames <= 0) return cudaSuccess;
-    kern<<<a.lanes, CH::T, smem, stream>>>(*reinterpret_cast<const ChainTables<real> *>(tables), a);
+    const long long ctas = (long long)a.lanes * (a.n_seg > 1 ? a.n_seg : 1);
+    kern<<<(unsigned)ctas, CH::T, smem, stream>>>(*reinterpret_cast<const ChainTables<real> *>(tables), a);
     return cudaGetLastError();
 }
 

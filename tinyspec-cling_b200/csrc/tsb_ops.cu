@@ -413,6 +413,58 @@ cudaError_t op_pv_shift(const double *tmp, double *pvdata, const double *fn_freq
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ time-parallel PV bookkeeping
+// Per (lane, bin): turn the segments' total increments sum[s] into each segment's starting phase_sum, in
+// segment order — carry_0 = base, carry_{s+1} = carry_s + total_s — the same left-to-right additions the
+// sequential render performs, regrouped per segment.  total_out (optional) receives the sum over all segments.
+__global__ void timepar_scan_kernel(double *sum, const double *base, double *total_out, long long lanes, long long m,
+                                    int n_seg) {
+    long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= lanes * m) return;
+    double c = base ? base[idx] : 0.0, tot = 0.0;
+    for (int s = 0; s < n_seg; s++) {
+        double t = sum[(long long)s * lanes * m + idx];
+        if (total_out) tot = __dadd_rn(tot, t);
+        else {
+            sum[(long long)s * lanes * m + idx] = c;
+            c = __dadd_rn(c, t);
+        }
+    }
+    if (total_out) total_out[idx] = tot;
+}
+cudaError_t op_timepar_scan(double *sum, const double *base, double *total_out, long long lanes, long long m, int n_seg,
+                            cudaStream_t st) {
+    if (lanes * m == 0) return cudaSuccess;
+    const int TB = 128;
+    timepar_scan_kernel<<<(unsigned)((lanes * m + TB - 1) / TB), TB, 0, st>>>(sum, base, total_out, lanes, m, n_seg);
+    return cudaGetLastError();
+}
+// out[lane][pos + i] += tail[lane][i] (i < n): a segment's overlap tail lands on the head of the next segment's
+// range.  One thread per sample, fixed order: deterministic, no atomics.
+template <typename real>
+__global__ void add_tail_kernel(real *out, long long out_stride, long long out_len, const long long *pos_tab, int n_tails,
+                                const double *tails, long long lanes, long long n) {
+    long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= (long long)n_tails * lanes * n) return;
+    long long i = idx % n, l = (idx / n) % lanes, t = idx / (n * lanes);
+    long long p = pos_tab[t] + i;
+    double v = tails[(t * lanes + l) * n + i];
+    if (v != 0.0 && p < out_len) out[l * out_stride + p] += (real)v;
+}
+cudaError_t op_add_tails(void *out, int is_f64, long long out_stride, long long out_len, const long long *pos_tab,
+                         int n_tails, const double *tails, long long lanes, long long n, cudaStream_t st) {
+    long long work = (long long)n_tails * lanes * n;
+    if (work == 0) return cudaSuccess;
+    const int TB = 256;
+    if (is_f64)
+        add_tail_kernel<double><<<(unsigned)((work + TB - 1) / TB), TB, 0, st>>>((double *)out, out_stride, out_len, pos_tab,
+                                                                                  n_tails, tails, lanes, n);
+    else
+        add_tail_kernel<float><<<(unsigned)((work + TB - 1) / TB), TB, 0, st>>>((float *)out, out_stride, out_len, pos_tab,
+                                                                                 n_tails, tails, lanes, n);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ frame gather, tinyspec.cpp:151-157
 // frame[l][i] = (double) in[l][in_off + i], zero past the end of the input (planar float rows -> planar double).
 __global__ void gather_kernel(const float *in, long long in_stride, long long in_len, long long in_off, double *frame,
