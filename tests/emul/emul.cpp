@@ -82,6 +82,38 @@ extern "C" int emul_chain_render(int precision, int log2n, int program, int win_
     return program == PROG_PV_SHIFT ? by_size<double, PROG_PV_SHIFT>(log2n, d, a) : by_size<double, PROG_GAIN>(log2n, d, a);
 }
 
+// Same with the time-segment controls of ChainArgs: one segment, optional warm-up frame, pre-pass mode.
+extern "C" int emul_chain_render_ex(int precision, int log2n, int program, int win_in, int win_out, double hop_d,
+                                    double rate, double ratio, const double *fn_bins, const double *gain,
+                                    const float *in, long long in_stride, long long in_len, void *out,
+                                    long long out_stride, long long out_len, long long n_frames, long long in_off0,
+                                    long long out_off0, int hop, const int *hop_tab, double *st_last_phase,
+                                    double *st_phase_sum, double *st_ola, int load_state, int lanes, int mode, int warm,
+                                    int warm_hop, double *st_warm_phase) {
+    PlanDesc d;
+    d.n = 1 << log2n;
+    d.program = program;
+    d.win_in = win_in;
+    d.win_out = win_out;
+    d.hop = hop_d;
+    d.rate = rate;
+    d.ratio = ratio;
+    d.fn_bins = fn_bins;
+    d.gain = gain;
+    long long seg[6] = {0, n_frames, in_off0, out_off0, warm, warm_hop};
+    ChainArgs a;
+    a.in = in; a.in_stride = in_stride; a.in_len = in_len;
+    a.out = out; a.out_stride = out_stride; a.out_len = out_len;
+    a.n_frames = n_frames; a.in_off0 = in_off0; a.out_off0 = out_off0;
+    a.hop = hop; a.hop_tab = hop_tab;
+    a.st_last_phase = st_last_phase; a.st_phase_sum = st_phase_sum; a.st_ola = st_ola;
+    a.load_state = load_state; a.lanes = lanes;
+    a.n_seg = 1; a.seg_tab = seg; a.mode = mode; a.st_warm_phase = st_warm_phase;
+    if (precision == 0)
+        return program == PROG_PV_SHIFT ? by_size<float, PROG_PV_SHIFT>(log2n, d, a) : by_size<float, PROG_GAIN>(log2n, d, a);
+    return program == PROG_PV_SHIFT ? by_size<double, PROG_PV_SHIFT>(log2n, d, a) : by_size<double, PROG_GAIN>(log2n, d, a);
+}
+
 // M-point complex forward FFT through the kernel's Stockham passes (for unit tests of tsb_math.cuh)
 template <typename real, int LOG2M>
 static void fft_only(const double *in, double *out) {

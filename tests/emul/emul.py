@@ -22,6 +22,7 @@ def lib():
                                                                              C.c_longlong, C.c_int, P, P, P, P,
                                                                              C.c_int, C.c_int]
         _lib.emul_fft.argtypes = [C.c_int, C.c_int, P, P]
+        _lib.emul_chain_render_ex.argtypes = _lib.emul_chain_render.argtypes + [C.c_int, C.c_int, C.c_int, P]
     return _lib
 
 
@@ -56,3 +57,45 @@ def chain_render(x, n, hop, n_frames, precision="f64", program="pv", ratio=2.0, 
                                 int(load), lanes)
     assert r == 0
     return out, state
+
+
+class ReplayBackend:
+    """CPU stand-in for the device side of tinyspec-cling_b200/shard.py (kernel phases replayed thread by thread),
+    so the multi-rank orchestration can be tested with gloo in a container without a GPU."""
+
+    def __init__(self, n, hop, ratio, precision="f64", rate=48000.0):
+        self.n, self.hop, self.ratio, self.precision, self.rate = n, hop, ratio, precision, rate
+
+    def _call(self, x, n_frames, in_off0, out_len, mode, warm, state, warm_phase, load):
+        lanes, L = x.shape
+        dt = np.float64 if self.precision == "f64" else np.float32
+        out = np.zeros((lanes, max(out_len, 1)), dt)
+        r = lib().emul_chain_render_ex(1 if self.precision == "f64" else 0, int(np.log2(self.n)), 0, 2, 2, float(self.hop),
+                                       self.rate, self.ratio, None, None, _p(x), L, L, _p(out), out.shape[1], out_len,
+                                       n_frames, in_off0, 0, int(self.hop), None, _p(state["last_phase"]),
+                                       _p(state["phase_sum"]), _p(state["ola"]), int(load), lanes, mode, int(warm),
+                                       int(self.hop), _p(warm_phase))
+        assert r == 0
+        return out
+
+    def prepass(self, x, n_frames, in_off0, warm):
+        lanes = x.shape[0]
+        m = self.n // 2
+        self._x, self._nf, self._off, self._warm = np.ascontiguousarray(x, np.float32), n_frames, in_off0, warm
+        self._wp = np.zeros((lanes, m))
+        st = dict(last_phase=np.zeros((lanes, m)), phase_sum=np.zeros((lanes, m)), ola=np.zeros((lanes, self.n)))
+        self._call(self._x, n_frames, in_off0, 0, 1, warm, st, self._wp, True)
+        return st["phase_sum"].copy()
+
+    def render(self, carry):
+        lanes = self._x.shape[0]
+        m = self.n // 2
+        st = dict(last_phase=np.zeros((lanes, m)), phase_sum=np.ascontiguousarray(carry, np.float64).copy(),
+                  ola=np.zeros((lanes, self.n)))
+        out = self._call(self._x, self._nf, self._off, self._nf * self.hop, 0, self._warm, st, self._wp, True)
+        return out, st["ola"].copy()
+
+    def add_tail(self, out, tail):
+        w = min(self.n, out.shape[1])
+        out[:, :w] += tail[:, :w].astype(out.dtype)
+        return out
