@@ -303,7 +303,7 @@ def main():
         ofps = world * S_other * F / (oms * 1e-3)
         line["other_precision"] = {"dtype": other, "value": ofps, "unit": "frames/s", "ms_per_step": oms,
                                    "streams_per_gpu": S_other,
-                                   "roofline_frac": ofps * CH * b_alg(other) / 1e9 / peak}
+                                   "roofline_frac": ofps / world * CH * b_alg(other) / 1e9 / peak}
         if world == 1:
             plan1 = tsb200.Plan(ctx, N_FRAME, precision=args.precision, program="pv", hop=HOP, rate=RATE, ratio=SHIFT)
             x1 = x_all[:CH].contiguous()

@@ -91,6 +91,15 @@ def granular_case(name, samples, vary, n_first=0, stream=0):
     print(name, "frames", len(r["t"]), "stream", r["stream"].shape)
 
 
+def bytebeat_case(name, n, ch, frames):
+    r = run_ref("ref_bytebeat_tap", dict(TSREF_N=n, TSREF_CH=ch, TSREF_MAX_FRAMES=frames, TSREF_DUMP_FIRST=frames),
+                [("t", np.float64), ("out", np.float64)])
+    k = len(r["t"])
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), meta=np.array([n, ch, frames], np.int64), t=r["t"],
+                        out=r["out"].reshape(k, ch, n), stream=r["stream"].reshape(-1, ch))
+    print(name, "frames dumped", k, "stream", r["stream"].shape)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL)
@@ -107,3 +116,4 @@ if __name__ == "__main__":
     filter_case("filter_lp_n512_stereo", 512, 0.5, 2, 12000, 1, 3, 16)
     granular_case("granular_1800", 60000, 0)
     granular_case("granular_vary", 60000, 1, n_first=64, stream=2)
+    bytebeat_case("bytebeat_n2048", 2048, 2, 12)

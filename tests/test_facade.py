@@ -34,15 +34,15 @@ def test_reference_hacks_compile_unchanged(hack, tmp_path):
 
 
 def test_examples_build():
-    for h in ("pitchshift_cfg1", "passthrough_cfg2", "lowpass_raw"):
+    for h in ("pitchshift_cfg1", "passthrough_cfg2", "lowpass_raw", "granular", "bytebeat"):
         assert os.path.exists(build(os.path.join(EX, h + ".cpp")))
 
 
-def render(binary, *args, lanes=1, f64=False):
+def render(binary, *args, lanes=1, f64=False, env=None):
     with tempfile.TemporaryDirectory() as d:
         out = os.path.join(d, "o.bin")
         cmd = [binary, "--out", out, "--timing"] + [str(a) for a in args] + (["--out-f64"] if f64 else [])
-        r = subprocess.run(cmd, capture_output=True, text=True)
+        r = subprocess.run(cmd, capture_output=True, text=True, env=dict(os.environ, **(env or {})))
         if r.returncode != 0:
             return r, None, None
         info = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
@@ -113,3 +113,49 @@ def test_fused_mode_refuses_raw_access_loudly():
     b = build(os.path.join(EX, "lowpass_raw.cpp"))
     r, _, _ = render(b, "--seconds", 0.2)
     assert r.returncode != 0 and "immediate" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,env", [("granular_1800", {}),
+                                      ("granular_vary", {"GRANULAR_VARY": "1", "GRANULAR_NFIRST": "64", "GRANULAR_STREAM": "2"})])
+def test_immediate_granular_cfg4_bit_exact(golden, name, env):
+    """cfg4: per-frame varying frame size (64..8192 or 1800) and hop, out.size != in.size.  Gather, window_hann
+    and the float32 overlap-add run on the device; the result is the compiled reference's stream bit for bit."""
+    from oracle import orc
+    g = golden(name)
+    samples, _, _, stream = (int(v) for v in g["meta"])
+    b = build(os.path.join(EX, "granular.cpp"))
+    x = orc.gen_signal(stream, 2, samples)
+    with tempfile.TemporaryDirectory() as d:
+        inp = os.path.join(d, "in.f32")
+        np.ascontiguousarray(x.T).tofile(inp)
+        r, info, y = render(b, "--mode", "immediate", "--in", inp, lanes=2, env=env)
+    assert r.returncode == 0, r.stderr
+    assert info["frames"] == len(g["t"])
+    assert y.shape[1] == g["stream"].shape[0]
+    assert np.array_equal(y.T, g["stream"])
+
+
+@pytest.mark.gpu
+def test_immediate_bytebeat_cfg5_pattern(golden):
+    """cfg5 pattern at a small size: Hermitian spectrum of 2*frame points -> frft(-1) on the device -> triangular
+    window (hack code) -> overlap-add; against the compiled reference's stream."""
+    g = golden("bytebeat_n2048")
+    n, ch, frames = (int(v) for v in g["meta"])
+    b = build(os.path.join(EX, "bytebeat.cpp"))
+    r, info, y = render(b, "--mode", "immediate", "--max-frames", frames, "--seconds", 100, lanes=ch,
+                        env={"BYTEBEAT_N": str(n), "BYTEBEAT_CH": str(ch)})
+    assert r.returncode == 0, r.stderr
+    assert info["frames"] == frames and y.shape[1] == g["stream"].shape[0]
+    d = np.abs(y.T - g["stream"])
+    assert d.max() <= 1.2e-7 * np.abs(g["stream"]).max() and (d == 0).mean() > 0.99
+
+
+@pytest.mark.gpu
+def test_immediate_bytebeat_full_size_runs():
+    """The real cfg5 size: frame 65536 -> inverse FFT of 131072 points (four-step), 4 channels, 3 frames."""
+    b = build(os.path.join(EX, "bytebeat.cpp"))
+    r, info, y = render(b, "--mode", "immediate", "--max-frames", 3, "--seconds", 100, lanes=4,
+                        env={"BYTEBEAT_N": "65536", "BYTEBEAT_CH": "4"})
+    assert r.returncode == 0, r.stderr
+    assert info["frames"] == 3 and y.shape[1] == 3 * 16384 and np.isfinite(y).all() and np.abs(y).max() > 0
