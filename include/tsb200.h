@@ -118,9 +118,11 @@ typedef struct tsb_chain_args {
 } tsb_chain_args;
 int tsb_chain_render(tsb_ctx *ctx, tsb_plan *plan, const tsb_chain_args *args);
 
-/* Same, with HOST buffers (in, out, hop_tab, state_* are host pointers): uploads the input, runs the
- * chain, downloads the output and the state, and returns when the result is in `out`.  Pinned host
- * buffers make the copies asynchronous; pageable ones work too. */
+/* Same, with HOST buffers (in, out, hop_tab, state_* are host pointers): returns when the result is in `out`.
+ * Large batches are cut into lane chunks whose upload, chain kernel and download overlap (separate copy engines
+ * per direction, one stream per chunk); per-lane results are bit-identical to tsb_chain_render.  Pinned host
+ * buffers make the copies asynchronous; pageable ones work too.  Whole rows are copied, so `out` rows come back
+ * as the device computed them: zero outside the emitted range. */
 int tsb_chain_render_host(tsb_ctx *ctx, tsb_plan *plan, const tsb_chain_args *args);
 
 /* ---- time-parallel rendering ------------------------------------------------------------------ */

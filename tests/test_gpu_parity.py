@@ -183,6 +183,19 @@ def test_host_path_matches_device_path(env):
     assert np.array_equal(sa["phase_sum"], sb["phase_sum"])
 
 
+@pytest.mark.parametrize("n,hr,samples,ch", [(256, 0.25, 2200000, 40), (512, 0.2003, 900000, 150)])
+def test_host_path_pipelined_chunks_bit_identical(env, n, hr, samples, ch):
+    """Large enough (> 1 GB of rows) for several pipelined lane chunks, constant and fractional hop: same bits
+    as one launch over device-resident buffers."""
+    x = np.random.default_rng(3).uniform(-0.5, 0.5, (samples, ch)).astype(np.float32)
+    a, F, sa = run_pv(env, x, n, hr, 1.5, "f32", host=False)
+    b, F2, sb = run_pv(env, x, n, hr, 1.5, "f32", host=True)
+    assert F == F2 and F > 1500
+    assert np.array_equal(a, b)
+    for k in ("last_phase", "phase_sum", "ola"):
+        assert np.array_equal(sa[k], sb[k])
+
+
 def test_many_lanes_match_single_lane(env):
     """Lanes are independent: a batch of 300 streams gives, lane by lane, what each gives alone."""
     torch, tsb, orc = env["torch"], env["tsb"], env["orc"]

@@ -291,56 +291,116 @@ TSB_API int tsb_chain_render(tsb_ctx *c, tsb_plan *p, const tsb_chain_args *a) {
     return TSB_OK;
 }
 
+// Host-buffer render.  Lanes are independent and a lane's rows are contiguous in the caller's arrays, so the
+// batch is cut into lane chunks and pipelined: chunk k's input upload (one contiguous copy), its chain kernel on
+// its own stream, and its output download overlap the other chunks' (uploads and downloads use separate copy
+// engines; the chunk kernels share the SMs).  Row-strided 2-D copies of time blocks were measured 10-20x slower
+// than contiguous ones on this platform (tools/pcie_probe.py), hence lanes, not time, are the pipeline axis.
+// Per-lane results are bit-identical to tsb_chain_render.
 TSB_API int tsb_chain_render_host(tsb_ctx *c, tsb_plan *p, const tsb_chain_args *a) {
     if (!c || !p) return fail(TSB_EINVAL, "null context / plan");
     int r = check_args(a);
     if (r) return r;
     if (a->lanes == 0 || a->n_frames == 0) return TSB_OK;
     CU(cudaSetDevice(c->device));
-    const size_t n = p->desc.n, m = n / 2, lanes = (size_t)a->lanes;
+    const int64_t n = p->desc.n, m = n / 2, lanes = a->lanes, F = a->n_frames;
     const size_t osz = p->desc.precision == TSB_F32 ? 4 : 8;
-    const size_t in_bytes = lanes * (size_t)a->in_stride * 4, out_bytes = lanes * (size_t)a->out_stride * osz;
-    struct Dev {
+    const size_t in_bytes = (size_t)lanes * a->in_stride * 4, out_bytes = (size_t)lanes * a->out_stride * osz;
+    // chunks: enough lanes each to keep copies large (>= 256 MB) and at most 8 chunks
+    int64_t nc = (int64_t)((in_bytes + out_bytes) / (512ull << 20));
+    nc = nc < 1 ? 1 : (nc > 8 ? 8 : nc);
+    if (nc > lanes) nc = lanes;
+    struct Res {
         std::vector<void *> ptrs;
-        ~Dev() { for (void *q : ptrs) cudaFree(q); }
+        std::vector<cudaEvent_t> evs;
+        std::vector<cudaStream_t> streams;
+        ~Res() {
+            for (cudaEvent_t e : evs) cudaEventDestroy(e);
+            for (cudaStream_t s : streams) cudaStreamDestroy(s);
+            for (void *q : ptrs) cudaFree(q);
+        }
         void *get(size_t bytes) {
             void *q = nullptr;
             if (cudaMalloc(&q, bytes ? bytes : 16) != cudaSuccess) return nullptr;
             ptrs.push_back(q);
             return q;
         }
-    } dev;
-    tsb_chain_args d = *a;
-    float *din = (float *)dev.get(in_bytes);
-    void *dout = dev.get(out_bytes);
+        cudaEvent_t ev() {
+            cudaEvent_t e = nullptr;
+            cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+            evs.push_back(e);
+            return e;
+        }
+        cudaStream_t stream() {
+            cudaStream_t s = nullptr;
+            cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+            streams.push_back(s);
+            return s;
+        }
+    } res;
+    float *din = (float *)res.get(in_bytes);
+    char *dout = (char *)res.get(out_bytes);
     if (!din || !dout) return fail(TSB_ENOMEM, "device allocation of %zu + %zu bytes failed", in_bytes, out_bytes);
-    CU(cudaMemcpyAsync(din, a->in, in_bytes, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemsetAsync(dout, 0, out_bytes, c->stream));
-    d.in = din;
-    d.out = dout;
+    int32_t *dhops = nullptr;
     if (a->hop_tab) {
-        int32_t *dh = (int32_t *)dev.get((size_t)a->n_frames * 4);
-        if (!dh) return fail(TSB_ENOMEM, "device allocation failed");
-        CU(cudaMemcpyAsync(dh, a->hop_tab, (size_t)a->n_frames * 4, cudaMemcpyHostToDevice, c->stream));
-        d.hop_tab = dh;
+        dhops = (int32_t *)res.get((size_t)F * 4);
+        if (!dhops) return fail(TSB_ENOMEM, "device allocation failed");
+        CU(cudaMemcpyAsync(dhops, a->hop_tab, (size_t)F * 4, cudaMemcpyHostToDevice, c->stream));
     }
     double *host_state[3] = {a->state_last_phase, a->state_phase_sum, a->state_ola};
-    double **dev_state[3] = {&d.state_last_phase, &d.state_phase_sum, &d.state_ola};
-    size_t st_bytes[3] = {lanes * m * 8, lanes * m * 8, lanes * n * 8};
+    double *dev_state[3] = {nullptr, nullptr, nullptr};
+    size_t st_w[3] = {(size_t)m, (size_t)m, (size_t)n};
     for (int i = 0; i < 3; i++) {
         if (!host_state[i]) continue;
-        double *q = (double *)dev.get(st_bytes[i]);
-        if (!q) return fail(TSB_ENOMEM, "device allocation failed");
-        if (a->load_state) CU(cudaMemcpyAsync(q, host_state[i], st_bytes[i], cudaMemcpyHostToDevice, c->stream));
-        *dev_state[i] = q;
+        dev_state[i] = (double *)res.get((size_t)lanes * st_w[i] * 8);
+        if (!dev_state[i]) return fail(TSB_ENOMEM, "device allocation failed");
+        if (a->load_state) CU(cudaMemcpyAsync(dev_state[i], host_state[i], (size_t)lanes * st_w[i] * 8, cudaMemcpyHostToDevice, c->stream));
     }
-    r = tsb_chain_render(c, p, &d);
-    if (r) return r;
-    CU(cudaMemcpyAsync(a->out, dout, out_bytes, cudaMemcpyDeviceToHost, c->stream));
-    for (int i = 0; i < 3; i++)
-        if (host_state[i]) CU(cudaMemcpyAsync(host_state[i], *dev_state[i], st_bytes[i], cudaMemcpyDeviceToHost, c->stream));
+    cudaEvent_t setup = res.ev();
+    CU(cudaEventRecord(setup, c->stream));
+    cudaStream_t s_in = res.stream(), s_out = res.stream();
+    CU(cudaStreamWaitEvent(s_in, setup, 0));
+    cudaStream_t saved = c->stream;
+    int rc = TSB_OK;
+    int64_t l0 = 0;
+    for (int64_t k = 0; k < nc && rc == TSB_OK; k++) {
+        int64_t cnt = lanes / nc + (k < lanes % nc ? 1 : 0);
+        cudaEvent_t in_done = res.ev(), k_done = res.ev();
+        cudaStream_t s_k = res.stream();
+        cudaError_t e = cudaMemcpyAsync(din + (size_t)l0 * a->in_stride, a->in + (size_t)l0 * a->in_stride,
+                                        (size_t)cnt * a->in_stride * 4, cudaMemcpyHostToDevice, s_in);
+        if (e == cudaSuccess) e = cudaEventRecord(in_done, s_in);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s_k, in_done, 0);
+        if (e != cudaSuccess) { rc = fail(TSB_ECUDA, "upload: %s", cudaGetErrorString(e)); break; }
+        tsb_chain_args d = *a;
+        d.in = din + (size_t)l0 * a->in_stride;
+        d.out = dout + (size_t)l0 * a->out_stride * osz;
+        d.hop_tab = dhops;
+        d.state_last_phase = dev_state[0] ? dev_state[0] + (size_t)l0 * m : nullptr;
+        d.state_phase_sum = dev_state[1] ? dev_state[1] + (size_t)l0 * m : nullptr;
+        d.state_ola = dev_state[2] ? dev_state[2] + (size_t)l0 * n : nullptr;
+        d.lanes = (int32_t)cnt;
+        e = cudaMemsetAsync((void *)d.out, 0, (size_t)cnt * a->out_stride * osz, s_k);
+        if (e != cudaSuccess) { rc = fail(TSB_ECUDA, "memset: %s", cudaGetErrorString(e)); break; }
+        c->stream = s_k;  // launch this chunk on its own stream
+        rc = tsb_chain_render(c, p, &d);
+        c->stream = saved;
+        if (rc) break;
+        e = cudaEventRecord(k_done, s_k);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s_out, k_done, 0);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync((char *)a->out + (size_t)l0 * a->out_stride * osz, dout + (size_t)l0 * a->out_stride * osz,
+                                (size_t)cnt * a->out_stride * osz, cudaMemcpyDeviceToHost, s_out);
+        for (int i = 0; i < 3 && e == cudaSuccess; i++)
+            if (host_state[i])
+                e = cudaMemcpyAsync(host_state[i] + (size_t)l0 * st_w[i], dev_state[i] + (size_t)l0 * st_w[i],
+                                    (size_t)cnt * st_w[i] * 8, cudaMemcpyDeviceToHost, s_out);
+        if (e != cudaSuccess) { rc = fail(TSB_ECUDA, "download: %s", cudaGetErrorString(e)); break; }
+        l0 += cnt;
+    }
+    for (cudaStream_t s : res.streams) cudaStreamSynchronize(s);
     CU(cudaStreamSynchronize(c->stream));
-    return TSB_OK;
+    return rc;
 }
 
 // ---- the helpers one by one ----
