@@ -2,6 +2,8 @@
 // One CTA per lane; the CTA walks the lane's frames in order (see tsb_chain.cuh for the phases).
 #include "tsb_launch.hpp"
 
+#include <cstdlib>
+
 #ifndef TSB_LOG2N
 #error "compile with -DTSB_LOG2N=<6..13>"
 #endif
@@ -41,6 +43,9 @@ constexpr int min_blocks() {
     return b < 1 ? 1 : (b > 32 ? 32 : b);
 }
 
+template <class CH>
+constexpr int default_carveout_kb() { return 228; }
+
 template <typename real, int LOG2N, int PROG>
 __global__ void __launch_bounds__(Chain<real, LOG2N, PROG>::T, min_blocks<Chain<real, LOG2N, PROG>>())
 chain_kernel(const ChainTables<real> tb, const ChainArgs a) {
@@ -60,7 +65,13 @@ static cudaError_t launch(const void *tables, const ChainArgs &a, cudaStream_t s
     size_t smem = sizeof(typename CH::Smem);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    // Shared memory and L1 share 228 KB per SM.  The constant tables (twiddles, windows, per-bin phase
+    // constants, shift map: ~20 KB fp32 / ~34 KB fp64 at N=1024) are read through L1 every frame, so the
+    // carve-out leaves them room instead of packing the last CTA in (TSB_CARVEOUT_KB overrides, for tuning).
+    int carve_kb = default_carveout_kb<CH>();
+    if (const char *ev = getenv("TSB_CARVEOUT_KB")) carve_kb = atoi(ev);
+    int pct = carve_kb >= 228 ? 100 : (carve_kb * 100 + 227) / 228;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     if (e != cudaSuccess) return e;
     if (a.lanes <= 0 || a.n_frames <= 0) return cudaSuccess;
     const long long ctas = (long long)a.lanes * (a.n_seg > 1 ? a.n_seg : 1);
