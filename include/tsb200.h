@@ -157,6 +157,22 @@ int tsb_chain_render_timepar(tsb_ctx *ctx, tsb_plan *plan, const tsb_chain_args 
 int tsb_add_tail(tsb_ctx *ctx, tsb_plan *plan, void *out, int64_t out_stride, int64_t out_len, int64_t pos,
                  const double *tail, int64_t lanes);
 
+/* ---- chunked streaming front end ---------------------------------------------------------------- */
+/* What tinyspec.cpp's JACK callback + worker do for a live stream (tinyspec.cpp:205-239 feeding :113-203), without
+ * the threads: every call appends `len` new input samples per lane (one audio period) and returns the output
+ * samples that became final, for a plan rendered with next_hop_samples(n, hop) on every frame.  The first frame
+ * needs 2048 + n samples, so early calls return nothing — that latency is the reference's.
+ * Frames are scheduled exactly as tsb_schedule_const does for the concatenated input, and the PV state and
+ * overlap tail stay on the device between calls: any chunking gives bit-identical output to one whole render. */
+typedef struct tsb_stream tsb_stream;
+int tsb_stream_create(tsb_ctx *ctx, tsb_plan *plan, int32_t lanes, double hop, double rate, tsb_stream **stream);
+/* host_in: [lanes][in_stride] float32, `len` valid samples per row; host_out: [lanes][out_stride] float32/float64
+ * (the plan's precision) receiving *out_len samples per row (never more than out_cap: size it >= len + n). */
+int tsb_stream_process(tsb_stream *stream, const float *host_in, int64_t in_stride, int64_t len, void *host_out,
+                       int64_t out_stride, int64_t out_cap, int64_t *out_len);
+int64_t tsb_stream_frames(tsb_stream *stream);  /* frames rendered so far */
+int tsb_stream_destroy(tsb_stream *stream);
+
 /* ---- the helpers one by one ("immediate mode") ------------------------------------------------ */
 /* One call = one helper of the reference's rtinc/ library, on DEVICE buffers laid out like Buf<T>
  * (planar [channel][size]; FFTBuf interleaved re,im; PVBuf interleaved amp,freq), double precision,

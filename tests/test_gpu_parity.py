@@ -62,6 +62,9 @@ CASES = [  # n, hop_ratio, shift, channels, samples, stream
     (512, 0.2003, 0.75, 1, 16000, 3),   # fractional hop: computed_hop alternates 102/103
     (2048, 0.125, 2.0, 2, 30000, 0),
     (8192, 0.25, 1.5, 1, 60000, 2),     # largest fused frame
+    (64, 1.6, 1.5, 2, 9000, 1),         # hop larger than the frame (tinyspec.cpp:184-191), fractional
+    (128, 1.0, 2.0, 2, 9000, 1),        # hop equal to the frame: no overlap at all
+    (256, 0.3, 1.5, 2, 9000, 1),        # odd hops 76/77
 ]
 
 
@@ -290,3 +293,28 @@ def test_timepar_two_blocks_like_two_gpus(env):
     plan.add_tail(out, int(sch["out_off"][F0]), st0["ola"])
     torch.cuda.synchronize()
     assert np.abs(out.cpu().numpy() - whole.cpu().numpy()).max() <= 1e-9 * float(whole.abs().max())
+
+
+@pytest.mark.parametrize("n,hr,precision", [(1024, 0.25, "f64"), (512, 0.2003, "f32"), (64, 1.6, "f64")])
+def test_streaming_front_end_bit_identical(env, n, hr, precision):
+    """Audio periods of arbitrary, varying length pushed one by one (tsb_stream_process) give exactly the samples
+    of one whole render, and nothing comes out before the reference's start-up latency (2048 + frame samples)."""
+    torch, tsb, orc = env["torch"], env["tsb"], env["orc"]
+    ch, samples = 2, 40000
+    x = orc.gen_signal(4, ch, samples)
+    whole, F, _ = run_pv(env, x, n, hr, 1.5, precision)
+    plan = tsb.Plan(env["ctx"], n, precision=precision, program="pv", hop=n * hr, ratio=1.5)
+    st = tsb.Stream(plan, ch, n * hr)
+    rng = np.random.default_rng(0)
+    pos, parts, first_output_at = 0, [], None
+    while pos < samples:
+        k = int(min(samples - pos, rng.choice([1, 64, 256, 1024, 4096, 777])))
+        y = st.process(np.ascontiguousarray(x[pos:pos + k].T))
+        pos += k
+        if y.shape[1] and first_output_at is None:
+            first_output_at = pos
+        parts.append(y)
+    got = np.concatenate(parts, axis=1)
+    assert st.frames == F and got.shape == whole.shape
+    assert np.array_equal(got, whole)
+    assert first_output_at >= 2048 + n

@@ -80,3 +80,16 @@ def test_gain_chain(n, filt):
     assert maxrel(out, ref["ola64"][:out.shape[1]].T) < 1e-13
     out, _ = emul.chain_render(x.T, n, n // 4, F, precision="f32", program="gain", gain=gain)
     assert rmsrel(out, ref["ola64"][:out.shape[1]].T) < 1e-5
+
+
+@pytest.mark.parametrize("n,hr,shift,samples", [(64, 1.6, 1.5, 9000), (128, 1.0, 2.0, 9000), (256, 0.3, 1.5, 9000),
+                                                (64, 0.01, 1.2, 2600)])
+def test_pv_chain_hop_edge_cases(n, hr, shift, samples):
+    """hop larger than the frame (tinyspec.cpp:184-191), hop equal to the frame, fractional hops, hops of 0/1."""
+    x = orc.gen_signal(1, 2, samples)
+    ref = orc.render_pv(x, n, hr, shift, want_tables=True)
+    tabs, F = ref["tables"], ref["frames"]
+    const = bool(np.all(tabs["hop"] == tabs["hop"][0]))
+    out, _ = emul.chain_render(x.T, n, int(tabs["hop"][0]), F, precision="f64", ratio=shift, hop_d=n * hr,
+                               hop_tab=None if const else tabs["hop"])
+    assert maxrel(out, ref["ola64"][:out.shape[1]].T) < 1e-11

@@ -80,6 +80,11 @@ def _load():
     L.tsb_timepar_destroy.argtypes = [P]
     L.tsb_chain_render_timepar.argtypes = [P, P, C.POINTER(_ChainArgs), P, I32]
     L.tsb_add_tail.argtypes = [P, P, P, I64, I64, I64, P, I64]
+    L.tsb_stream_create.argtypes = [P, P, I32, D, D, C.POINTER(P)]
+    L.tsb_stream_process.argtypes = [P, P, I64, I64, P, I64, I64, C.POINTER(I64)]
+    L.tsb_stream_frames.argtypes = [P]
+    L.tsb_stream_frames.restype = I64
+    L.tsb_stream_destroy.argtypes = [P]
     _lib = L
     return L
 
@@ -393,6 +398,42 @@ class TimePar:
     def close(self):
         if getattr(self, "h", None):
             _load().tsb_timepar_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Stream:
+    """tsb_stream_*: chunked (audio-period) front end; process(chunk) -> the samples that became final."""
+
+    def __init__(self, plan, lanes, hop, rate=48000.0):
+        self.plan, self.lanes = plan, lanes
+        h = C.c_void_p()
+        _check(_load().tsb_stream_create(plan.ctx.h, plan.h, lanes, float(hop), float(rate), C.byref(h)))
+        self.h = h
+
+    def process(self, chunk):
+        """chunk: float32 [lanes, len] (numpy).  Returns [lanes, k] in the plan's precision, k >= 0."""
+        x = np.ascontiguousarray(chunk, np.float32)
+        assert x.ndim == 2 and x.shape[0] == self.lanes
+        cap = x.shape[1] + 2 * self.plan.n + 4096
+        out = np.zeros((self.lanes, cap), np.float64 if self.plan.precision == F64 else np.float32)
+        n = C.c_int64()
+        _check(_load().tsb_stream_process(self.h, x.ctypes.data, x.shape[1], x.shape[1], out.ctypes.data, cap, cap,
+                                          C.byref(n)))
+        return out[:, :n.value]
+
+    @property
+    def frames(self):
+        return _load().tsb_stream_frames(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            _load().tsb_stream_destroy(self.h)
             self.h = None
 
     def __del__(self):

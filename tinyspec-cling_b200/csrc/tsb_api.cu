@@ -752,3 +752,160 @@ TSB_API int tsb_add_tail(tsb_ctx *c, tsb_plan *p, void *out, int64_t out_stride,
     c->launches++;
     return TSB_OK;
 }
+
+// ---- chunked streaming front end ----
+struct tsb_stream {
+    tsb_ctx *ctx;
+    tsb_plan *plan;
+    int lanes;
+    double hop;
+    SchedState st;
+    int64_t pushed = 0;   // input samples received per lane
+    int64_t base = 0;     // absolute index of the first sample kept in d_in
+    int64_t cap = 0;      // samples per row of d_in
+    int64_t frames = 0;
+    float *d_in = nullptr;
+    void *d_out = nullptr;
+    int64_t out_cap = 0;
+    int32_t *d_hops = nullptr;
+    int64_t hops_cap = 0;
+    double *d_last = nullptr, *d_sum = nullptr, *d_ola = nullptr;
+    bool started = false;
+};
+TSB_API int tsb_stream_destroy(tsb_stream *s) {
+    if (!s) return TSB_OK;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    cudaFree(s->d_in);
+    cudaFree(s->d_out);
+    cudaFree(s->d_hops);
+    cudaFree(s->d_last);
+    cudaFree(s->d_sum);
+    cudaFree(s->d_ola);
+    delete s;
+    return TSB_OK;
+}
+TSB_API int64_t tsb_stream_frames(tsb_stream *s) { return s ? s->frames : 0; }
+TSB_API int tsb_stream_create(tsb_ctx *c, tsb_plan *p, int32_t lanes, double hop, double rate, tsb_stream **out) {
+    if (!c || !p || !out) return fail(TSB_EINVAL, "null argument");
+    if (lanes <= 0) return fail(TSB_EINVAL, "lanes must be positive");
+    if (hop < 0) return fail(TSB_EINVAL, "ignoring invalid hop: %g", hop);
+    CU(cudaSetDevice(c->device));
+    tsb_stream *s = new tsb_stream();
+    s->ctx = c;
+    s->plan = p;
+    s->lanes = lanes;
+    s->hop = hop;
+    s->st.rate = rate;
+    const size_t n = p->desc.n, m = n / 2;
+    cudaError_t e = cudaMalloc(&s->d_last, (size_t)lanes * m * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_sum, (size_t)lanes * m * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_ola, (size_t)lanes * n * 8);
+    if (e != cudaSuccess) {
+        tsb_stream_destroy(s);
+        return fail(TSB_ENOMEM, "stream state: %s", cudaGetErrorString(e));
+    }
+    *out = s;
+    return TSB_OK;
+}
+TSB_API int tsb_stream_process(tsb_stream *s, const float *host_in, int64_t in_stride, int64_t len, void *host_out,
+                               int64_t out_stride, int64_t out_cap, int64_t *out_len) {
+    if (!s || !out_len) return fail(TSB_EINVAL, "null argument");
+    if (len < 0 || (len > 0 && !host_in)) return fail(TSB_EINVAL, "bad input chunk");
+    tsb_ctx *c = s->ctx;
+    CU(cudaSetDevice(c->device));
+    const int64_t n = s->plan->desc.n, lanes = s->lanes;
+    const size_t osz = s->plan->desc.precision == TSB_F32 ? 4 : 8;
+    *out_len = 0;
+    // append the chunk to the pending input (rows hold absolute samples [base, pushed))
+    int64_t have = s->pushed - s->base, need = have + len;
+    if (need > s->cap) {
+        int64_t cap = need + (need >> 1) + 2 * n + 4096;
+        cap = (cap + 3) & ~(int64_t)3;
+        float *nd = nullptr;
+        cudaError_t e = cudaMalloc(&nd, (size_t)lanes * cap * 4);
+        if (e != cudaSuccess) return fail(TSB_ENOMEM, "stream input buffer: %s", cudaGetErrorString(e));
+        if (have > 0)
+            CU(cudaMemcpy2DAsync(nd, (size_t)cap * 4, s->d_in, (size_t)s->cap * 4, (size_t)have * 4, (size_t)lanes,
+                                 cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(s->d_in);
+        s->d_in = nd;
+        s->cap = cap;
+    }
+    if (len > 0)
+        CU(cudaMemcpy2DAsync(s->d_in + have, (size_t)s->cap * 4, host_in, (size_t)in_stride * 4, (size_t)len * 4, (size_t)lanes,
+                             cudaMemcpyHostToDevice, c->stream));
+    s->pushed += len;
+    // frames that can run now (tinyspec.cpp:142-149 on the concatenated input)
+    int64_t out0 = s->st.out_pos;
+    std::vector<FrameRec> fr = schedule_const(s->st, s->pushed, (uint32_t)n, s->hop, -1);
+    if (!fr.empty()) {
+        int64_t total = s->st.out_pos - out0;
+        if (total > out_cap) return fail(TSB_EINVAL, "out_cap %lld too small for %lld finished samples", (long long)out_cap, (long long)total);
+        if (total > s->out_cap) {
+            cudaFree(s->d_out);
+            s->d_out = nullptr;
+            int64_t cap = total + (total >> 1) + 1024;
+            cudaError_t e = cudaMalloc(&s->d_out, (size_t)lanes * cap * osz);
+            if (e != cudaSuccess) return fail(TSB_ENOMEM, "stream output buffer: %s", cudaGetErrorString(e));
+            s->out_cap = cap;
+        }
+        if ((int64_t)fr.size() > s->hops_cap) {
+            cudaFree(s->d_hops);
+            s->d_hops = nullptr;
+            s->hops_cap = (int64_t)fr.size() * 2 + 64;
+            cudaError_t e = cudaMalloc(&s->d_hops, (size_t)s->hops_cap * 4);
+            if (e != cudaSuccess) return fail(TSB_ENOMEM, "stream hop table: %s", cudaGetErrorString(e));
+        }
+        std::vector<int32_t> hops(fr.size());
+        for (size_t i = 0; i < fr.size(); i++) hops[i] = fr[i].hop;
+        CU(cudaMemcpyAsync(s->d_hops, hops.data(), hops.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        tsb_chain_args a;
+        memset(&a, 0, sizeof a);
+        a.in = s->d_in;
+        a.in_stride = s->cap;
+        a.in_len = s->pushed - s->base;
+        a.out = s->d_out;
+        a.out_stride = s->out_cap;
+        a.out_len = total;
+        a.n_frames = (int64_t)fr.size();
+        a.in_off0 = fr[0].in_off - s->base;
+        a.out_off0 = 0;
+        a.hop = hops[0];
+        a.hop_tab = s->d_hops;
+        a.state_last_phase = s->d_last;
+        a.state_phase_sum = s->d_sum;
+        a.state_ola = s->d_ola;
+        a.load_state = s->started ? 1 : 0;
+        a.lanes = (int32_t)lanes;
+        int r = tsb_chain_render(c, s->plan, &a);
+        if (r) return r;
+        s->started = true;
+        s->frames += (int64_t)fr.size();
+        if (total > 0)
+            CU(cudaMemcpy2DAsync(host_out, (size_t)out_stride * osz, s->d_out, (size_t)s->out_cap * osz, (size_t)total * osz,
+                                 (size_t)lanes, cudaMemcpyDeviceToHost, c->stream));
+        *out_len = total;
+        // drop what no later frame can read: the next frame starts at in_pos + computed_hop >= in_pos
+        int64_t keep_from = s->st.in_pos;
+        if (keep_from > s->base) {
+            int64_t left = s->pushed - keep_from;
+            CU(cudaStreamSynchronize(c->stream));
+            if (left > 0) {
+                // rows overlap themselves when shifting left: go through the output buffer's neighbour-free scratch
+                float *tmp = nullptr;
+                CU(cudaMalloc(&tmp, (size_t)lanes * left * 4));
+                CU(cudaMemcpy2DAsync(tmp, (size_t)left * 4, s->d_in + (keep_from - s->base), (size_t)s->cap * 4, (size_t)left * 4,
+                                     (size_t)lanes, cudaMemcpyDeviceToDevice, c->stream));
+                CU(cudaMemcpy2DAsync(s->d_in, (size_t)s->cap * 4, tmp, (size_t)left * 4, (size_t)left * 4, (size_t)lanes,
+                                     cudaMemcpyDeviceToDevice, c->stream));
+                CU(cudaStreamSynchronize(c->stream));
+                cudaFree(tmp);
+            }
+            s->base = keep_from;
+        }
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    return TSB_OK;
+}
