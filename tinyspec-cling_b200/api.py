@@ -20,7 +20,8 @@ class TsbError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libtsb200.so")
+    # TSB200_LIB: load another build of the library (kernel tuning experiments)
+    return os.environ.get("TSB200_LIB") or os.path.join(_HERE, "libtsb200.so")
 
 
 class _PlanDesc(C.Structure):

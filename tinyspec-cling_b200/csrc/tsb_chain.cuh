@@ -49,6 +49,14 @@ inline long long d2ll_rn(double a) { return llrint(a); }
 
 #define TSB_PI 3.14159265358979323846 /* M_PI */
 
+// Compiler-level scheduling fence: keeps the unrolled per-slot bodies of the PV phases from being interleaved
+// into one long stretch whose live values exceed the register budget (spills cost more than the lost overlap).
+TSB_HD void sched_fence() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("" ::: "memory");
+#endif
+}
+
 // Tables built once per plan on the host (tsb_host.cpp) and kept in device memory.
 template <typename real>
 struct ChainTables {
@@ -267,7 +275,17 @@ struct Chain {
     static constexpr int N = 1 << LOG2N;
     static constexpr int LOG2M = LOG2N - 1;
     static constexpr int M = N / 2;
-    static constexpr int T = (N / 16) < 32 ? 32 : (N / 16);  // threads per lane
+    // Threads per lane: T0 = N/16 runs one radix-8 butterfly per thread and pass.  The fp64 PV kernel, whose
+    // time goes to per-bin double-precision atan2/sincos rather than to the FFT, uses 2*T0 threads: the extra
+    // warps only take part in the per-bin (PV, window, overlap-add) phases, which then own 4 bins per thread
+    // instead of 8 (measured +5 % at N=1024; fp32 is fastest at T0).  TSB_TMUL overrides, for tuning.
+    static constexpr int T0 = (N / 16) < 32 ? 32 : (N / 16);
+#ifdef TSB_TMUL
+    static constexpr int TMUL = (PROG == PROG_PV_SHIFT && N >= 256) ? TSB_TMUL : 1;
+#else
+    static constexpr int TMUL = (PROG == PROG_PV_SHIFT && sizeof(real) == 8 && N >= 256 && N <= 2048) ? 2 : 1;
+#endif
+    static constexpr int T = T0 * TMUL > 1024 ? 1024 : T0 * TMUL;
     static constexpr int HALF = M / 2;                       // split pairs (k, M-k), k < M/2
     static constexpr int S = (HALF + T - 1) / T;             // pair slots per thread
     static constexpr int PASSES = RadixPlan<LOG2M>::passes;
@@ -306,31 +324,29 @@ struct Chain {
     static constexpr int inv_buf(int p) { return (p & 1) ? (INV0 ^ 1) : INV0; }
 
     // ------------------------------------------------------------------ state in / out
-    // state rows: registers <-> [row][M] arrays, thread `tid` owning bins (k, M-k) of its slots
-    static TSB_HD void regs_from(int tid, const double *arr, long long row, real *dst_real, double *dst_dbl) {
+    // state rows: registers <-> [row][M] arrays, thread `tid` owning bins (k, M-k) of its slots.  The register
+    // arrays are passed by reference and indexed with unrolled constants so that they stay in registers.
+    template <typename V>
+    static TSB_HD void regs_from(int tid, const double *arr, long long row, V (&dst)[2 * S]) {
 #pragma unroll
         for (int i = 0; i < S; i++) {
             int k = tid + T * i;
             if (k < HALF) {
                 int kb = k == 0 ? HALF : M - k;
-                if (dst_real) {
-                    dst_real[2 * i] = (real)arr[row * M + k];
-                    dst_real[2 * i + 1] = (real)arr[row * M + kb];
-                } else {
-                    dst_dbl[2 * i] = arr[row * M + k];
-                    dst_dbl[2 * i + 1] = arr[row * M + kb];
-                }
+                dst[2 * i] = (V)arr[row * M + k];
+                dst[2 * i + 1] = (V)arr[row * M + kb];
             }
         }
     }
-    static TSB_HD void regs_to(int tid, double *arr, long long row, const real *src_real, const double *src_dbl) {
+    template <typename V>
+    static TSB_HD void regs_to(int tid, double *arr, long long row, const V (&src)[2 * S]) {
 #pragma unroll
         for (int i = 0; i < S; i++) {
             int k = tid + T * i;
             if (k < HALF) {
                 int kb = k == 0 ? HALF : M - k;
-                arr[row * M + k] = src_real ? (double)src_real[2 * i] : src_dbl[2 * i];
-                arr[row * M + kb] = src_real ? (double)src_real[2 * i + 1] : src_dbl[2 * i + 1];
+                arr[row * M + k] = (double)src[2 * i];
+                arr[row * M + kb] = (double)src[2 * i + 1];
             }
         }
     }
@@ -344,11 +360,11 @@ struct Chain {
             if (a.mode == 1) {
                 // pre-pass: increments are summed from zero; last_phase comes from the caller only for a
                 // segment that starts the render (no warm-up frame)
-                if (!sg.warm && a.st_last_phase) regs_from(tid, a.st_last_phase, sg.row, rg.last_phase, nullptr);
+                if (!sg.warm && a.st_last_phase) regs_from(tid, a.st_last_phase, sg.row, rg.last_phase);
             } else {
-                if (sg.warm && a.st_warm_phase) regs_from(tid, a.st_warm_phase, sg.row, rg.last_phase, nullptr);
-                else if (a.st_last_phase) regs_from(tid, a.st_last_phase, sg.row, rg.last_phase, nullptr);
-                if (a.st_phase_sum) regs_from(tid, a.st_phase_sum, sg.row, nullptr, rg.phase_sum);
+                if (sg.warm && a.st_warm_phase) regs_from(tid, a.st_warm_phase, sg.row, rg.last_phase);
+                else if (a.st_last_phase) regs_from(tid, a.st_last_phase, sg.row, rg.last_phase);
+                if (a.st_phase_sum) regs_from(tid, a.st_phase_sum, sg.row, rg.phase_sum);
             }
         }
         for (int i = tid; i < N; i += T) {
@@ -359,8 +375,8 @@ struct Chain {
     }
     static TSB_HD void store_state(int tid, Smem &sm, Regs &rg, const ChainArgs &a, const SegInfo &sg, long long out_pos) {
         if (PROG == PROG_PV_SHIFT && a.st_last_phase && a.st_phase_sum) {
-            regs_to(tid, a.st_last_phase, sg.row, rg.last_phase, nullptr);
-            regs_to(tid, a.st_phase_sum, sg.row, nullptr, rg.phase_sum);
+            regs_to(tid, a.st_last_phase, sg.row, rg.last_phase);
+            regs_to(tid, a.st_phase_sum, sg.row, rg.phase_sum);
         }
         if (a.st_ola && a.mode == 0)
             for (int i = tid; i < N; i += T) a.st_ola[sg.row * N + i] = (double)sm.ola[(int)((out_pos + i) & (N - 1))];
@@ -515,6 +531,7 @@ struct Chain {
             PvMath<real>::analyze(kb, Xb, rg.last_phase[2 * i + 1], tb, N, amp, inc, false);
             amp_x[kb] = amp;
             inc_x[kb] = inc;
+            sched_fence();
         }
     }
     // shift gather for destination bin k (rtlib/pv.hpp:70-78: amplitudes add in ascending source
@@ -564,6 +581,7 @@ struct Chain {
                 H[SW::f(0)] = mk<real>(z0, -z0);
                 H[SW::f(HALF)] = mk<real>((real)2 * Yb.x, (real)-2 * Yb.y);  // 2*Z[M/2], Z = conj(Y)
             }
+            sched_fence();
         }
     }
     // ------------------------------------------------------------------ gain program: split * g -> C2R pre
@@ -696,13 +714,10 @@ struct InvPasses<CH, END, END> {
 // The whole launch for one (segment, lane).  `Exec::each(f)` runs f(tid, regs) for every thread of the lane and
 // ends with a barrier: on the device that is { f(threadIdx.x, regs); __syncthreads(); }, in the CPU
 // test harness a loop over tid.  Barriers per frame: 2*PASSES + (PV ? 2 : 1).
-template <class CH, class Exec>
-TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const typename CH::Tables &tb, const ChainArgs &a) {
-    using Regs = typename CH::Regs;
-    constexpr int N = CH::N;
-    static_assert(CH::PASSES >= 2, "frame sizes below 64 are not instantiated");
+template <class CH>
+TSB_HD SegInfo seg_info(const ChainArgs &a, int lane, int seg) {
     SegInfo sg;
-    if (a.n_seg > 1 || a.seg_tab) {
+    if (a.seg_tab) {
         const long long *t = a.seg_tab + 6 * (long long)seg;
         sg.first_frame = TSB_LDG(&t[0]);
         sg.n_frames = TSB_LDG(&t[1]);
@@ -719,20 +734,40 @@ TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const t
         sg.warm_hop = 0;
     }
     sg.row = (long long)seg * a.lanes + lane;
-    const bool prepass = CH::IS_PV && a.mode == 1;
-    const bool warm = prepass && sg.warm;
-    // a warm-up frame is the frame before the segment: it only primes last_phase
-    long long in_off = warm ? sg.in_off0 - sg.warm_hop : sg.in_off0, out_pos = sg.out_off0;
-    ex.each([&](int tid, Regs &rg) {
-        CH::load_state(tid, sm, rg, a, sg);
-        CH::ring_fill(tid, lane, sm, a, in_off, N);
-        CH::ring_wait();
-    });
-    const long long total = sg.n_frames + (warm ? 1 : 0);
-    for (long long ff = 0; ff < total; ff++) {
+    return sg;
+}
+
+template <class CH, class Exec>
+TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const typename CH::Tables &tb, const ChainArgs &a) {
+    using Regs = typename CH::Regs;
+    constexpr int N = CH::N;
+    static_assert(CH::PASSES >= 2, "frame sizes below 64 are not instantiated");
+    // Only what the frame loop needs stays live across it (registers are what limits residency): the segment
+    // description is re-read from the argument block / table at the end.
+    long long in_off, out_pos;
+    int total;
+    const int *hop_tab;
+    bool prepass, warm;
+    int warm_hop;
+    {
+        SegInfo sg = seg_info<CH>(a, lane, seg);
+        prepass = CH::IS_PV && a.mode == 1;
+        warm = prepass && sg.warm;
+        warm_hop = sg.warm_hop;
+        // a warm-up frame is the frame before the segment: it only primes last_phase
+        in_off = warm ? sg.in_off0 - sg.warm_hop : sg.in_off0;
+        out_pos = sg.out_off0;
+        total = (int)sg.n_frames + (warm ? 1 : 0);
+        hop_tab = a.hop_tab ? a.hop_tab + sg.first_frame - (warm ? 1 : 0) : nullptr;  // indexed by ff below
+        ex.each([&](int tid, Regs &rg) {
+            CH::load_state(tid, sm, rg, a, sg);
+            CH::ring_fill(tid, lane, sm, a, in_off, N);
+            CH::ring_wait();
+        });
+    }
+    for (int ff = 0; ff < total; ff++) {
         const bool is_warm = warm && ff == 0;
-        const long long f = sg.first_frame + ff - (warm ? 1 : 0);  // index into hop_tab (the warm-up frame uses warm_hop)
-        int hop = is_warm ? sg.warm_hop : (a.hop_tab ? TSB_LDG(&a.hop_tab[f]) : a.hop);
+        int hop = is_warm ? warm_hop : (hop_tab ? TSB_LDG(&hop_tab[ff]) : a.hop);
         // slots [in_off, in_off+hop) are dead once pass 0 has read the frame
         int cnt = ff + 1 < total ? (hop < N ? hop : N) : 0;
         long long first = in_off + hop + N - cnt;
@@ -741,8 +776,10 @@ TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const t
             ex.each([&](int tid, Regs &rg) { CH::phase_pv_analyze(tid, sm, rg, tb); });
             if (prepass) {
                 if (is_warm) {
-                    if (a.st_warm_phase)
-                        ex.each([&](int tid, Regs &rg) { CH::regs_to(tid, a.st_warm_phase, sg.row, rg.last_phase, nullptr); });
+                    if (a.st_warm_phase) {
+                        const long long row = (long long)seg * a.lanes + lane;
+                        ex.each([&](int tid, Regs &rg) { CH::regs_to(tid, a.st_warm_phase, row, rg.last_phase); });
+                    }
                 } else {
                     ex.each([&](int tid, Regs &rg) { CH::phase_pv_accumulate(tid, sm, rg, tb); });
                 }
@@ -758,7 +795,10 @@ TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const t
         in_off += hop;
         out_pos += hop;
     }
-    ex.each([&](int tid, Regs &rg) { CH::store_state(tid, sm, rg, a, sg, out_pos); });
+    {
+        SegInfo sg = seg_info<CH>(a, lane, seg);
+        ex.each([&](int tid, Regs &rg) { CH::store_state(tid, sm, rg, a, sg, out_pos); });
+    }
 }
 
 }  // namespace tsb

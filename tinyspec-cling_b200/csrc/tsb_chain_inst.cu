@@ -11,7 +11,7 @@
 #define TSB_REGS_PV32 80
 #endif
 #ifndef TSB_REGS_PV64
-#define TSB_REGS_PV64 128
+#define TSB_REGS_PV64 96
 #endif
 
 namespace tsb {

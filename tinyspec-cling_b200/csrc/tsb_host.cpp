@@ -106,8 +106,8 @@ std::vector<double> pass_twiddle_table(int m) {
     for (size_t p = 0; p < radix.size(); p++) {
         int r = radix[p];
         if (p >= 1) {
-            for (int jm = 0; jm < ns; jm++)
-                for (int k = 0; k < r; k++) {
+            for (int k = 1; k < r; k++)
+                for (int jm = 0; jm < ns; jm++) {
                     long double a = -tau * (long double)(jm * k) / (long double)(ns * r);
                     t.push_back((double)cosl(a));
                     t.push_back((double)sinl(a));

@@ -56,7 +56,7 @@ void build_shift_map(int n, double rate, const double *fn_bins, std::vector<uint
 std::vector<double> twiddle_table(int m, int count);
 
 // Per-pass twiddle tables of an m-point Stockham FFT with the radix plan of tsb_math.cuh (radix 8 passes,
-// remainder 2 or 4 last): for each pass p >= 1, entries [jm*R + t] = exp(-2*pi*i*jm*t/(Ns*R)); passes
+// remainder 2 or 4 last): for each pass p >= 1, entries [(t-1)*Ns + jm] = exp(-2*pi*i*jm*t/(Ns*R)), t >= 1; passes
 // concatenated (re,im interleaved).  Matches TwLayout<log2 m>.
 std::vector<double> pass_twiddle_table(int m);
 

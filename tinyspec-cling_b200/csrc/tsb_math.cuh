@@ -23,37 +23,61 @@ struct alignas(2 * sizeof(T)) cpx {
     T x, y;
 };
 
-// read-only (non-coherent) global loads for the constant tables
-template <typename T>
-TSB_HD T ldg(const T *p) {
+// Read-only (non-coherent) global loads for the constant tables.  Most table entries a thread reads are the
+// same every frame, and the compiler would hoist them out of the frame loop and then spill them (the register
+// budget is what buys residency); `asm volatile` keeps each load where it is written — an L1 hit per frame.
 #if defined(__CUDA_ARCH__)
-    return __ldg(p);
-#else
-    return *p;
-#endif
+TSB_D float ldg(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
 }
-TSB_HD cpx<float> ldg(const cpx<float> *p) {
-#if defined(__CUDA_ARCH__)
-    float2 v = __ldg(reinterpret_cast<const float2 *>(p));
+TSB_D double ldg(const double *p) {
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+TSB_D cpx<float> ldg(const cpx<float> *p) {
     cpx<float> r;
-    r.x = v.x;
-    r.y = v.y;
+    asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
     return r;
-#else
-    return *p;
-#endif
 }
-TSB_HD cpx<double> ldg(const cpx<double> *p) {
-#if defined(__CUDA_ARCH__)
-    double2 v = __ldg(reinterpret_cast<const double2 *>(p));
+TSB_D cpx<double> ldg(const cpx<double> *p) {
     cpx<double> r;
-    r.x = v.x;
-    r.y = v.y;
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
     return r;
-#else
-    return *p;
-#endif
 }
+TSB_D uint32_t ldg(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+TSB_D int ldg(const int *p) {
+    int v;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+TSB_D int ldg(const int16_t *p) {
+    int v;
+    asm volatile("ld.global.nc.s16 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+TSB_D int ldg(const uint16_t *p) {
+    int v;
+    asm volatile("ld.global.nc.u16 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+TSB_D long long ldg(const long long *p) {
+    long long v;
+    asm volatile("ld.global.nc.s64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+#else
+template <typename T>
+inline T ldg(const T *p) { return *p; }
+inline int ldg(const int16_t *p) { return *p; }
+inline int ldg(const uint16_t *p) { return *p; }
+#endif
 template <typename T>
 TSB_HD cpx<T> mk(T x, T y) {
     cpx<T> r;
@@ -147,13 +171,14 @@ struct Swz<double> {  // 16-byte elements: 8 lanes per wavefront
     static TSB_HD constexpr int f(int i) { return i ^ (((i >> 3) ^ (i >> 4)) & 7); }
 };
 
-// Per-pass twiddle tables: for pass P, entry [jm*R + t] = exp(-2*pi*i*jm*t/(Ns*R)), jm < Ns, t < R, so
-// that a butterfly's R-1 twiddles are one contiguous run (t = 0 is the unused 1).  Passes are laid out
-// one after the other; pass 0 (Ns = 1) needs none.
+// Per-pass twiddle tables: for pass P, entry [(t-1)*Ns + jm] = exp(-2*pi*i*jm*t/(Ns*R)), 1 <= t < R, jm < Ns.
+// For a fixed t consecutive threads (consecutive jm) read consecutive entries: one coalesced 8/16-byte load per
+// twiddle (the [jm][t] layout costs 8x the L1 wavefronts: measured, it doubled the kernel's L1 data-pipe load).
+// Passes are laid out one after the other; pass 0 (Ns = 1) needs none.
 template <int LOG2M>
 struct TwLayout {
     using RP = RadixPlan<LOG2M>;
-    static constexpr int offset(int p) { return p <= 1 ? 0 : offset(p - 1) + RP::ns(p - 1) * RP::radix(p - 1); }
+    static constexpr int offset(int p) { return p <= 1 ? 0 : offset(p - 1) + RP::ns(p - 1) * (RP::radix(p - 1) - 1); }
     static constexpr int total = offset(RP::passes);
 };
 
@@ -179,9 +204,9 @@ TSB_HD void stockham_pass_io(int tid, const cpx<T> *twp, In in, Out out) {
         for (int t = 0; t < R; t++) v[t] = in(j, t * NB);
         if (Ns > 1) {
             int jm = j & (Ns - 1);
-            const cpx<T> *w = twp + TwLayout<LOG2M>::offset(P) + jm * R;
+            const cpx<T> *w = twp + TwLayout<LOG2M>::offset(P) + jm;
 #pragma unroll
-            for (int t = 1; t < R; t++) v[t] = cmul(v[t], TSB_LDG(&w[t]));
+            for (int t = 1; t < R; t++) v[t] = cmul(v[t], TSB_LDG(&w[(t - 1) * Ns]));
             dftR<R>(v);
             int base = ((j - jm) * R) + jm;
 #pragma unroll
