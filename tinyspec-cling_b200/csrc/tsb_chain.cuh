@@ -275,15 +275,16 @@ struct Chain {
     static constexpr int N = 1 << LOG2N;
     static constexpr int LOG2M = LOG2N - 1;
     static constexpr int M = N / 2;
-    // Threads per lane: T0 = N/16 runs one radix-8 butterfly per thread and pass.  The fp64 PV kernel, whose
-    // time goes to per-bin double-precision atan2/sincos rather than to the FFT, uses 2*T0 threads: the extra
-    // warps only take part in the per-bin (PV, window, overlap-add) phases, which then own 4 bins per thread
-    // instead of 8 (measured +5 % at N=1024; fp32 is fastest at T0).  TSB_TMUL overrides, for tuning.
+    // Threads per lane: T0 = N/16 runs one radix-8 butterfly per thread and pass.  The PV kernels use 2*T0
+    // threads: the extra warps only take part in the per-bin (PV, window, overlap-add) phases, which then own
+    // 4 bins per thread instead of 8 — half the register-resident state, so more warps fit, and the per-bin
+    // transcendental work (the bulk of the fp64 kernel) gets twice the threads (measured at N=1024: fp64 +45 %
+    // together with the coalesced twiddle tables, fp32 +5 %).  TSB_TMUL overrides, for tuning.
     static constexpr int T0 = (N / 16) < 32 ? 32 : (N / 16);
 #ifdef TSB_TMUL
     static constexpr int TMUL = (PROG == PROG_PV_SHIFT && N >= 256) ? TSB_TMUL : 1;
 #else
-    static constexpr int TMUL = (PROG == PROG_PV_SHIFT && sizeof(real) == 8 && N >= 256 && N <= 2048) ? 2 : 1;
+    static constexpr int TMUL = (PROG == PROG_PV_SHIFT && N >= 256 && N <= 2048) ? 2 : 1;
 #endif
     static constexpr int T = T0 * TMUL > 1024 ? 1024 : T0 * TMUL;
     static constexpr int HALF = M / 2;                       // split pairs (k, M-k), k < M/2

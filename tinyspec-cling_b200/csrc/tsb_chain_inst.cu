@@ -8,7 +8,7 @@
 #error "compile with -DTSB_LOG2N=<6..13>"
 #endif
 #ifndef TSB_REGS_PV32
-#define TSB_REGS_PV32 80
+#define TSB_REGS_PV32 64
 #endif
 #ifndef TSB_REGS_PV64
 #define TSB_REGS_PV64 96
