@@ -20,8 +20,6 @@ struct HostExec {
     void each(F f) {
         for (int tid = 0; tid < CH::T; tid++) f(tid, regs[tid]);
     }
-    template <class F>
-    void each_nosync(F f) { each(f); }
 };
 
 template <typename real, int LOG2N, int PROG>

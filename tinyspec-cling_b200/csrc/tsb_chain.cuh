@@ -11,13 +11,21 @@
 // rtlib/fft.hpp:3-42, rtlib/windowfn.hpp:1-14).
 //
 // The code is organised as per-thread PHASES with no barrier inside a phase; the CUDA kernel
-// (tsb_kernels.cu) calls them with __syncthreads() in between, and the CPU test harness
-// (tests/emul) replays the same phases thread by thread.  Shared-memory layout per lane:
-//     ring[N]  float   input samples, slot = absolute sample index mod N
-//     ola[N]   real    overlap-add accumulator, slot = absolute output position mod N
-//     bufA[M], bufB[M] complex<real>, ping-pong FFT buffers (M = N/2); the idle one doubles as the
-//                      phase-increment exchange array of the PV stage
-//     amp[M]   real    PV amplitude exchange array (fp32 PV only; fp64 keeps it in the idle buffer)
+// (tsb_chain_inst.cu) calls them with __syncthreads() in between, and the CPU test harness
+// (tests/emul) replays the same phases thread by thread.  Per frame (P = Stockham passes of the M-point FFT):
+//     forward pass 0      ring -> analysis window -> butterflies -> buf        (gather + window fused into the load)
+//     forward pass 1..P-1 buf <-> buf; pass 1 also issues the cp.async fetch of the next frame's new samples
+//     PV analyse          real-FFT split + |X|, arg X, wrapped phase advance -> exchange arrays      [PV program]
+//     PV synthesise       shift gather, phase accumulation, polar, C2R pre-processing -> buf          [PV program]
+//     gain                split, multiply, C2R pre-processing -> buf                                  [gain program]
+//     inverse pass 0..P-2 buf <-> buf
+//     inverse pass P-1    butterflies -> synthesis window -> overlap-add ring -> `hop` samples to HBM (fused store)
+// Shared-memory layout per lane:
+//     ring[N]    float   input samples, slot = absolute sample index mod N
+//     ola[N]     real    overlap-add accumulator, slot = absolute output position mod N
+//     buf[2][M]  complex<real>, ping-pong FFT buffers (M = N/2), XOR-swizzled (Swz<real>); the idle one doubles
+//                as the PV stage's phase-increment (and, in fp64, amplitude) exchange array
+//     amp_own[M] real    PV amplitude exchange array (fp32 PV only)
 //
 // Real-FFT mapping: the reference runs complex FFTs of real data.  Here the N
 // real samples are packed into M = N/2 complex points, transformed once, and split; with

@@ -24,10 +24,6 @@ struct DevExec {
         f((int)threadIdx.x, rg);
         __syncthreads();
     }
-    template <class F>
-    __device__ __forceinline__ void each_nosync(F f) {
-        f((int)threadIdx.x, rg);
-    }
 };
 
 // Resident CTAs per SM the kernel is compiled for: what shared memory allows (227 KB, 1 KB reserved per
