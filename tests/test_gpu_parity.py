@@ -318,3 +318,33 @@ def test_streaming_front_end_bit_identical(env, n, hr, precision):
     assert st.frames == F and got.shape == whole.shape
     assert np.array_equal(got, whole)
     assert first_output_at >= 2048 + n
+
+
+def test_timepar_gain_program(env):
+    """Without a phase vocoder only the overlap tail crosses segments: the time-parallel render of the spectral-gain
+    chain differs from the sequential one by the regrouping of at most four additions per sample."""
+    torch, tsb, orc = env["torch"], env["tsb"], env["orc"]
+    n, hop = 2048, 512
+    x = orc.gen_signal(0, 2, 150000)
+    sch = tsb.schedule_const(x.shape[0], n, hop)
+    gain = 1.0 / (1.0 + np.arange(n // 2 + 1) / 64.0)
+    plan = tsb.Plan(env["ctx"], n, precision="f64", program="gain", gain=gain)
+    xd = torch.from_numpy(np.ascontiguousarray(x.T)).cuda()
+    seq = plan.render(xd, sch["n_frames"], hop).clone()
+    par = plan.render_timepar(xd, sch["n_frames"], hop, 40)
+    torch.cuda.synchronize()
+    assert float((par - seq).abs().max()) <= 1e-15 * float(seq.abs().max()) * 4
+    ref = orc.render_filter(x, n, 0.25, gain)
+    assert maxrel(par.cpu().numpy(), ref["ola64"][:par.shape[1]].T) <= 1e-12
+
+
+def test_timepar_rejects_bad_arguments(env):
+    torch, tsb = env["torch"], env["tsb"]
+    plan = tsb.Plan(env["ctx"], 1024, precision="f32", program="pv", hop=256, ratio=2.0)
+    x = torch.zeros((2, 20000), dtype=torch.float32, device="cuda")
+    with pytest.raises(tsb.TsbError, match="warm-up frame would start before the input"):
+        plan.timepar(x, 10, 256, 2, in_off0=100, warmup=True, warm_hop=256)
+    tp = plan.timepar(x, 60, 256, 1000)       # asks for far more segments than frames allow
+    assert 1 <= tp.segments <= 60 // 4        # every segment emits at least one frame length
+    with pytest.raises(tsb.TsbError, match="before tsb_timepar_prepass"):
+        tp.render()

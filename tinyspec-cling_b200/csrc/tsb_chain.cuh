@@ -402,9 +402,11 @@ struct Chain {
             int kb = is_special(i, k) ? HALF : M - k;
             real amp;
             double inc;
-            gather_bin(amp_x, inc_x, tb, k, amp, inc);
+            if (tb.map1) gather_bin<true>(amp_x, inc_x, tb, k, amp, inc);
+            else gather_bin<false>(amp_x, inc_x, tb, k, amp, inc);
             rg.phase_sum[2 * i] = PvMath<real>::accumulate(rg.phase_sum[2 * i], inc);
-            gather_bin(amp_x, inc_x, tb, kb, amp, inc);
+            if (tb.map1) gather_bin<true>(amp_x, inc_x, tb, kb, amp, inc);
+            else gather_bin<false>(amp_x, inc_x, tb, kb, amp, inc);
             rg.phase_sum[2 * i + 1] = PvMath<real>::accumulate(rg.phase_sum[2 * i + 1], inc);
         }
     }
@@ -544,18 +546,21 @@ struct Chain {
         }
     }
     // shift gather for destination bin k (rtlib/pv.hpp:70-78: amplitudes add in ascending source
-    // order, the frequency of the last source wins; bins with no source are silent with freq 0)
+    // order, the frequency of the last source wins; bins with no source are silent with freq 0).
+    // SIMPLE: at most one source per destination (any upward shift) — a table lookup and two selects.
+    template <bool SIMPLE>
     static TSB_HD void gather_bin(const real *amp_x, const double *inc_x, const Tables &tb, int k, real &amp, double &inc) {
-        amp = 0;
-        inc = 0;
-        if (tb.map1) {  // at most one source per destination (any upward shift): no loop
+        if (SIMPLE) {
             int j = TSB_LDG(&tb.map1[k]);
-            if (j >= 0) {
-                amp = amp_x[j];
-                inc = inc_x[j];
-            }
+            int jj = j < 0 ? 0 : j;
+            real a = amp_x[jj];
+            double d = inc_x[jj];
+            amp = j < 0 ? (real)0 : a;
+            inc = j < 0 ? 0.0 : d;
             return;
         }
+        amp = 0;
+        inc = 0;
         uint32_t e = TSB_LDG(&tb.map[k]);
         int first = (int)(e >> 16), cnt = (int)(e & 0xffff);
 #pragma unroll 1
@@ -568,6 +573,11 @@ struct Chain {
     // ------------------------------------------------------------------ PV phase D: synthesis + C2R pre
     // (rtlib/pv.hpp:29-38 on the shifted bins, then Z = conj(Y) [1/2 folded into win_s])
     static TSB_HD void phase_pv_synth(int tid, Smem &sm, Regs &rg, const Tables &tb) {
+        if (tb.map1) phase_pv_synth_t<true>(tid, sm, rg, tb);  // uniform: decided once per plan
+        else phase_pv_synth_t<false>(tid, sm, rg, tb);
+    }
+    template <bool SIMPLE>
+    static TSB_HD void phase_pv_synth_t(int tid, Smem &sm, Regs &rg, const Tables &tb) {
         C *H = fwd_result(sm);  // the packed spectrum has been consumed; reuse its buffer
         const double *inc_x = xch_inc(sm);
         const real *amp_x = xch_amp(sm);
@@ -579,9 +589,9 @@ struct Chain {
             int kb = sp ? HALF : M - k;
             real amp;
             double inc;
-            gather_bin(amp_x, inc_x, tb, k, amp, inc);
+            gather_bin<SIMPLE>(amp_x, inc_x, tb, k, amp, inc);
             C Ya = PvMath<real>::synth(amp, inc, rg.phase_sum[2 * i]);
-            gather_bin(amp_x, inc_x, tb, kb, amp, inc);
+            gather_bin<SIMPLE>(amp_x, inc_x, tb, kb, amp, inc);
             C Yb = PvMath<real>::synth(amp, inc, rg.phase_sum[2 * i + 1]);
             if (!sp) {
                 merge_pair(H, tb, k, conj(Ya), conj(Yb));
@@ -637,10 +647,13 @@ struct Chain {
             // samples of this frame that may be written: n < lim (everything when the row has room)
             const long long room = a.out_len - out_pos;
             const int lim = room >= (long long)N + hop ? 0x7fffffff : (room < 0 ? 0 : (int)room);
-            if (((ob | hop) & 1) == 0 && ((reinterpret_cast<uintptr_t>(dstg) & (2 * sizeof(real) - 1)) == 0)) {
-                // pairs (2m, 2m+1) never straddle the hop boundary and are aligned in the ring and in the row
+            if (((ob | hop | (lim == 0x7fffffff ? 0 : lim)) & 1) == 0 &&
+                ((reinterpret_cast<uintptr_t>(dstg) & (2 * sizeof(real) - 1)) == 0)) {
+                // pairs (2m, 2m+1) never straddle the hop boundary or the end of the row and are aligned in the
+                // ring and in the row: one 2-sample load / add / (predicated) store per pair, no branches
                 C *ola2 = reinterpret_cast<C *>(sm.ola);
                 const int ob2 = ob >> 1;
+                const int emit_end = hop < lim ? hop : lim;
                 auto out = [&](int x, int c, C f) {
                     const int m = x + c;
                     C w = TSB_LDG(ws + m);
@@ -648,12 +661,9 @@ struct Chain {
                     C acc = *slot;
                     acc.x += f.x * w.x;
                     acc.y -= f.y * w.y;
-                    if (2 * m < hop) {
-                        if (2 * m + 1 < lim) *reinterpret_cast<C *>(dstg + 2 * m) = acc;
-                        else if (2 * m < lim) dstg[2 * m] = acc.x;
-                        acc = mk<real>(0, 0);
-                    }
-                    *slot = acc;
+                    const bool done = 2 * m < hop;
+                    if (2 * m < emit_end) *reinterpret_cast<C *>(dstg + 2 * m) = acc;
+                    *slot = mk<real>(done ? (real)0 : acc.x, done ? (real)0 : acc.y);
                 };
                 stockham_pass_io<real, LOG2M, T, P>(tid, tb.tw, in, out);
             } else {
