@@ -295,6 +295,8 @@ struct Chain {
     static constexpr int TMUL = (PROG == PROG_PV_SHIFT && N >= 256 && N <= 2048) ? 2 : 1;
 #endif
     static constexpr int T = T0 * TMUL > 1024 ? 1024 : T0 * TMUL;
+    // With twice the FFT's threads, the two halves of the CTA transform two frames at once (see run_lane).
+    static constexpr bool PIPE = (PROG == PROG_PV_SHIFT) && T == 2 * T0;
     static constexpr int HALF = M / 2;                       // split pairs (k, M-k), k < M/2
     static constexpr int S = (HALF + T - 1) / T;             // pair slots per thread
     static constexpr int PASSES = RadixPlan<LOG2M>::passes;
@@ -307,6 +309,9 @@ struct Chain {
         float ring[N];
         real ola[N];
         C buf[2][M];  // ping-pong FFT buffers, swizzled (Swz<real>)
+        // software pipeline (PIPE): the inverse transform of frame f runs on its own buffers while the other
+        // half of the threads runs the forward transform of frame f+1 in `buf`
+        C ibuf[PIPE ? 2 : 1][PIPE ? M : 1];
         // PV amplitude exchange array: fp32 needs its own (the spare FFT buffer is filled by the M fp64
         // increments); in fp64 the spare buffer (16*M bytes) holds both, so nothing extra is reserved.
         real amp_own[(PROG == PROG_PV_SHIFT && sizeof(real) == 4) ? M : 1];
@@ -329,8 +334,9 @@ struct Chain {
     }
     // The inverse transform starts from H: PV writes it over the consumed spectrum (RB), the gain program
     // into the spare buffer (no barrier between its split and merge).  Inverse pass p reads IB(p), writes IB(p+1).
-    static constexpr int INV0 = IS_PV ? RB : SB;
+    static constexpr int INV0 = PIPE ? 0 : (IS_PV ? RB : SB);
     static constexpr int inv_buf(int p) { return (p & 1) ? (INV0 ^ 1) : INV0; }
+    static TSB_HD C *inv_buffer(Smem &sm, int p) { return PIPE ? sm.ibuf[inv_buf(p)] : sm.buf[inv_buf(p)]; }
 
     // ------------------------------------------------------------------ state in / out
     // state rows: registers <-> [row][M] arrays, thread `tid` owning bins (k, M-k) of its slots.  The register
@@ -416,20 +422,22 @@ struct Chain {
     // On the device this is an asynchronous global->shared copy (cp.async / LDGSTS): it is issued
     // right after the window phase has consumed the slots it overwrites and completes in the
     // background while the frame is transformed; ring_wait() + a barrier precede the next use.
+    // NT = number of threads taking part (tid < NT)
+    template <int NT = T>
     static TSB_HD void ring_fill(int tid, int lane, Smem &sm, const ChainArgs &a, long long first, int count) {
         const float *src = a.in + (long long)lane * a.in_stride;
 #if defined(__CUDA_ARCH__)
         bool vec = ((first | (long long)count | a.in_stride) & 3) == 0 && first >= 0 && first + count <= a.in_len &&
                    ((reinterpret_cast<uintptr_t>(a.in) & 15) == 0);
         if (vec) {
-            for (int i = tid * 4; i < count; i += T * 4) {
+            for (int i = tid * 4; i < count; i += NT * 4) {
                 long long s0 = first + i;
                 unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.ring[(int)(s0 & (N - 1))]);
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src + s0) : "memory");
             }
             return;
         }
-        for (int i = tid; i < count; i += T) {
+        for (int i = tid; i < count; i += NT) {
             long long s0 = first + i;
             float *d = &sm.ring[(int)(s0 & (N - 1))];
             if (s0 >= 0 && s0 < a.in_len) {
@@ -440,7 +448,7 @@ struct Chain {
             }
         }
 #else
-        for (int i = tid; i < count; i += T) {
+        for (int i = tid; i < count; i += NT) {
             long long s0 = first + i;
             sm.ring[(int)(s0 & (N - 1))] = (s0 >= 0 && s0 < a.in_len) ? src[s0] : 0.f;
         }
@@ -459,7 +467,7 @@ struct Chain {
     static TSB_HD C ld_sw(const C *buf, int a, int c) { return buf[SW::f(a) ^ SW::f(c)]; }
     static TSB_HD void st_sw(C *buf, int a, int c, C v) { buf[SW::f(a) ^ SW::f(c)] = v; }
 
-    template <int P>
+    template <int P, int NT = T>
     static TSB_HD void fwd_pass(int tid, Smem &sm, const Tables &tb, long long in_off) {
         C *dst = sm.buf[P & 1];
         auto out = [&](int a, int c, C v) { st_sw(dst, a, c, v); };
@@ -474,7 +482,7 @@ struct Chain {
                     C w = TSB_LDG(wa + a + c);
                     return mk<real>((real)q.x * w.x, (real)q.y * w.y);
                 };
-                stockham_pass_io<real, LOG2M, T, P>(tid, tb.tw, in, out);
+                stockham_pass_io<real, LOG2M, NT, P>(tid, tb.tw, in, out);
             } else {
                 auto in = [&](int a, int c) {
                     int m = a + c;
@@ -483,12 +491,12 @@ struct Chain {
                     C w = TSB_LDG(wa + m);
                     return mk<real>((real)x0 * w.x, (real)x1 * w.y);
                 };
-                stockham_pass_io<real, LOG2M, T, P>(tid, tb.tw, in, out);
+                stockham_pass_io<real, LOG2M, NT, P>(tid, tb.tw, in, out);
             }
         } else {
             const C *src = sm.buf[(P - 1) & 1];
             auto in = [&](int a, int c) { return ld_sw(src, a, c); };
-            stockham_pass_io<real, LOG2M, T, P>(tid, tb.tw, in, out);
+            stockham_pass_io<real, LOG2M, NT, P>(tid, tb.tw, in, out);
         }
     }
 
@@ -578,7 +586,7 @@ struct Chain {
     }
     template <bool SIMPLE>
     static TSB_HD void phase_pv_synth_t(int tid, Smem &sm, Regs &rg, const Tables &tb) {
-        C *H = fwd_result(sm);  // the packed spectrum has been consumed; reuse its buffer
+        C *H = inv_buffer(sm, 0);  // not pipelined: the consumed packed spectrum's buffer; pipelined: ibuf[0]
         const double *inc_x = xch_inc(sm);
         const real *amp_x = xch_amp(sm);
 #pragma unroll
@@ -631,15 +639,15 @@ struct Chain {
     // The last pass hands its outputs F[m] straight to the synthesis window and the overlap-add:
     // x[2m] = Re F[m], x[2m+1] = -Im F[m]; out = x*ws; accumulate into the ring; the first `hop`
     // positions are complete (tinyspec.cpp:173-182) and leave the chip, the rest is the tail (194-200).
-    template <int P>
+    template <int P, int NT = T>
     static TSB_HD void inv_pass(int tid, int lane, Smem &sm, const Tables &tb, const ChainArgs &a, long long out_pos,
                                 int hop) {
-        const C *src = sm.buf[inv_buf(P)];
+        const C *src = inv_buffer(sm, P);
         auto in = [&](int x, int c) { return ld_sw(src, x, c); };
         if (P < PASSES - 1) {
-            C *dst = sm.buf[inv_buf(P + 1)];
+            C *dst = inv_buffer(sm, P + 1);
             auto out = [&](int x, int c, C v) { st_sw(dst, x, c, v); };
-            stockham_pass_io<real, LOG2M, T, P>(tid, tb.tw, in, out);
+            stockham_pass_io<real, LOG2M, NT, P>(tid, tb.tw, in, out);
         } else {
             real *dstg = reinterpret_cast<real *>(a.out) + (long long)lane * a.out_stride + out_pos;
             const C *ws = reinterpret_cast<const C *>(tb.win_s);
@@ -665,7 +673,7 @@ struct Chain {
                     if (2 * m < emit_end) *reinterpret_cast<C *>(dstg + 2 * m) = acc;
                     *slot = mk<real>(done ? (real)0 : acc.x, done ? (real)0 : acc.y);
                 };
-                stockham_pass_io<real, LOG2M, T, P>(tid, tb.tw, in, out);
+                stockham_pass_io<real, LOG2M, NT, P>(tid, tb.tw, in, out);
             } else {
                 auto out = [&](int x, int c, C f) {
                     const int m = x + c;
@@ -683,10 +691,10 @@ struct Chain {
                         sm.ola[slot] = acc;
                     }
                 };
-                stockham_pass_io<real, LOG2M, T, P>(tid, tb.tw, in, out);
+                stockham_pass_io<real, LOG2M, NT, P>(tid, tb.tw, in, out);
             }
             // hop larger than the frame: nothing overlaps those positions (tinyspec.cpp:184-191)
-            for (int n = N + tid; n < hop; n += T)
+            for (int n = N + tid; n < hop; n += NT)
                 if (n < lim) dstg[n] = 0;
         }
     }
@@ -728,6 +736,37 @@ template <class CH, int END>
 struct InvPasses<CH, END, END> {
     template <class Exec>
     static TSB_HD void run(Exec &, int, typename CH::Smem &, const typename CH::Tables &, const ChainArgs &, long long, int) {}
+};
+
+// Software-pipelined pass pairs (CH::PIPE): in one barrier interval the first T0 threads run forward pass P of
+// the NEXT frame while the other T0 threads run inverse pass P of the CURRENT frame (different buffers; the
+// split is at warp granularity).  Both transforms have the same pass structure, so they stay in step.
+template <class CH, int P, int END>
+struct PipePasses {
+    template <class Exec>
+    static TSB_HD void run(Exec &ex, int lane, typename CH::Smem &sm, const typename CH::Tables &tb, const ChainArgs &a,
+                           bool have_next, long long next_in_off, long long fetch_first, int fetch_cnt, bool have_cur,
+                           long long out_pos, int hop) {
+        ex.each([&](int tid, typename CH::Regs &) {
+            if (tid < CH::T0) {
+                if (have_next) {
+                    if (P == 1 && fetch_cnt > 0) CH::template ring_fill<CH::T0>(tid, lane, sm, a, fetch_first, fetch_cnt);
+                    CH::template fwd_pass<P, CH::T0>(tid, sm, tb, next_in_off);
+                    if (P == END - 1) CH::ring_wait();
+                }
+            } else if (have_cur) {
+                CH::template inv_pass<P, CH::T0>(tid - CH::T0, lane, sm, tb, a, out_pos, hop);
+            }
+        });
+        PipePasses<CH, P + 1, END>::run(ex, lane, sm, tb, a, have_next, next_in_off, fetch_first, fetch_cnt, have_cur,
+                                        out_pos, hop);
+    }
+};
+template <class CH, int END>
+struct PipePasses<CH, END, END> {
+    template <class Exec>
+    static TSB_HD void run(Exec &, int, typename CH::Smem &, const typename CH::Tables &, const ChainArgs &, bool, long long,
+                           long long, int, bool, long long, int) {}
 };
 
 // The whole launch for one (segment, lane).  `Exec::each(f)` runs f(tid, regs) for every thread of the lane and
@@ -784,6 +823,33 @@ TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const t
             CH::ring_wait();
         });
     }
+    if (CH::PIPE && !prepass) {
+        // frame f: [analyse f][synthesise f][inverse passes of f  ||  forward passes of f+1]; the forward passes of
+        // the first frame run alone as a prologue.  `hop_of(f)` = samples emitted after frame f.
+        auto hop_of = [&](int f) { return hop_tab ? TSB_LDG(&hop_tab[f]) : a.hop; };
+        if (total > 0) {
+            int hop0 = hop_of(0);
+            int cnt = total > 1 ? (hop0 < N ? hop0 : N) : 0;
+            PipePasses<CH, 0, CH::PASSES>::run(ex, lane, sm, tb, a, true, in_off, in_off + hop0 + N - cnt, cnt, false, out_pos, 0);
+        }
+        for (int ff = 0; ff < total; ff++) {
+            const int hop = hop_of(ff);
+            ex.each([&](int tid, Regs &rg) { CH::phase_pv_analyze(tid, sm, rg, tb); });
+            ex.each([&](int tid, Regs &rg) { CH::phase_pv_synth(tid, sm, rg, tb); });
+            const bool have_next = ff + 1 < total;
+            const long long next_in = in_off + hop;
+            int cnt = 0;
+            long long first = 0;
+            if (have_next && ff + 2 < total) {  // while frame ff+1 is transformed, fetch what frame ff+2 adds
+                int hop1 = hop_of(ff + 1);
+                cnt = hop1 < N ? hop1 : N;
+                first = next_in + hop1 + N - cnt;
+            }
+            PipePasses<CH, 0, CH::PASSES>::run(ex, lane, sm, tb, a, have_next, next_in, first, cnt, true, out_pos, hop);
+            in_off = next_in;
+            out_pos += hop;
+        }
+    } else
     for (int ff = 0; ff < total; ff++) {
         const bool is_warm = warm && ff == 0;
         int hop = is_warm ? warm_hop : (hop_tab ? TSB_LDG(&hop_tab[ff]) : a.hop);
