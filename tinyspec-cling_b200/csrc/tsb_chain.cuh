@@ -750,9 +750,13 @@ struct PipePasses {
         ex.each([&](int tid, typename CH::Regs &) {
             if (tid < CH::T0) {
                 if (have_next) {
-                    if (P == 1 && fetch_cnt > 0) CH::template ring_fill<CH::T0>(tid, lane, sm, a, fetch_first, fetch_cnt);
+                    // The samples this frame adds were requested during the previous frame's last pass (below) and
+                    // had the whole PV stage to arrive (the synthesis phase ends with ring_wait + barrier).  The
+                    // request for the frame after goes out in the LAST forward pass — the lightest one, opposite
+                    // the inverse side's overlap-add pass — so that the two halves of the CTA reach each barrier
+                    // at about the same time.
                     CH::template fwd_pass<P, CH::T0>(tid, sm, tb, next_in_off);
-                    if (P == END - 1) CH::ring_wait();
+                    if (P == END - 1 && fetch_cnt > 0) CH::template ring_fill<CH::T0>(tid, lane, sm, a, fetch_first, fetch_cnt);
                 }
             } else if (have_cur) {
                 CH::template inv_pass<P, CH::T0>(tid - CH::T0, lane, sm, tb, a, out_pos, hop);
@@ -835,7 +839,10 @@ TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const t
         for (int ff = 0; ff < total; ff++) {
             const int hop = hop_of(ff);
             ex.each([&](int tid, Regs &rg) { CH::phase_pv_analyze(tid, sm, rg, tb); });
-            ex.each([&](int tid, Regs &rg) { CH::phase_pv_synth(tid, sm, rg, tb); });
+            ex.each([&](int tid, Regs &rg) {
+                CH::phase_pv_synth(tid, sm, rg, tb);
+                CH::ring_wait();  // next frame's samples (requested a frame ago) are in the ring after this barrier
+            });
             const bool have_next = ff + 1 < total;
             const long long next_in = in_off + hop;
             int cnt = 0;
