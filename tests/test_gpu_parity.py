@@ -348,3 +348,34 @@ def test_timepar_rejects_bad_arguments(env):
     assert 1 <= tp.segments <= 60 // 4        # every segment emits at least one frame length
     with pytest.raises(tsb.TsbError, match="before tsb_timepar_prepass"):
         tp.render()
+
+
+def test_two_minute_render_does_not_diverge(env):
+    """BASELINE.json: the PV phase state must not diverge over long renders.  120 s of cfg1 (22,489 frames,
+    phase_sum up to 1.8e7 rad): fp64 stays within 1e-9 of the oracle with every wrap on the oracle's side; fp32 at
+    the hack's own integer ratio (x2, hacks/pitchshift-pv.cpp:6) stays within 1e-5 RMS (a wrap taken on the other
+    side shifts a bin by 4*pi there, i.e. not at all)."""
+    torch, tsb, orc = env["torch"], env["tsb"], env["orc"]
+    n, hop, ch, samples = 1024, 256, 2, 120 * 48000
+    x = orc.gen_signal(0, ch, samples)
+    ref = orc.render_pv(x, n, 0.25, 2.0)
+    F = ref["frames"]
+    want = ref["ola64"][:F * hop].T
+    xd = torch.from_numpy(np.ascontiguousarray(x.T)).cuda()
+    for precision in ("f64", "f32"):
+        plan = tsb.Plan(env["ctx"], n, precision=precision, program="pv", hop=hop, ratio=2.0)
+        st = {k: torch.zeros((ch, w), dtype=torch.float64, device="cuda") for k, w in
+              (("last_phase", n // 2), ("phase_sum", n // 2), ("ola", n))}
+        out = plan.render(xd, F, hop, state=st)
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        dps = np.abs(st["phase_sum"].cpu().numpy() - ref["phase_sum"][:, :n // 2])
+        tail = slice(-5 * 48000, None)
+        if precision == "f64":
+            assert maxrel(got, want) <= F64_MAXREL
+            assert dps.max() < 1e-6                      # no wrap flips; ulp(phase_sum) is 4e-9 here
+        else:
+            assert rmsrel(got, want) <= F32_RMSREL
+            assert rmsrel(got[:, tail], want[:, tail]) <= F32_RMSREL   # no growth towards the end
+            flips = dps > 1
+            assert np.all(np.abs(dps[flips] / (4 * np.pi) - np.round(dps[flips] / (4 * np.pi))) < 1e-3)  # multiples of 4*pi
