@@ -308,7 +308,7 @@ def main():
             plan1 = tsb200.Plan(ctx, N_FRAME, precision=args.precision, program="pv", hop=HOP, rate=RATE, ratio=SHIFT)
             x1 = x_all[:CH].contiguous()
             o1 = torch.zeros((CH, F * HOP), dtype=plan1.out_dtype, device=dev)
-            nseg = 444
+            nseg = 296
             for _ in range(2):
                 plan1.render_timepar(x1, F, HOP, nseg, out=o1)
             torch.cuda.synchronize()

@@ -41,6 +41,9 @@ struct tsb_ctx {
     std::map<std::pair<int64_t, int>, double *> windows;  // (size, kind) -> device table
     double *scratch = nullptr;                            // frft's FFT output / shift's copy
     size_t scratch_bytes = 0;
+    char *tp_pool = nullptr;                              // scratch of the time-parallel render, reused call to call
+    size_t tp_pool_bytes = 0;
+    bool tp_pool_busy = false;
 };
 
 struct tsb_plan {
@@ -93,6 +96,7 @@ TSB_API int tsb_ctx_destroy(tsb_ctx *c) {
     if (c->own_stream) cudaStreamDestroy(c->stream);
     for (auto &kv : c->windows) cudaFree(kv.second);
     if (c->scratch) cudaFree(c->scratch);
+    if (c->tp_pool) cudaFree(c->tp_pool);
     delete c;
     return TSB_OK;
 }
@@ -567,18 +571,19 @@ struct tsb_timepar {
     std::vector<long long> seg;  // [n_seg][6]
     long long *d_seg = nullptr, *d_pos = nullptr;
     double *d_last = nullptr, *d_sum = nullptr, *d_warm = nullptr, *d_ola = nullptr;
+    char *block = nullptr;   // one allocation holding all of the above
+    bool from_pool = false;
     bool prepassed = false;
 };
 TSB_API int tsb_timepar_destroy(tsb_timepar *tp) {
     if (!tp) return TSB_OK;
     cudaSetDevice(tp->ctx->device);
-    cudaStreamSynchronize(tp->ctx->stream);
-    cudaFree(tp->d_seg);
-    cudaFree(tp->d_pos);
-    cudaFree(tp->d_last);
-    cudaFree(tp->d_sum);
-    cudaFree(tp->d_warm);
-    cudaFree(tp->d_ola);
+    if (tp->from_pool) {
+        tp->ctx->tp_pool_busy = false;  // work queued on the stream keeps using it until it completes: stream order
+    } else if (tp->block) {
+        cudaStreamSynchronize(tp->ctx->stream);
+        cudaFree(tp->block);
+    }
     delete tp;
     return TSB_OK;
 }
@@ -635,19 +640,39 @@ TSB_API int tsb_timepar_create(tsb_ctx *c, tsb_plan *p, const tsb_chain_args *a,
         f += cnt;
     }
     size_t rows = (size_t)nseg * tp->lanes;
-    cudaError_t e = cudaMalloc(&tp->d_seg, tp->seg.size() * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&tp->d_pos, (size_t)nseg * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&tp->d_last, rows * tp->m * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&tp->d_sum, rows * tp->m * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&tp->d_warm, rows * tp->m * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&tp->d_ola, rows * tp->n * 8);
-    if (e != cudaSuccess) {
-        tsb_timepar_destroy(tp);
-        return fail(TSB_ENOMEM, "time-parallel scratch: %s", cudaGetErrorString(e));
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t b_seg = al(tp->seg.size() * 8), b_pos = al((size_t)nseg * 8), b_m = al(rows * tp->m * 8), b_n = al(rows * tp->n * 8);
+    const size_t total = b_seg + b_pos + 3 * b_m + b_n;
+    // one block for everything; the context keeps it for the next call (allocation costs as much as the render of
+    // a single stream).  Reuse is safe in stream order; a second live tsb_timepar gets its own block.
+    if (!c->tp_pool_busy) {
+        if (c->tp_pool_bytes < total) {
+            CU(cudaStreamSynchronize(c->stream));
+            if (c->tp_pool) cudaFree(c->tp_pool);
+            c->tp_pool = nullptr;
+            c->tp_pool_bytes = 0;
+            if (cudaMalloc(&c->tp_pool, total) == cudaSuccess) c->tp_pool_bytes = total;
+        }
+        if (c->tp_pool_bytes >= total) {
+            tp->block = c->tp_pool;
+            tp->from_pool = true;
+            c->tp_pool_busy = true;
+        }
     }
+    if (!tp->block && cudaMalloc(&tp->block, total) != cudaSuccess) {
+        tsb_timepar_destroy(tp);
+        return fail(TSB_ENOMEM, "time-parallel scratch (%zu bytes)", total);
+    }
+    char *q = tp->block;
+    tp->d_seg = (long long *)q; q += b_seg;
+    tp->d_pos = (long long *)q; q += b_pos;
+    tp->d_last = (double *)q; q += b_m;
+    tp->d_sum = (double *)q; q += b_m;
+    tp->d_warm = (double *)q; q += b_m;
+    tp->d_ola = (double *)q;
     CU(cudaMemcpyAsync(tp->d_seg, tp->seg.data(), tp->seg.size() * 8, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(tp->d_pos, pos.data(), (size_t)nseg * 8, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->stream));  // seg / pos are host temporaries
     *out = tp;
     return TSB_OK;
 }
