@@ -85,6 +85,89 @@ fft_rows_kernel(const cd *in, cd *out, RowAddr ia, RowAddr oa, long long rows, c
     }
 }
 
+// Tiled variant for the two steps of the four-step transform, where either the elements of a row or the rows
+// themselves are contiguous in memory but not both: one CTA transforms C rows that are ADJACENT in memory
+// (consecutive r with inner_stride 1, or rows that are each contiguous) and moves them with the contiguous
+// dimension fastest, so that every global access is a full 128-byte line instead of one 16-byte element per
+// sector.  The C transforms run side by side (T threads each) with CTA-wide barriers between passes.
+template <int LOG2M, int T, int P, int END>
+struct TilePasses {
+    static __device__ __forceinline__ cd *run(int lt, cd *src, cd *dst, const cd *tw) {
+        stockham_pass_io<double, LOG2M, T, P>(
+            lt, tw, [&](int a, int c) { return src[Swz<double>::f(a) ^ Swz<double>::f(c)]; },
+            [&](int a, int c, cd v) { dst[Swz<double>::f(a) ^ Swz<double>::f(c)] = v; });
+        __syncthreads();
+        return TilePasses<LOG2M, T, P + 1, END>::run(lt, dst, src, tw);
+    }
+};
+template <int LOG2M, int T, int END>
+struct TilePasses<LOG2M, T, END, END> {
+    static __device__ __forceinline__ cd *run(int, cd *src, cd *, const cd *) { return src; }
+};
+template <int LOG2M>
+struct TileCfg {
+    static constexpr int M = 1 << LOG2M;
+    static constexpr int T = (M / 8) < 32 ? 32 : (M / 8);
+    // C*M <= 2048 keeps the tile at 64 KB so that three CTAs share an SM and overlap each other's loads and stores
+    static constexpr int C = M <= 256 ? 8 : (M <= 512 ? 4 : (M <= 1024 ? 2 : 1));
+};
+template <int LOG2M>
+__global__ void __launch_bounds__(TileCfg<LOG2M>::C *TileCfg<LOG2M>::T)
+fft_tile_kernel(const cd *in, cd *out, RowAddr ia, RowAddr oa, long long rows, const cd *tw, int flags, double ntw,
+                double scale) {
+    constexpr int M = TileCfg<LOG2M>::M, T = TileCfg<LOG2M>::T, C = TileCfg<LOG2M>::C, NT = C * T;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cd *bufA = reinterpret_cast<cd *>(smem_raw), *bufB = bufA + C * M;
+    const int g = threadIdx.x / T, lt = threadIdx.x % T;
+    for (long long r0 = (long long)blockIdx.x * C; r0 < rows; r0 += (long long)gridDim.x * C) {
+        const bool in_rows_contig = ia.es == 1;
+        for (int i = threadIdx.x; i < C * M; i += NT) {
+            int c = in_rows_contig ? i / M : i % C, e = in_rows_contig ? i % M : i / C;
+            cd v = in[row_base(ia, r0 + c) + e * ia.es];
+            if (flags & 1) v.y = -v.y;
+            bufA[c * M + Swz<double>::f(e)] = v;
+        }
+        __syncthreads();
+        cd *res = TilePasses<LOG2M, T, 0, RadixPlan<LOG2M>::passes>::run(lt, bufA + g * M, bufB + g * M, tw);
+        res -= g * M;  // base of the buffer the results are in
+        const bool out_rows_contig = oa.es == 1;
+        if ((flags & 2) && !out_rows_contig) {
+            // four-step twiddle W_n^(j2*k1): this thread keeps one row (j2) and walks k1 in steps of NT/C, so the
+            // factor advances by a constant rotation — two sincospi per thread instead of one per element
+            const int c = threadIdx.x % C, e0 = threadIdx.x / C;
+            const double j2 = (double)((r0 + c) % ia.inner);
+            double sn, cs;
+            sincospi(-2.0 * (j2 * (double)e0) / ntw, &sn, &cs);
+            cd w = mk<double>(cs, sn);
+            sincospi(-2.0 * (j2 * (double)(NT / C)) / ntw, &sn, &cs);
+            const cd step = mk<double>(cs, sn);
+            cd *dst = out + row_base(oa, r0 + c);
+            for (int e = e0; e < M; e += NT / C) {
+                cd v = cmul(res[c * M + Swz<double>::f(e)], w);
+                if (flags & 1) v.y = -v.y;
+                v.x *= scale;
+                v.y *= scale;
+                dst[e * oa.es] = v;
+                w = cmul(w, step);
+            }
+        } else
+        for (int i = threadIdx.x; i < C * M; i += NT) {
+            int c = out_rows_contig ? i / M : i % C, e = out_rows_contig ? i % M : i / C;
+            cd v = res[c * M + Swz<double>::f(e)];
+            if (flags & 2) {
+                double sn, cs;
+                sincospi(-2.0 * ((double)((r0 + c) % ia.inner) * (double)e) / ntw, &sn, &cs);
+                v = cmul(v, mk<double>(cs, sn));
+            }
+            if (flags & 1) v.y = -v.y;
+            v.x *= scale;
+            v.y *= scale;
+            out[row_base(oa, r0 + c) + e * oa.es] = v;
+        }
+        __syncthreads();
+    }
+}
+
 struct FftPlanCache {
     std::map<int, cd *> pass_tw;                                 // log2 m -> device per-pass twiddles
     std::map<long long, std::pair<cd *, cd *>> bluestein;        // n -> (chirp c[n], FFT_L of the wrapped conj chirp)
@@ -134,6 +217,30 @@ static cudaError_t launch_rows(const cd *in, cd *out, RowAddr ia, RowAddr oa, lo
     if (launches) ++*launches;
     return cudaGetLastError();
 }
+template <int LOG2M>
+static cudaError_t launch_tile(const cd *in, cd *out, RowAddr ia, RowAddr oa, long long rows, const cd *tw, int flags,
+                               double ntw, double scale, cudaStream_t st, long long *launches) {
+    using TC = TileCfg<LOG2M>;
+    if (TC::C == 1 || rows % TC::C != 0) return launch_rows<LOG2M>(in, out, ia, oa, rows, tw, flags, ntw, scale, st, launches);
+    size_t smem = 2 * (size_t)TC::C * TC::M * sizeof(cd);
+    auto kern = fft_tile_kernel<LOG2M>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    long long tiles = rows / TC::C;
+    long long grid = tiles < 148LL * 12 ? tiles : 148LL * 12;
+    kern<<<(unsigned)grid, TC::C * TC::T, smem, st>>>(in, out, ia, oa, rows, tw, flags, ntw, scale);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+static cudaError_t tile_dispatch(int log2m, const cd *in, cd *out, RowAddr ia, RowAddr oa, long long rows, const cd *tw,
+                                 int flags, double ntw, double scale, cudaStream_t st, long long *launches) {
+    switch (log2m) {
+#define C(L) case L: return launch_tile<L>(in, out, ia, oa, rows, tw, flags, ntw, scale, st, launches);
+        C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(9) C(10) C(11) C(12)
+#undef C
+    }
+    return cudaErrorInvalidValue;
+}
 static cudaError_t rows_dispatch(int log2m, const cd *in, cd *out, RowAddr ia, RowAddr oa, long long rows, const cd *tw,
                                  int flags, double ntw, double scale, cudaStream_t st, long long *launches) {
     switch (log2m) {
@@ -171,11 +278,11 @@ static cudaError_t fft_pow2(int device, const cd *in, cd *out, long long rows, l
     // step 1: for every (row, j2): length-n1 FFT over j1 (stride n2), times W_n^(j2*k1), stored as tmp[row][k1][j2]
     if ((e = pass_twiddles(pc, l1, &tw)) != cudaSuccess) return e;
     RowAddr ia{n2, n, 1, n2}, oa{n2, n, 1, n2};
-    if ((e = rows_dispatch(l1, in, tmp, ia, oa, rows * n2, tw, cj | 2, (double)n, 1.0, st, launches)) != cudaSuccess) return e;
+    if ((e = tile_dispatch(l1, in, tmp, ia, oa, rows * n2, tw, cj | 2, (double)n, 1.0, st, launches)) != cudaSuccess) return e;
     // step 2: for every (row, k1): length-n2 FFT over j2 (contiguous), stored at out[row][k1 + n1*k2]
     if ((e = pass_twiddles(pc, l2, &tw)) != cudaSuccess) return e;
     RowAddr ib{n1, n, n2, 1}, ob{n1, n, 1, n1};
-    return rows_dispatch(l2, tmp, out, ib, ob, rows * n1, tw, cj, 1.0, scale, st, launches);
+    return tile_dispatch(l2, tmp, out, ib, ob, rows * n1, tw, cj, 1.0, scale, st, launches);
 }
 
 // ------------------------------------------------------------------ Bluestein (any n)
