@@ -290,13 +290,13 @@ struct Chain {
     // together with the coalesced twiddle tables, fp32 +5 %).  TSB_TMUL overrides, for tuning.
     static constexpr int T0 = (N / 16) < 32 ? 32 : (N / 16);
 #ifdef TSB_TMUL
-    static constexpr int TMUL = (PROG == PROG_PV_SHIFT && N >= 256) ? TSB_TMUL : 1;
+    static constexpr int TMUL = N >= 256 ? TSB_TMUL : 1;
 #else
-    static constexpr int TMUL = (PROG == PROG_PV_SHIFT && N >= 256 && N <= 2048) ? 2 : 1;
+    static constexpr int TMUL = (N >= 256 && N <= 2048) ? 2 : 1;
 #endif
     static constexpr int T = T0 * TMUL > 1024 ? 1024 : T0 * TMUL;
     // With twice the FFT's threads, the two halves of the CTA transform two frames at once (see run_lane).
-    static constexpr bool PIPE = (PROG == PROG_PV_SHIFT) && T == 2 * T0;
+    static constexpr bool PIPE = T == 2 * T0;
     static constexpr int HALF = M / 2;                       // split pairs (k, M-k), k < M/2
     static constexpr int S = (HALF + T - 1) / T;             // pair slots per thread
     static constexpr int PASSES = RadixPlan<LOG2M>::passes;
@@ -614,7 +614,7 @@ struct Chain {
     // ------------------------------------------------------------------ gain program: split * g -> C2R pre
     static TSB_HD void phase_gain(int tid, Smem &sm, const Tables &tb) {
         const C *Zc = fwd_result(sm);
-        C *H = fwd_spare(sm);
+        C *H = inv_buffer(sm, 0);  // not pipelined: the spare forward buffer; pipelined: ibuf[0]
 #pragma unroll
         for (int i = 0; i < S; i++) {
             int k = tid + T * i;
@@ -838,11 +838,18 @@ TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const t
         }
         for (int ff = 0; ff < total; ff++) {
             const int hop = hop_of(ff);
-            ex.each([&](int tid, Regs &rg) { CH::phase_pv_analyze(tid, sm, rg, tb); });
-            ex.each([&](int tid, Regs &rg) {
-                CH::phase_pv_synth(tid, sm, rg, tb);
-                CH::ring_wait();  // next frame's samples (requested a frame ago) are in the ring after this barrier
-            });
+            if (CH::IS_PV) {
+                ex.each([&](int tid, Regs &rg) { CH::phase_pv_analyze(tid, sm, rg, tb); });
+                ex.each([&](int tid, Regs &rg) {
+                    CH::phase_pv_synth(tid, sm, rg, tb);
+                    CH::ring_wait();  // next frame's samples (requested a frame ago) are in the ring after this barrier
+                });
+            } else {
+                ex.each([&](int tid, Regs &) {
+                    CH::phase_gain(tid, sm, tb);
+                    CH::ring_wait();
+                });
+            }
             const bool have_next = ff + 1 < total;
             const long long next_in = in_off + hop;
             int cnt = 0;
