@@ -292,7 +292,7 @@ struct Chain {
 #ifdef TSB_TMUL
     static constexpr int TMUL = N >= 256 ? TSB_TMUL : 1;
 #else
-    static constexpr int TMUL = (N >= 256 && N <= 2048) ? 2 : 1;
+    static constexpr int TMUL = (N >= 256 && N <= (sizeof(real) == 4 ? 4096 : 2048)) ? 2 : 1;  // fp64 at 4096: one 512-thread CTA per SM, measured slower
 #endif
     static constexpr int T = T0 * TMUL > 1024 ? 1024 : T0 * TMUL;
     // With twice the FFT's threads, the two halves of the CTA transform two frames at once (see run_lane).
