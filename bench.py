@@ -155,6 +155,9 @@ def main():
                     help="independent stereo streams per GPU (default: one full wave of resident CTAs, see STREAMS)")
     ap.add_argument("--seconds", type=float, default=60.0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-out", default="f32", choices=["f32", "f64"],
+                    help="sample type the end-to-end leg returns to the host: the reference's float32 stream (default) "
+                         "or, in fp64 mode, the unrounded float64 accumulation")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary figures (other precision, single stream)")
     args = ap.parse_args()
 
@@ -280,7 +283,10 @@ def main():
 
     # ---- end to end through the C ABI with HOST buffers (tsb_chain_render_host) ----
     if not args.no_e2e:
-        plan = tsb200.Plan(ctx, N_FRAME, precision=args.precision, program="pv", hop=HOP, rate=RATE, ratio=SHIFT)
+        # the reference hands float32 to JACK (tinyspec.cpp:43,173-200): the fp64 chain delivers that stream type
+        # (TSB_F64_OUT32: same arithmetic and PV state as the device leg, float32 tail/output as the reference's)
+        eprec = "f64o32" if (args.precision == "f64" and args.e2e_out == "f32") else args.precision
+        plan = tsb200.Plan(ctx, N_FRAME, precision=eprec, program="pv", hop=HOP, rate=RATE, ratio=SHIFT)
         xh = torch.empty((lanes, L), dtype=torch.float32, pin_memory=True)
         xh.copy_(x)
         oh = torch.empty((lanes, F * HOP), dtype=plan.out_dtype, pin_memory=True)
@@ -295,8 +301,10 @@ def main():
         ems = max_over_ranks((time.perf_counter() - t0) * 1e3) / esteps
         line["e2e"] = {"value": frames_all / (ems * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": lanes * L * 4,
                        "d2h_bytes_per_step": lanes * F * HOP * oh.element_size(), "ms_per_step": ems, "steps": esteps,
+                       "out_dtype": str(oh.dtype).replace("torch.", ""), "arithmetic": args.precision,
                        "api": "tsb_chain_render_host (pinned host buffers; upload + kernel + download inside the timed region)"}
         del oh, xh
+        ctx.trim()  # the context keeps the staging rows between calls: release them for the legs below
     # ---- secondary figures (rank 0 describes them; all ranks run them to stay in step) ----
     if not args.no_extras:
         oms, _, _ = device_leg(other, x_all[:S_other * CH], max(1, args.steps), 2)

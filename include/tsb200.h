@@ -29,7 +29,11 @@ extern "C" {
 #define TSB_ABI_VERSION 1
 
 enum { TSB_OK = 0, TSB_EINVAL = -1, TSB_ECUDA = -2, TSB_EUNSUPPORTED = -3, TSB_ENOMEM = -4 };
-enum { TSB_F32 = 0, TSB_F64 = 1 };            /* arithmetic of the chain (phase accumulators are fp64 in both) */
+/* arithmetic of the chain (phase accumulators are fp64 in all three).  TSB_F64_OUT32 computes like TSB_F64 and
+ * delivers the reference's own output type: a float32 stream whose overlap tail is kept in float32 and combined
+ * exactly as tinyspec.cpp:173-200 does (emitted sample = float(double(tail) + value), tail += float(value)), so it
+ * is comparable bit for bit with what the reference hands to JACK and moves half the bytes of TSB_F64. */
+enum { TSB_F32 = 0, TSB_F64 = 1, TSB_F64_OUT32 = 2 };
 enum { TSB_PROG_PV_SHIFT = 0, TSB_PROG_GAIN = 1 };
 enum { TSB_WIN_NONE = 0, TSB_WIN_HANN = 1, TSB_WIN_SQRT_HANN = 2 }; /* rtlib/windowfn.hpp:1-14 */
 
@@ -45,6 +49,9 @@ const char *tsb_last_error(void);
 int tsb_ctx_create(int device, void *cuda_stream, int new_stream, tsb_ctx **ctx);
 int tsb_ctx_destroy(tsb_ctx *ctx);
 int tsb_ctx_sync(tsb_ctx *ctx);
+/* The context keeps device scratch between calls (staging rows of tsb_chain_render_host, the time-parallel
+ * render's segment state, frft's work buffer): this waits for the stream and releases all of it. */
+int tsb_ctx_trim(tsb_ctx *ctx);
 /* device memory for bindings that have no CUDA runtime of their own (cgo / JNI / ctypes) */
 int tsb_malloc(tsb_ctx *ctx, size_t bytes, void **dptr);
 int tsb_free(tsb_ctx *ctx, void *dptr);
@@ -75,7 +82,7 @@ int tsb_shift_map(uint32_t n, double rate, const double *fn_bins, int32_t *dest)
  * and the per-bin phase constants of PhaseVocoder (rtlib/pv.hpp:39-48). */
 typedef struct tsb_plan_desc {
     uint32_t n;          /* frame size: power of two, 64..8192 */
-    int32_t precision;   /* TSB_F32 | TSB_F64 */
+    int32_t precision;   /* TSB_F32 | TSB_F64 | TSB_F64_OUT32 */
     int32_t program;     /* TSB_PROG_PV_SHIFT: pv.analyze(in); pv.shift(fn); pv.synthesize(out)  (hacks/pitchshift-pv.cpp:5-7)
                             TSB_PROG_GAIN:     window(in); frft(+1); spectrum *= gain; frft(-1); real; window(out) */
     int32_t win_in;      /* TSB_PROG_GAIN only (PV always uses sqrt-Hann twice, rtlib/pv.hpp:5,15) */
@@ -95,7 +102,7 @@ int tsb_plan_destroy(tsb_plan *plan);
  * tinyspec.cpp:170-200 (overlap-add).  All pointers are DEVICE pointers; the call is asynchronous on
  * the context's stream.
  *   in        [lanes][in_stride]  float32 (the reference's queues are float, tinyspec.cpp:43)
- *   out       [lanes][out_stride] float32 (TSB_F32) or float64 (TSB_F64): position p of a lane
+ *   out       [lanes][out_stride] float32 (TSB_F32, TSB_F64_OUT32) or float64 (TSB_F64): position p of a lane
  *             receives the finished overlap-added sample p; n_frames frames finish sum(hop) samples
  *   hop_tab   per-frame emitted samples (device, int32) or NULL for the constant `hop`
  *   state_*   float64 [lanes][n/2], [lanes][n/2], [lanes][n]: PhaseVocoder::last_phase / phase_sum

@@ -22,9 +22,9 @@ struct HostExec {
     }
 };
 
-template <typename real, int LOG2N, int PROG>
+template <typename real, int LOG2N, int PROG, bool OUT32>
 static int run(const PlanDesc &d, const ChainArgs &a) {
-    using CH = Chain<real, LOG2N, PROG>;
+    using CH = Chain<real, LOG2N, PROG, OUT32>;
     HostTables<real> ht = build_tables<real>(d);
     ChainTables<real> tb = ht.view();
     auto sm = std::make_unique<typename CH::Smem>();
@@ -36,17 +36,17 @@ static int run(const PlanDesc &d, const ChainArgs &a) {
     return 0;
 }
 
-template <typename real, int PROG>
+template <typename real, int PROG, bool OUT32 = false>
 static int by_size(int log2n, const PlanDesc &d, const ChainArgs &a) {
     switch (log2n) {
-        case 6: return run<real, 6, PROG>(d, a);
-        case 7: return run<real, 7, PROG>(d, a);
-        case 8: return run<real, 8, PROG>(d, a);
-        case 9: return run<real, 9, PROG>(d, a);
-        case 10: return run<real, 10, PROG>(d, a);
-        case 11: return run<real, 11, PROG>(d, a);
-        case 12: return run<real, 12, PROG>(d, a);
-        case 13: return run<real, 13, PROG>(d, a);
+        case 6: return run<real, 6, PROG, OUT32>(d, a);
+        case 7: return run<real, 7, PROG, OUT32>(d, a);
+        case 8: return run<real, 8, PROG, OUT32>(d, a);
+        case 9: return run<real, 9, PROG, OUT32>(d, a);
+        case 10: return run<real, 10, PROG, OUT32>(d, a);
+        case 11: return run<real, 11, PROG, OUT32>(d, a);
+        case 12: return run<real, 12, PROG, OUT32>(d, a);
+        case 13: return run<real, 13, PROG, OUT32>(d, a);
     }
     return -1;
 }
@@ -77,6 +77,9 @@ extern "C" int emul_chain_render(int precision, int log2n, int program, int win_
     a.n_seg = 0; a.seg_tab = nullptr; a.mode = 0; a.st_warm_phase = nullptr;
     if (precision == 0)
         return program == PROG_PV_SHIFT ? by_size<float, PROG_PV_SHIFT>(log2n, d, a) : by_size<float, PROG_GAIN>(log2n, d, a);
+    if (precision == 2)
+        return program == PROG_PV_SHIFT ? by_size<double, PROG_PV_SHIFT, true>(log2n, d, a)
+                                        : by_size<double, PROG_GAIN, true>(log2n, d, a);
     return program == PROG_PV_SHIFT ? by_size<double, PROG_PV_SHIFT>(log2n, d, a) : by_size<double, PROG_GAIN>(log2n, d, a);
 }
 

@@ -44,13 +44,14 @@ def chain_render(x, n, hop, n_frames, precision="f64", program="pv", ratio=2.0, 
         out_len = out_off0 + (int(np.sum(hop_tab)) if hop_tab is not None else n_frames * hop)
     dt = np.float64 if precision == "f64" else np.float32
     out = np.zeros((lanes, out_len), dt)
+    prec = {"f32": 0, "f64": 1, "f64o32": 2}[precision]
     load = state is not None
     if state is None:
         state = dict(last_phase=np.zeros((lanes, m)), phase_sum=np.zeros((lanes, m)), ola=np.zeros((lanes, n)))
     ht = None if hop_tab is None else np.ascontiguousarray(hop_tab, np.int32)
     g = None if gain is None else np.ascontiguousarray(gain, np.float64)
     fb = None if fn_bins is None else np.ascontiguousarray(fn_bins, np.float64)
-    r = lib().emul_chain_render(1 if precision == "f64" else 0, int(np.log2(n)), 0 if program == "pv" else 1,
+    r = lib().emul_chain_render(prec, int(np.log2(n)), 0 if program == "pv" else 1,
                                 WIN[win_in], WIN[win_out], float(hop if hop_d is None else hop_d), rate, ratio,
                                 _p(fb), _p(g), _p(x), L, L, _p(out), out_len, out_len, n_frames, in_off0, out_off0,
                                 int(hop), _p(ht), _p(state["last_phase"]), _p(state["phase_sum"]), _p(state["ola"]),

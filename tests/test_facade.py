@@ -73,6 +73,23 @@ def test_fused_pitchshift(precision):
 
 
 @pytest.mark.gpu
+def test_fused_pitchshift_default_output_is_the_reference_float_stream():
+    """fp64 mode without --out-f64: the fused launch itself keeps the float32 overlap tail and narrows as
+    tinyspec.cpp:173-200 does, so the file is the reference's float32 stream."""
+    from oracle import orc
+    b = build(os.path.join(EX, "pitchshift_cfg1.cpp"))
+    r, info, y = render(b, "--seconds", 1.0, "--streams", 2, lanes=4)
+    assert r.returncode == 0, r.stderr
+    assert info["mode"] == "fused" and info["gpu_launches"] == 1
+    for s in range(2):
+        ref = orc.render_pv(orc.gen_signal(s, 2, 48000), 1024, 0.25, 2.0)
+        want = ref["stream"].T
+        got = y[2 * s:2 * s + 2, :want.shape[1]]
+        assert (got == want).mean() > 0.999
+        assert np.abs(got.astype(np.float64) - want).max() <= 2.0 ** -23 * np.abs(want).max()
+
+
+@pytest.mark.gpu
 def test_immediate_pitchshift_matches_reference_stream():
     """Immediate mode runs the reference's loop with device operators, float32 overlap tail included: the output
     is the reference's float32 stream up to the last bit of float rounding."""

@@ -379,3 +379,50 @@ def test_two_minute_render_does_not_diverge(env):
             assert rmsrel(got[:, tail], want[:, tail]) <= F32_RMSREL   # no growth towards the end
             flips = dps > 1
             assert np.all(np.abs(dps[flips] / (4 * np.pi) - np.round(dps[flips] / (4 * np.pi))) < 1e-3)  # multiples of 4*pi
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,hr,shift,ch,samples", [(1024, 0.25, 2.0, 2, 96000), (4096, 0.25, 1.5, 8, 60000),
+                                                   (256, 0.3, 1.5, 2, 9000), (64, 1.6, 1.5, 1, 9000),
+                                                   (512, 0.2003, 0.75, 1, 16000), (8192, 0.25, 1.5, 1, 60000)])
+def test_f64_out32_is_the_reference_float_stream(env, n, hr, shift, ch, samples):
+    """TSB_F64_OUT32 (fp64 arithmetic, float32 tail/output combined as tinyspec.cpp:173-200): the output is the
+    reference's own float32 stream — identical samples except where the ~1e-10 arithmetic difference straddles a
+    float32 rounding boundary (then one float32 step of the tail) — and the PV state is that of the fp64 mode."""
+    orc = env["orc"]
+    x = orc.gen_signal(2, ch, samples)
+    ref = orc.render_pv(x, n, hr, shift)
+    out, F, st = run_pv(env, x, n, hr, shift, "f64o32")
+    assert out.dtype == np.float32
+    want = ref["stream"][:out.shape[1]].T
+    assert np.count_nonzero(out != want) <= 1e-3 * out.size
+    assert np.abs(out.astype(np.float64) - want).max() <= 2.0 ** -23 * np.abs(want).max()
+    _, _, st64 = run_pv(env, x, n, hr, shift, "f64")
+    assert np.array_equal(st["phase_sum"], st64["phase_sum"]) and np.array_equal(st["last_phase"], st64["last_phase"])
+    # host-buffer path: same bits, also from the staging buffers the context kept, also after releasing them
+    for rep in range(3):
+        outh, _, _ = run_pv(env, x, n, hr, shift, "f64o32", host=True)
+        assert np.array_equal(outh, out)
+        if rep == 1:
+            env["ctx"].trim()
+
+
+@pytest.mark.gpu
+def test_f64_out32_stream_and_timepar(env):
+    torch, tsb, orc = env["torch"], env["tsb"], env["orc"]
+    n, hr, ch, samples = 1024, 0.25, 2, 120000
+    x = orc.gen_signal(4, ch, samples)
+    whole, F, _ = run_pv(env, x, n, hr, 1.5, "f64o32")
+    plan = tsb.Plan(env["ctx"], n, precision="f64o32", program="pv", hop=n * hr, ratio=1.5)
+    st = tsb.Stream(plan, ch, n * hr)
+    parts = [st.process(np.ascontiguousarray(x[p:p + 5000].T)) for p in range(0, samples, 5000)]
+    got = np.concatenate(parts, axis=1)
+    assert got.dtype == np.float32 and np.array_equal(got, whole)
+    # time-parallel: the tails of earlier segments are added afterwards (regrouped float32 additions)
+    xd = torch.from_numpy(np.ascontiguousarray(x.T)).cuda()
+    sch = tsb.schedule_const(samples, n, n * hr)
+    tp = plan.render_timepar(xd, F, int(sch["hop"][0]), in_off0=int(sch["in_off"][0]), n_segments=16)
+    torch.cuda.synchronize()
+    tp = tp.cpu().numpy()
+    assert tp.dtype == np.float32
+    assert np.abs(tp.astype(np.float64) - whole).max() <= 4 * 2.0 ** -23 * np.abs(whole).max()

@@ -93,3 +93,34 @@ def test_pv_chain_hop_edge_cases(n, hr, shift, samples):
     out, _ = emul.chain_render(x.T, n, int(tabs["hop"][0]), F, precision="f64", ratio=shift, hop_d=n * hr,
                                hop_tab=None if const else tabs["hop"])
     assert maxrel(out, ref["ola64"][:out.shape[1]].T) < 1e-11
+
+
+@pytest.mark.parametrize("n,hr,shift,ch,samples", [(1024, 0.25, 2.0, 2, 30000), (256, 0.3, 1.5, 2, 9000),
+                                                   (64, 1.6, 1.5, 1, 9000), (512, 0.2003, 0.75, 1, 12000)])
+def test_pv_chain_float32_output_is_the_reference_stream(n, hr, shift, ch, samples):
+    """TSB_F64_OUT32: fp64 arithmetic, float32 tail and output combined as tinyspec.cpp:173-200 does.  The result is
+    the reference's own float32 stream (what it hands to JACK): identical except where the 1e-10 arithmetic
+    difference straddles a float32 rounding boundary, and then off by one float32 step of the running tail."""
+    x = orc.gen_signal(2, ch, samples)
+    ref = orc.render_pv(x, n, hr, shift, want_tables=True)
+    tabs, F = ref["tables"], ref["frames"]
+    const = bool(np.all(tabs["hop"] == tabs["hop"][0]))
+    out, st = emul.chain_render(x.T, n, int(tabs["hop"][0]), F, precision="f64o32", ratio=shift, hop_d=n * hr,
+                                hop_tab=None if const else tabs["hop"])
+    want = ref["stream"][:out.shape[1]].T
+    assert out.dtype == np.float32 and want.dtype == np.float32
+    differ = np.count_nonzero(out != want)
+    assert differ <= 1e-3 * out.size
+    assert np.abs(out.astype(np.float64) - want).max() <= 2.0 ** -23 * np.abs(want).max()
+    # the tail handed on is float32-valued
+    assert np.array_equal(st["ola"], st["ola"].astype(np.float32).astype(np.float64))
+
+
+def test_gain_chain_float32_output_is_the_reference_stream():
+    x = orc.gen_signal(0, 2, 2048 + 12 * 2048)
+    gain = 1.0 / (1.0 + np.arange(1025) / 64.0)
+    ref = orc.render_filter(x, 2048, 0.25, gain)
+    out, _ = emul.chain_render(x.T, 2048, 512, ref["frames"], precision="f64o32", program="gain", gain=gain)
+    want = ref["stream"][:out.shape[1]].T
+    assert np.count_nonzero(out != want) <= 1e-3 * out.size
+    assert np.abs(out.astype(np.float64) - want).max() <= 2.0 ** -23 * np.abs(want).max()

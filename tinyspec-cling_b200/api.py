@@ -5,11 +5,11 @@ import os
 
 import numpy as np
 
-F32, F64 = 0, 1
+F32, F64, F64_OUT32 = 0, 1, 2
 PROG_PV_SHIFT, PROG_GAIN = 0, 1
 WIN_NONE, WIN_HANN, WIN_SQRT_HANN = 0, 1, 2
 _WIN = {None: 0, "none": 0, "hann": 1, "sqrt_hann": 2, 0: 0, 1: 1, 2: 2}
-_PREC = {"f32": 0, "f64": 1, 0: 0, 1: 1}
+_PREC = {"f32": 0, "f64": 1, "f64o32": 2, 0: 0, 1: 1, 2: 2}
 _PROG = {"pv": 0, "pv_shift": 0, "gain": 1, 0: 0, 1: 1}
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -55,6 +55,7 @@ def _load():
     L.tsb_ctx_create.argtypes = [C.c_int, P, C.c_int, C.POINTER(P)]
     L.tsb_ctx_destroy.argtypes = [P]
     L.tsb_ctx_sync.argtypes = [P]
+    L.tsb_ctx_trim.argtypes = [P]
     L.tsb_launch_count.argtypes = [P]
     L.tsb_launch_count.restype = C.c_int64
     L.tsb_hop_fixed.argtypes = [C.c_double, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -151,6 +152,10 @@ class Context:
 
     def sync(self):
         _check(_load().tsb_ctx_sync(self.h))
+
+    def trim(self):
+        """release the device scratch the context keeps between calls (host-render staging, time-parallel state)"""
+        _check(_load().tsb_ctx_trim(self.h))
 
     @property
     def launches(self):
@@ -275,7 +280,8 @@ class Plan:
                 t = state[k]
                 assert t.is_cuda and t.dtype == torch.float64 and t.shape == (lanes, w) and t.is_contiguous()
             st = (state["last_phase"].data_ptr(), state["phase_sum"].data_ptr(), state["ola"].data_ptr())
-        a = self._args(lanes, x.data_ptr(), x.stride(0), L, out.data_ptr(), out.stride(0), out.shape[1], n_frames,
+        a = self._args(lanes, x.data_ptr(), x.stride(0) if lanes > 1 else L, L, out.data_ptr(),
+                       out.stride(0) if lanes > 1 else out.shape[1], out.shape[1], n_frames,
                        in_off0, out_off0, hop, None if ht is None else ht.data_ptr(), st, load_state)
         _check(_load().tsb_chain_render(self.ctx.h, self.h, C.byref(a)))
         self._keep = (x, out, ht, state)
@@ -304,7 +310,8 @@ class Plan:
                 t = state[k]
                 assert t.is_cuda and t.dtype == torch.float64 and t.shape == (lanes, w) and t.is_contiguous()
             st = (state["last_phase"].data_ptr(), state["phase_sum"].data_ptr(), state["ola"].data_ptr())
-        a = self._args(lanes, x.data_ptr(), x.stride(0), L, out.data_ptr(), out.stride(0), out.shape[1], n_frames,
+        a = self._args(lanes, x.data_ptr(), x.stride(0) if lanes > 1 else L, L, out.data_ptr(),
+                       out.stride(0) if lanes > 1 else out.shape[1], out.shape[1], n_frames,
                        in_off0, out_off0, hop, None if ht is None else ht.data_ptr(), st, load_state)
         return a, out, ht, ht_host
 
@@ -352,7 +359,9 @@ class Plan:
             for k, w in (("last_phase", self.n // 2), ("phase_sum", self.n // 2), ("ola", self.n)):
                 assert state[k].dtype == np.float64 and state[k].shape == (lanes, w)
             st = tuple(state[k].ctypes.data for k in ("last_phase", "phase_sum", "ola"))
-        a = self._args(lanes, xt.data_ptr(), xt.stride(0), L, ot.data_ptr(), ot.stride(0), ot.shape[1], n_frames,
+        # (a size-1 dimension reports an arbitrary stride)
+        a = self._args(lanes, xt.data_ptr(), xt.stride(0) if lanes > 1 else L, L, ot.data_ptr(),
+                       ot.stride(0) if lanes > 1 else ot.shape[1], ot.shape[1], n_frames,
                        in_off0, out_off0, hop, None if ht is None else ht.ctypes.data, st, load_state)
         _check(_load().tsb_chain_render_host(self.ctx.h, self.h, C.byref(a)))
         return out

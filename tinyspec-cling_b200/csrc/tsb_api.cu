@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdarg>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -44,6 +45,11 @@ struct tsb_ctx {
     char *tp_pool = nullptr;                              // scratch of the time-parallel render, reused call to call
     size_t tp_pool_bytes = 0;
     bool tp_pool_busy = false;
+    // staging of the host-buffer render, kept call to call (allocating and freeing tens of GB per call cost
+    // 100-400 ms on the test boxes, more than the render itself); tsb_ctx_trim releases it
+    void *host_stage[2] = {nullptr, nullptr};             // device copies of the caller's input / output rows
+    size_t host_stage_bytes[2] = {0, 0};
+    std::vector<cudaStream_t> host_streams;               // [0] uploads, [1] downloads, [2..] one per lane chunk
 };
 
 struct tsb_plan {
@@ -97,7 +103,29 @@ TSB_API int tsb_ctx_destroy(tsb_ctx *c) {
     for (auto &kv : c->windows) cudaFree(kv.second);
     if (c->scratch) cudaFree(c->scratch);
     if (c->tp_pool) cudaFree(c->tp_pool);
+    for (void *q : c->host_stage)
+        if (q) cudaFree(q);
+    for (cudaStream_t st : c->host_streams) cudaStreamDestroy(st);
     delete c;
+    return TSB_OK;
+}
+TSB_API int tsb_ctx_trim(tsb_ctx *c) {
+    if (!c) return fail(TSB_EINVAL, "null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 2; i++) {
+        if (c->host_stage[i]) cudaFree(c->host_stage[i]);
+        c->host_stage[i] = nullptr;
+        c->host_stage_bytes[i] = 0;
+    }
+    if (c->tp_pool && !c->tp_pool_busy) {
+        cudaFree(c->tp_pool);
+        c->tp_pool = nullptr;
+        c->tp_pool_bytes = 0;
+    }
+    if (c->scratch) cudaFree(c->scratch);
+    c->scratch = nullptr;
+    c->scratch_bytes = 0;
     return TSB_OK;
 }
 TSB_API int tsb_ctx_sync(tsb_ctx *c) {
@@ -215,7 +243,7 @@ TSB_API int tsb_plan_create(tsb_ctx *c, const tsb_plan_desc *desc, tsb_plan **ou
     uint32_t n = desc->n;
     if (n < 64 || n > 8192 || (n & (n - 1)))
         return fail(TSB_EUNSUPPORTED, "frame size %u: the fused chain supports powers of two in 64..8192", n);
-    if (desc->precision != TSB_F32 && desc->precision != TSB_F64) return fail(TSB_EINVAL, "bad precision %d", desc->precision);
+    if (desc->precision != TSB_F32 && desc->precision != TSB_F64 && desc->precision != TSB_F64_OUT32) return fail(TSB_EINVAL, "bad precision %d", desc->precision);
     if (desc->program != TSB_PROG_PV_SHIFT && desc->program != TSB_PROG_GAIN) return fail(TSB_EINVAL, "bad program %d", desc->program);
     if (desc->program == TSB_PROG_PV_SHIFT && !(desc->hop > 0)) return fail(TSB_EINVAL, "phase vocoder needs hop > 0 (got %g)", desc->hop);
     if (!(desc->rate > 0)) return fail(TSB_EINVAL, "bad rate %g", desc->rate);
@@ -266,6 +294,10 @@ static int check_args(const tsb_chain_args *a) {
     if (a->lanes && a->n_frames && (!a->in || !a->out)) return fail(TSB_EINVAL, "null in/out");
     if (!a->hop_tab && a->hop < 0) return fail(TSB_EINVAL, "negative hop");
     if (a->in_off0 < 0 || a->out_off0 < 0) return fail(TSB_EINVAL, "negative offset");
+    if (a->in_len < 0 || a->out_len < 0) return fail(TSB_EINVAL, "negative row length");
+    if (a->lanes > 1 && (a->in_stride < a->in_len || a->out_stride < a->out_len))
+        return fail(TSB_EINVAL, "row stride shorter than the row (in %lld < %lld or out %lld < %lld)", (long long)a->in_stride,
+                    (long long)a->in_len, (long long)a->out_stride, (long long)a->out_len);
     return TSB_OK;
 }
 static ChainArgs to_args(const tsb_chain_args *a) {
@@ -301,26 +333,35 @@ TSB_API int tsb_chain_render(tsb_ctx *c, tsb_plan *p, const tsb_chain_args *a) {
 // engines; the chunk kernels share the SMs).  Row-strided 2-D copies of time blocks were measured 10-20x slower
 // than contiguous ones on this platform (tools/pcie_probe.py), hence lanes, not time, are the pipeline axis.
 // Per-lane results are bit-identical to tsb_chain_render.
-TSB_API int tsb_chain_render_host(tsb_ctx *c, tsb_plan *p, const tsb_chain_args *a) {
+TSB_API int tsb_chain_render_host(tsb_ctx *c, tsb_plan *p, const tsb_chain_args *a_in) {
     if (!c || !p) return fail(TSB_EINVAL, "null context / plan");
-    int r = check_args(a);
+    int r = check_args(a_in);
     if (r) return r;
-    if (a->lanes == 0 || a->n_frames == 0) return TSB_OK;
+    if (a_in->lanes == 0 || a_in->n_frames == 0) return TSB_OK;
+    tsb_chain_args a_norm = *a_in;
+    if (a_norm.lanes == 1) {  // a single row: its stride means nothing (numpy reports 1 for it), the row is what is copied
+        a_norm.in_stride = a_norm.in_len;
+        a_norm.out_stride = a_norm.out_len;
+    }
+    const tsb_chain_args *a = &a_norm;
     CU(cudaSetDevice(c->device));
     const int64_t n = p->desc.n, m = n / 2, lanes = a->lanes, F = a->n_frames;
-    const size_t osz = p->desc.precision == TSB_F32 ? 4 : 8;
+    const size_t osz = p->desc.precision == TSB_F64 ? 8 : 4;
     const size_t in_bytes = (size_t)lanes * a->in_stride * 4, out_bytes = (size_t)lanes * a->out_stride * osz;
-    // chunks: enough lanes each to keep copies large (>= 256 MB) and at most 8 chunks
+    // chunks: enough lanes each to keep copies large (>= 256 MB) and at most 16 chunks
     int64_t nc = (int64_t)((in_bytes + out_bytes) / (512ull << 20));
-    nc = nc < 1 ? 1 : (nc > 8 ? 8 : nc);
+    nc = nc < 1 ? 1 : (nc > 16 ? 16 : nc);
+    if (const char *ev = getenv("TSB_HOST_CHUNKS")) nc = atoi(ev) > 0 ? atoi(ev) : nc;  // tuning
     if (nc > lanes) nc = lanes;
+    const bool trace = getenv("TSB_HOST_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    double t_alloc = 0, t_enq = 0, t_sync = 0;
     struct Res {
         std::vector<void *> ptrs;
         std::vector<cudaEvent_t> evs;
-        std::vector<cudaStream_t> streams;
         ~Res() {
             for (cudaEvent_t e : evs) cudaEventDestroy(e);
-            for (cudaStream_t s : streams) cudaStreamDestroy(s);
             for (void *q : ptrs) cudaFree(q);
         }
         void *get(size_t bytes) {
@@ -335,16 +376,28 @@ TSB_API int tsb_chain_render_host(tsb_ctx *c, tsb_plan *p, const tsb_chain_args 
             evs.push_back(e);
             return e;
         }
-        cudaStream_t stream() {
-            cudaStream_t s = nullptr;
-            cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
-            streams.push_back(s);
-            return s;
-        }
     } res;
-    float *din = (float *)res.get(in_bytes);
-    char *dout = (char *)res.get(out_bytes);
-    if (!din || !dout) return fail(TSB_ENOMEM, "device allocation of %zu + %zu bytes failed", in_bytes, out_bytes);
+    // staging rows and streams live in the context (grow-only; tsb_ctx_trim frees them)
+    const size_t want[2] = {in_bytes, out_bytes};
+    for (int i = 0; i < 2; i++) {
+        if (c->host_stage_bytes[i] >= want[i]) continue;
+        if (c->host_stage[i]) cudaFree(c->host_stage[i]);
+        c->host_stage[i] = nullptr;
+        c->host_stage_bytes[i] = 0;
+        if (cudaMalloc(&c->host_stage[i], want[i] ? want[i] : 16) != cudaSuccess) {
+            c->host_stage[i] = nullptr;
+            (void)cudaGetLastError();
+            return fail(TSB_ENOMEM, "device allocation of %zu bytes for the host-buffer render failed", want[i]);
+        }
+        c->host_stage_bytes[i] = want[i];
+    }
+    while ((int64_t)c->host_streams.size() < nc + 2) {
+        cudaStream_t st = nullptr;
+        CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        c->host_streams.push_back(st);
+    }
+    float *din = (float *)c->host_stage[0];
+    char *dout = (char *)c->host_stage[1];
     int32_t *dhops = nullptr;
     if (a->hop_tab) {
         dhops = (int32_t *)res.get((size_t)F * 4);
@@ -362,7 +415,8 @@ TSB_API int tsb_chain_render_host(tsb_ctx *c, tsb_plan *p, const tsb_chain_args 
     }
     cudaEvent_t setup = res.ev();
     CU(cudaEventRecord(setup, c->stream));
-    cudaStream_t s_in = res.stream(), s_out = res.stream();
+    t_alloc = now();
+    cudaStream_t s_in = c->host_streams[0], s_out = c->host_streams[1];
     CU(cudaStreamWaitEvent(s_in, setup, 0));
     cudaStream_t saved = c->stream;
     int rc = TSB_OK;
@@ -370,7 +424,7 @@ TSB_API int tsb_chain_render_host(tsb_ctx *c, tsb_plan *p, const tsb_chain_args 
     for (int64_t k = 0; k < nc && rc == TSB_OK; k++) {
         int64_t cnt = lanes / nc + (k < lanes % nc ? 1 : 0);
         cudaEvent_t in_done = res.ev(), k_done = res.ev();
-        cudaStream_t s_k = res.stream();
+        cudaStream_t s_k = c->host_streams[2 + k];
         cudaError_t e = cudaMemcpyAsync(din + (size_t)l0 * a->in_stride, a->in + (size_t)l0 * a->in_stride,
                                         (size_t)cnt * a->in_stride * 4, cudaMemcpyHostToDevice, s_in);
         if (e == cudaSuccess) e = cudaEventRecord(in_done, s_in);
@@ -402,8 +456,13 @@ TSB_API int tsb_chain_render_host(tsb_ctx *c, tsb_plan *p, const tsb_chain_args 
         if (e != cudaSuccess) { rc = fail(TSB_ECUDA, "download: %s", cudaGetErrorString(e)); break; }
         l0 += cnt;
     }
-    for (cudaStream_t s : res.streams) cudaStreamSynchronize(s);
+    t_enq = now();
+    for (int64_t k = 0; k < nc + 2; k++) cudaStreamSynchronize(c->host_streams[k]);
     CU(cudaStreamSynchronize(c->stream));
+    t_sync = now();
+    if (trace)
+        fprintf(stderr, "[tsb host render] chunks %lld  alloc %.1f ms  enqueue %.1f ms  wait %.1f ms  (in %.2f GB, out %.2f GB)\n",
+                (long long)nc, t_alloc - t_begin, t_enq - t_alloc, t_sync - t_enq, in_bytes / 1e9, out_bytes / 1e9);
     return rc;
 }
 
@@ -840,7 +899,7 @@ TSB_API int tsb_stream_process(tsb_stream *s, const float *host_in, int64_t in_s
     tsb_ctx *c = s->ctx;
     CU(cudaSetDevice(c->device));
     const int64_t n = s->plan->desc.n, lanes = s->lanes;
-    const size_t osz = s->plan->desc.precision == TSB_F32 ? 4 : 8;
+    const size_t osz = s->plan->desc.precision == TSB_F64 ? 8 : 4;
     *out_len = 0;
     // append the chunk to the pending input (rows hold absolute samples [base, pushed))
     int64_t have = s->pushed - s->base, need = have + len;

@@ -33,6 +33,8 @@
 // C2R(Z)[n]/sqrt(N) with Z[k] = (conj(Y[k]) + Y[N-k])/2.  1/sqrt(N) (and the 1/2 of the PV case,
 // where Y[k>=N/2] = 0 after shift) are folded into the window tables.
 #pragma once
+#include <type_traits>
+
 #include "tsb_math.cuh"
 
 namespace tsb {
@@ -45,12 +47,16 @@ enum Program { PROG_PV_SHIFT = 0, PROG_GAIN = 1 };
 TSB_D double mul_rn(double a, double b) { return __dmul_rn(a, b); }
 TSB_D double add_rn(double a, double b) { return __dadd_rn(a, b); }
 TSB_D double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+TSB_D float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+TSB_D float add_rn(float a, float b) { return __fadd_rn(a, b); }
 TSB_D int d2i_rz(double a) { return __double2int_rz(a); }
 TSB_D long long d2ll_rn(double a) { return __double2ll_rn(a); }
 #else
 inline double mul_rn(double a, double b) { return a * b; }  // host harness is built with -ffp-contract=off
 inline double add_rn(double a, double b) { return a + b; }
 inline double sub_rn(double a, double b) { return a - b; }
+inline float mul_rn(float a, float b) { return a * b; }
+inline float add_rn(float a, float b) { return a + b; }
 inline int d2i_rz(double a) { return (int)a; }
 inline long long d2ll_rn(double a) { return llrint(a); }
 #endif
@@ -278,8 +284,11 @@ struct PvMath<float> {
     }
 };
 
-template <typename real, int LOG2N, int PROG>
+// OUT32 (fp64 arithmetic only): the output row and the overlap tail are float32 and are combined exactly as the
+// reference's scheduler does (tinyspec.cpp:173-200): emitted sample = float(double(tail) + v), tail += float(v).
+template <typename real, int LOG2N, int PROG, bool OUT32 = false>
 struct Chain {
+    static_assert(!OUT32 || sizeof(real) == 8, "OUT32 is the float32-output variant of the fp64 chain");
     static constexpr int N = 1 << LOG2N;
     static constexpr int LOG2M = LOG2N - 1;
     static constexpr int M = N / 2;
@@ -304,10 +313,12 @@ struct Chain {
     using C = cpx<real>;
     using Tables = ChainTables<real>;
     using SW = Swz<real>;
+    using otype = typename std::conditional<OUT32, float, real>::type;  // element of the output row and of the tail
+    using OC = cpx<otype>;
 
     struct Smem {
         float ring[N];
-        real ola[N];
+        otype ola[N];
         C buf[2][M];  // ping-pong FFT buffers, swizzled (Swz<real>)
         // software pipeline (PIPE): the inverse transform of frame f runs on its own buffers while the other
         // half of the threads runs the forward transform of frame f+1 in `buf`
@@ -383,8 +394,8 @@ struct Chain {
             }
         }
         for (int i = tid; i < N; i += T) {
-            real v = 0;
-            if (ld && a.st_ola && a.mode == 0) v = (real)a.st_ola[sg.row * N + i];
+            otype v = 0;
+            if (ld && a.st_ola && a.mode == 0) v = (otype)a.st_ola[sg.row * N + i];
             sm.ola[(int)((sg.out_off0 + i) & (N - 1))] = v;
         }
     }
@@ -649,43 +660,50 @@ struct Chain {
             auto out = [&](int x, int c, C v) { st_sw(dst, x, c, v); };
             stockham_pass_io<real, LOG2M, NT, P>(tid, tb.tw, in, out);
         } else {
-            real *dstg = reinterpret_cast<real *>(a.out) + (long long)lane * a.out_stride + out_pos;
+            otype *dstg = reinterpret_cast<otype *>(a.out) + (long long)lane * a.out_stride + out_pos;
             const C *ws = reinterpret_cast<const C *>(tb.win_s);
             const int ob = (int)(out_pos & (N - 1));
             // samples of this frame that may be written: n < lim (everything when the row has room)
             const long long room = a.out_len - out_pos;
             const int lim = room >= (long long)N + hop ? 0x7fffffff : (room < 0 ? 0 : (int)room);
+            // one output sample: `done` positions leave the chip, the others stay in the tail.  OUT32 follows the
+            // reference's types: the finished sample is the float of (float tail + double value) (:180), the tail
+            // accumulates the value narrowed first, in float (:195-197).
+            // Products and sums are single IEEE operations (no FMA contraction): a sample must not depend on which
+            // of the two code paths below produced it (chunked and whole renders are bit-identical).
+            auto emit_val = [](otype tail, real v) -> otype { return (otype)add_rn((real)tail, v); };
+            auto tail_val = [](otype tail, real v) -> otype { return OUT32 ? add_rn(tail, (otype)v) : (otype)add_rn((real)tail, v); };
             if (((ob | hop | (lim == 0x7fffffff ? 0 : lim)) & 1) == 0 &&
-                ((reinterpret_cast<uintptr_t>(dstg) & (2 * sizeof(real) - 1)) == 0)) {
+                ((reinterpret_cast<uintptr_t>(dstg) & (2 * sizeof(otype) - 1)) == 0)) {
                 // pairs (2m, 2m+1) never straddle the hop boundary or the end of the row and are aligned in the
                 // ring and in the row: one 2-sample load / add / (predicated) store per pair, no branches
-                C *ola2 = reinterpret_cast<C *>(sm.ola);
+                OC *ola2 = reinterpret_cast<OC *>(sm.ola);
                 const int ob2 = ob >> 1;
                 const int emit_end = hop < lim ? hop : lim;
                 auto out = [&](int x, int c, C f) {
                     const int m = x + c;
                     C w = TSB_LDG(ws + m);
-                    C *slot = &ola2[(ob2 + m) & (M - 1)];
-                    C acc = *slot;
-                    acc.x += f.x * w.x;
-                    acc.y -= f.y * w.y;
+                    OC *slot = &ola2[(ob2 + m) & (M - 1)];
+                    const OC t = *slot;
+                    const real vx = mul_rn(f.x, w.x), vy = -mul_rn(f.y, w.y);
                     const bool done = 2 * m < hop;
-                    if (2 * m < emit_end) *reinterpret_cast<C *>(dstg + 2 * m) = acc;
-                    *slot = mk<real>(done ? (real)0 : acc.x, done ? (real)0 : acc.y);
+                    if (2 * m < emit_end) *reinterpret_cast<OC *>(dstg + 2 * m) = mk<otype>(emit_val(t.x, vx), emit_val(t.y, vy));
+                    *slot = mk<otype>(done ? (otype)0 : tail_val(t.x, vx), done ? (otype)0 : tail_val(t.y, vy));
                 };
                 stockham_pass_io<real, LOG2M, NT, P>(tid, tb.tw, in, out);
             } else {
                 auto out = [&](int x, int c, C f) {
                     const int m = x + c;
                     C w = TSB_LDG(ws + m);
-                    real v[2] = {f.x * w.x, -f.y * w.y};
+                    real v[2] = {mul_rn(f.x, w.x), -mul_rn(f.y, w.y)};
 #pragma unroll
                     for (int u = 0; u < 2; u++) {
                         int n = 2 * m + u;
                         int slot = (ob + n) & (N - 1);
-                        real acc = sm.ola[slot] + v[u];
+                        otype t = sm.ola[slot];
+                        otype acc = tail_val(t, v[u]);
                         if (n < hop) {
-                            if (n < lim) dstg[n] = acc;
+                            if (n < lim) dstg[n] = emit_val(t, v[u]);
                             acc = 0;
                         }
                         sm.ola[slot] = acc;

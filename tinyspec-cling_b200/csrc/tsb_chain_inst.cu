@@ -42,10 +42,10 @@ constexpr int min_blocks() {
 template <class CH>
 constexpr int default_carveout_kb() { return 228; }
 
-template <typename real, int LOG2N, int PROG>
-__global__ void __launch_bounds__(Chain<real, LOG2N, PROG>::T, min_blocks<Chain<real, LOG2N, PROG>>())
+template <typename real, int LOG2N, int PROG, bool OUT32>
+__global__ void __launch_bounds__(Chain<real, LOG2N, PROG, OUT32>::T, min_blocks<Chain<real, LOG2N, PROG, OUT32>>())
 chain_kernel(const ChainTables<real> tb, const ChainArgs a) {
-    using CH = Chain<real, LOG2N, PROG>;
+    using CH = Chain<real, LOG2N, PROG, OUT32>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typename CH::Smem &sm = *reinterpret_cast<typename CH::Smem *>(smem_raw);
     DevExec<CH> ex;
@@ -54,10 +54,10 @@ chain_kernel(const ChainTables<real> tb, const ChainArgs a) {
         run_lane<CH>(ex, (int)(b % a.lanes), (int)(b / a.lanes), sm, tb, a);
 }
 
-template <typename real, int LOG2N, int PROG>
+template <typename real, int LOG2N, int PROG, bool OUT32 = false>
 static cudaError_t launch(const void *tables, const ChainArgs &a, cudaStream_t stream) {
-    using CH = Chain<real, LOG2N, PROG>;
-    auto kern = chain_kernel<real, LOG2N, PROG>;
+    using CH = Chain<real, LOG2N, PROG, OUT32>;
+    auto kern = chain_kernel<real, LOG2N, PROG, OUT32>;
     size_t smem = sizeof(typename CH::Smem);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -82,6 +82,10 @@ cudaError_t TSB_CAT(launch_chain_, TSB_LOG2N)(int precision, int program, const 
     if (precision == 0) {
         return program == PROG_PV_SHIFT ? launch<float, TSB_LOG2N, PROG_PV_SHIFT>(tables, a, stream)
                                         : launch<float, TSB_LOG2N, PROG_GAIN>(tables, a, stream);
+    }
+    if (precision == 2) {  // fp64 arithmetic, float32 output stream (TSB_F64_OUT32)
+        return program == PROG_PV_SHIFT ? launch<double, TSB_LOG2N, PROG_PV_SHIFT, true>(tables, a, stream)
+                                        : launch<double, TSB_LOG2N, PROG_GAIN, true>(tables, a, stream);
     }
     return program == PROG_PV_SHIFT ? launch<double, TSB_LOG2N, PROG_PV_SHIFT>(tables, a, stream)
                                     : launch<double, TSB_LOG2N, PROG_GAIN>(tables, a, stream);

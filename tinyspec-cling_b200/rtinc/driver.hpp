@@ -214,11 +214,16 @@ struct Renderer {
         return false;
     }
 
+    // fp64 arithmetic delivers the reference's float32 stream (float32 overlap tail and narrowing done on the
+    // device exactly as tinyspec.cpp:173-200) unless the unrounded float64 accumulation was asked for (--out-f64)
+    int chain_precision() const { return (opt.precision == TSB_F64 && !opt.out_f64) ? (int)TSB_F64_OUT32 : opt.precision; }
+    size_t out_elem_size() const { return chain_precision() == TSB_F64 ? 8 : 4; }
+
     void flush(Pending &p) {
         if (p.hops.empty()) return;
         Runtime &rt = Runtime::get();
         const SegmentKey &k = p.key;
-        const size_t lanes = lanes_in, n = k.n, esz = opt.precision == TSB_F32 ? 4 : 8;
+        const size_t lanes = lanes_in, n = k.n, esz = out_elem_size();
         // plan (cached per distinct chain)
         char buf[256];
         snprintf(buf, sizeof buf, "%d|%u|%.17g|%.17g|%d|%d|%zu|", k.program, k.n, k.hop_d, k.ratio, k.win_in, k.win_out, k.fn_bins.size());
@@ -229,7 +234,7 @@ struct Renderer {
             tsb_plan_desc d;
             memset(&d, 0, sizeof d);
             d.n = k.n;
-            d.precision = opt.precision;
+            d.precision = chain_precision();
             d.program = k.program;
             d.win_in = k.win_in;
             d.win_out = k.win_out;
@@ -284,7 +289,7 @@ struct Renderer {
     void render_fused() {
         Runtime &rt = Runtime::get();
         if (internals::new_nch_in == 0) fatal("fused mode needs an input (a hack without inputs fills its spectrum itself): use --mode immediate");
-        const size_t esz = opt.precision == TSB_F32 ? 4 : 8;
+        const size_t esz = out_elem_size();
         d_in.ensure(host_in.size() * 4);
         check(tsb_upload(rt.context(), d_in.d, host_in.data(), host_in.size() * 4), "tsb_upload");
         d_out.ensure(lanes_out * (size_t)out_cap * esz, true);
@@ -322,7 +327,7 @@ struct Renderer {
         flush(pend);
         rt.sync();
         size_t total = lanes_out * (size_t)out_cap;
-        if (opt.precision == TSB_F32) {
+        if (esz == 4) {
             host_out.resize(total);
             check(tsb_download(rt.context(), host_out.data(), d_out.d, total * 4), "tsb_download");
             rt.sync();
