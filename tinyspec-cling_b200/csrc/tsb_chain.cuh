@@ -33,6 +33,8 @@
 // C2R(Z)[n]/sqrt(N) with Z[k] = (conj(Y[k]) + Y[N-k])/2.  1/sqrt(N) (and the 1/2 of the PV case,
 // where Y[k>=N/2] = 0 after shift) are folded into the window tables.
 #pragma once
+#include <cmath>
+#include <cstring>
 #include <type_traits>
 
 #include "tsb_math.cuh"
@@ -172,6 +174,128 @@ TSB_HD float fast_atan2f(float y, float x) {
     return copysignf(r, y);
 }
 
+// ---- branch-free fp64 kernels for the PV analysis (results within ~1 ulp of libm's; no special-case paths, so the
+// compiler can interleave the two bins a thread analyses back to back) ----
+// hardware seed reciprocals (~20 significant bits, MUFU.RCP64H / RSQ64H)
+#if !defined(__CUDA_ARCH__)
+inline double chop_seed(double v) {  // host harness: keep 20 mantissa bits like the hardware seed
+    uint64_t u;
+    memcpy(&u, &v, 8);
+    u &= 0xFFFFFFFF00000000ull;
+    memcpy(&v, &u, 8);
+    return v;
+}
+#endif
+TSB_HD double rcp_seed(double x) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+#else
+    return chop_seed(1.0 / x);
+#endif
+}
+TSB_HD double rsqrt_seed(double x) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+#else
+    return chop_seed(1.0 / sqrt(x));
+#endif
+}
+// n/d for d > 0 (normal range): seed, two Newton steps on the reciprocal, one correction of the quotient
+TSB_HD double div_pos(double n, double d) {
+    double r = rcp_seed(d);
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    double q = n * r;
+    return fma(fma(-d, q, n), r, q);
+}
+// sqrt(x), x >= 0: coupled Newton (Goldschmidt) iteration from the seed, then one correction; exact 0 for x = 0
+TSB_HD double sqrt_pos(double x) {
+    double xs = fmax(x, 1e-290);
+    double y = rsqrt_seed(xs);
+    double g = xs * y, h = 0.5 * y;
+    double r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    g = fma(fma(-g, g, xs), h, g);
+    return x > 0.0 ? g : 0.0;
+}
+// atan(i/64), i = 0..65, correctly rounded
+#if defined(__CUDA_ARCH__)
+static __device__ const double k_atan_tab[66] = {
+#else
+static const double k_atan_tab[66] = {
+#endif
+    0.0, 0.015623728620476831, 0.031239833430268277,
+    0.046840712915969654, 0.06241880999595735, 0.0779666338315423,
+    0.09347678115858947, 0.10894195698986579, 0.12435499454676144,
+    0.13970887428916365, 0.15499674192394097, 0.1702119252854744,
+    0.18534794999569476, 0.2003985538258785, 0.21535769969773805,
+    0.23021958727684372, 0.24497866312686414, 0.2596296294082575,
+    0.2741674511196588, 0.2885873618940774, 0.3028848683749714,
+    0.31705575320914703, 0.3310960767041321, 0.34500217720710513,
+    0.35877067027057225, 0.3723984466767542, 0.38588266939807375,
+    0.39922076957525254, 0.4124104415973873, 0.42544963737004227,
+    0.43833655985795783, 0.4510696559885235, 0.4636476090008061,
+    0.4760693303227612, 0.48833395105640554, 0.5004408131472942,
+    0.5123894603107377, 0.5241796287829132, 0.5358112379604637,
+    0.5472843809874369, 0.5585993153435624, 0.5697564534829784,
+    0.5807563535676704, 0.5915997103351114, 0.6022873461349642,
+    0.6128202021652414, 0.6231993299340659, 0.6334258829691446,
+    0.6435011087932844, 0.6534263411807619, 0.6632029927060933,
+    0.6728325475937632, 0.6823165548747481, 0.6916566218531999,
+    0.7008544078844502, 0.7099116184635249, 0.7188299996216245,
+    0.7276113326265107, 0.7362574289814281, 0.7447701257160751,
+    0.7531512809621944, 0.7614027698055784, 0.7695264804056583,
+    0.7775243103733478, 0.7853981633974483, 0.7931499461096552};
+// atan2(y, x): octant reduction to a/b in [0,1]; a/b = c + (a - c*b)/(b + c*a) with c = i/64 the nearest table
+// point, so that atan(a/b) = atan(c) + atan(t), |t| <= 1/128 + 2^-20, where four terms of the series give
+// 2^-59 relative.  One full-precision division.  Sign conventions of libm (atan2(+-0, x<0) = +-pi).
+TSB_HD double fast_atan2(double y, double x) {
+    const double ax = fabs(x), ay = fabs(y);
+    const double b = fmax(ax, ay), a = fmin(ax, ay);
+    const double bs = fmax(b, 1e-290);
+    const double q0 = a * rcp_seed(bs);                       // ~20 bits of a/b
+    const double m = q0 * 64.0 + 6755399441055744.0;          // round to nearest integer in the low word
+#if defined(__CUDA_ARCH__)
+    const int i = __double2loint(m);
+#else
+    const int i = (int)(long long)(m - 6755399441055744.0);
+#endif
+    const double c = (m - 6755399441055744.0) * 0.015625;
+    const double t = div_pos(fma(-c, bs, a), fma(c, a, bs));
+    const double t2 = t * t;
+    double p = fma(t2, -1.0 / 7.0, 0.2);
+    p = fma(t2, p, -1.0 / 3.0);
+    double v = TSB_LDG(&k_atan_tab[i]) + fma(t * t2, p, t);
+    v = ay > ax ? (1.5707963267948966 - v) + 6.123233995736766e-17 : v;
+    v = x < 0.0 ? (3.141592653589793 - v) + 1.2246467991473532e-16 : v;
+#if defined(__CUDA_ARCH__)
+    v = (b == 0.0 && __double2hiint(x) < 0) ? 3.141592653589793 : v;  // atan2(+-0, -0) = +-pi
+#else
+    v = (b == 0.0 && std::signbit(x)) ? 3.141592653589793 : v;
+#endif
+    return copysign(v, y);
+}
+// trunc(fl(delta / M_PI)): the correctly rounded quotient from a reciprocal multiply and two exact-remainder
+// corrections (Markstein), then the reference's (int) truncation (rtlib/pv.hpp:41).  delta = -M_PI (a DC sign
+// change) gives exactly -1.
+TSB_HD int wrap_quotient(double delta) {
+    const double inv_pi = 0.3183098861837907;
+    double q = delta * inv_pi;
+    q = fma(fma(-q, TSB_PI, delta), inv_pi, q);
+    q = fma(fma(-q, TSB_PI, delta), inv_pi, q);
+    return d2i_rz(q);
+}
+
 // The DC bin of a real frame is real, so its phase sits exactly on the branch cut of arg() and on the
 // wrap boundary of phase_to_frequency whenever its sign changes.  In the reference the value fed to
 // arg() carries a ~1e-16 imaginary leak of the same sign as the bin (pow(i,2) is inexact in
@@ -191,21 +315,20 @@ struct PvMath<double> {
     static TSB_HD void analyze(int j, cpx<double> X, double &last_phase, const ChainTables<double> &tb, int n,
                                double &amp, double &inc, bool dc) {
         double re = X.x, im = -X.y;  // frft(.,+1) of real data = conj(R2C)/sqrt(N)
-        amp = sqrt(add_rn(mul_rn(re, re), mul_rn(im, im)));  // abs(), pv.hpp:20
-        double phase = dc ? dc_phase(re, tb) : atan2(im, re);  // arg(), pv.hpp:21 (dc: bin 0)
+        amp = sqrt_pos(add_rn(mul_rn(re, re), mul_rn(im, im)));  // abs(), pv.hpp:20
+        double phase = dc ? dc_phase(re, tb) : fast_atan2(im, re);  // arg(), pv.hpp:21 (dc: bin 0)
         double diff = sub_rn(phase, last_phase);
         last_phase = phase;                                  // pv.hpp:23
         // phase_to_frequency, pv.hpp:39-45
         double delta = sub_rn(diff, TSB_LDG(&tb.expect[j]));
-        int qpd = d2i_rz(delta / TSB_PI);
-        if (qpd >= 0) qpd += qpd & 1;
-        else qpd -= qpd & 1;
+        int qpd = wrap_quotient(delta);  // (int)(delta / M_PI)
+        qpd += qpd >= 0 ? (qpd & 1) : -(qpd & 1);
         double t = sub_rn(delta, mul_rn(TSB_PI, (double)qpd));
         t = mul_rn(tb.size_over_hop, t);
         t = mul_rn(t, 0.5);  // "/2.0" is exact either way
         // The truncation above needs the true quotient (a DC sign change puts delta exactly on -pi); the two
         // divisions below only scale, so a reciprocal multiply (<= 1 ulp apart, ~1e-16 relative on the
-        // increment) replaces them: fp64 division costs ~20 instructions on the fp64 pipe.
+        // increment) replaces them.
         t = mul_rn(t, 1.0 / TSB_PI);
         t = add_rn((double)j, t);
         t = mul_rn(t, tb.rate);
