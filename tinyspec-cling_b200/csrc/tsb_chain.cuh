@@ -296,6 +296,112 @@ TSB_HD int wrap_quotient(double delta) {
     return d2i_rz(q);
 }
 
+// sin and cos of an unreduced phase (|x| up to ~1e14), branch-free: x*(32/pi) = k + f with the product carried in
+// two doubles (exact head via fma, so the reduction is as good at 1e9 rad as at 1), sin/cos(k*pi/32) from a
+// 64-entry table (the index wraps around the circle: no quadrant logic), and short series in r = f*pi/32,
+// |r| <= pi/64.  Absolute error ~1e-16 (what polar() needs), independent of the argument's size.
+struct SinCosEntry {
+    double s, c;
+};
+#if defined(__CUDA_ARCH__)
+static __device__ const SinCosEntry k_sincos_tab[64] = {
+#else
+static const SinCosEntry k_sincos_tab[64] = {
+#endif
+    {0.0, 1.0},
+    {0.0980171403295606, 0.9951847266721969},
+    {0.19509032201612828, 0.9807852804032304},
+    {0.2902846772544624, 0.9569403357322088},
+    {0.3826834323650898, 0.9238795325112867},
+    {0.47139673682599764, 0.881921264348355},
+    {0.5555702330196022, 0.8314696123025452},
+    {0.6343932841636455, 0.773010453362737},
+    {0.7071067811865476, 0.7071067811865476},
+    {0.773010453362737, 0.6343932841636455},
+    {0.8314696123025452, 0.5555702330196022},
+    {0.881921264348355, 0.47139673682599764},
+    {0.9238795325112867, 0.3826834323650898},
+    {0.9569403357322088, 0.2902846772544624},
+    {0.9807852804032304, 0.19509032201612828},
+    {0.9951847266721969, 0.0980171403295606},
+    {1.0, 2.4662128696421e-91},
+    {0.9951847266721969, -0.0980171403295606},
+    {0.9807852804032304, -0.19509032201612828},
+    {0.9569403357322088, -0.2902846772544624},
+    {0.9238795325112867, -0.3826834323650898},
+    {0.881921264348355, -0.47139673682599764},
+    {0.8314696123025452, -0.5555702330196022},
+    {0.773010453362737, -0.6343932841636455},
+    {0.7071067811865476, -0.7071067811865476},
+    {0.6343932841636455, -0.773010453362737},
+    {0.5555702330196022, -0.8314696123025452},
+    {0.47139673682599764, -0.881921264348355},
+    {0.3826834323650898, -0.9238795325112867},
+    {0.2902846772544624, -0.9569403357322088},
+    {0.19509032201612828, -0.9807852804032304},
+    {0.0980171403295606, -0.9951847266721969},
+    {4.9324257392842e-91, -1.0},
+    {-0.0980171403295606, -0.9951847266721969},
+    {-0.19509032201612828, -0.9807852804032304},
+    {-0.2902846772544624, -0.9569403357322088},
+    {-0.3826834323650898, -0.9238795325112867},
+    {-0.47139673682599764, -0.881921264348355},
+    {-0.5555702330196022, -0.8314696123025452},
+    {-0.6343932841636455, -0.773010453362737},
+    {-0.7071067811865476, -0.7071067811865476},
+    {-0.773010453362737, -0.6343932841636455},
+    {-0.8314696123025452, -0.5555702330196022},
+    {-0.881921264348355, -0.47139673682599764},
+    {-0.9238795325112867, -0.3826834323650898},
+    {-0.9569403357322088, -0.2902846772544624},
+    {-0.9807852804032304, -0.19509032201612828},
+    {-0.9951847266721969, -0.0980171403295606},
+    {-1.0, -1.7216825539521752e-90},
+    {-0.9951847266721969, 0.0980171403295606},
+    {-0.9807852804032304, 0.19509032201612828},
+    {-0.9569403357322088, 0.2902846772544624},
+    {-0.9238795325112867, 0.3826834323650898},
+    {-0.881921264348355, 0.47139673682599764},
+    {-0.8314696123025452, 0.5555702330196022},
+    {-0.773010453362737, 0.6343932841636455},
+    {-0.7071067811865476, 0.7071067811865476},
+    {-0.6343932841636455, 0.773010453362737},
+    {-0.5555702330196022, 0.8314696123025452},
+    {-0.47139673682599764, 0.881921264348355},
+    {-0.3826834323650898, 0.9238795325112867},
+    {-0.2902846772544624, 0.9569403357322088},
+    {-0.19509032201612828, 0.9807852804032304},
+    {-0.0980171403295606, 0.9951847266721969}};
+TSB_HD void fast_sincos(double x, double &sn, double &cs) {
+    const double c1 = 10.185916357881302, c2 = -6.297176536058395e-16;  // 32/pi = c1 + c2
+    const double p = x * c1;
+    const double e = fma(x, c1, -p);                          // exact tail of the product
+    const double m = p + 6755399441055744.0;                  // k = rint(p) in the low word
+    const double kd = m - 6755399441055744.0;
+#if defined(__CUDA_ARCH__)
+    const int ki = __double2loint(m) & 63;
+    const double2 sc = __ldg(reinterpret_cast<const double2 *>(k_sincos_tab) + ki);
+    const double S = sc.x, C = sc.y;
+#else
+    uint64_t mb;
+    memcpy(&mb, &m, 8);
+    const int ki = (int)(mb & 63);
+    const double S = k_sincos_tab[ki].s, C = k_sincos_tab[ki].c;
+#endif
+    const double f = (p - kd) + fma(x, c2, e);               // |f| <= 1/2 (+ rounding)
+    const double r = f * 0.09817477042468103;                                 // pi/32
+    const double r2 = r * r;
+    double ps = fma(r2, -1.0 / 5040.0, 1.0 / 120.0);
+    ps = fma(r2, ps, -1.0 / 6.0);
+    const double sr = fma(r * r2, ps, r);                      // sin r
+    double pc = fma(r2, 1.0 / 40320.0, -1.0 / 720.0);
+    pc = fma(r2, pc, 1.0 / 24.0);
+    pc = fma(r2, pc, -0.5);
+    const double cm = r2 * pc;                                 // cos r - 1
+    sn = fma(C, sr, fma(S, cm, S));
+    cs = fma(-S, sr, fma(C, cm, C));
+}
+
 // The DC bin of a real frame is real, so its phase sits exactly on the branch cut of arg() and on the
 // wrap boundary of phase_to_frequency whenever its sign changes.  In the reference the value fed to
 // arg() carries a ~1e-16 imaginary leak of the same sign as the bin (pow(i,2) is inexact in
@@ -338,15 +444,20 @@ struct PvMath<double> {
         inc = mul_rn(mul_rn(mul_rn(2.0 * TSB_PI, freq), tb.inv_rate), tb.hop);
     }
     static TSB_HD double accumulate(double phase_sum, double inc) { return add_rn(phase_sum, inc); }
+    template <bool FAST = true>
     static TSB_HD cpx<double> synth(double amp, double inc, double &phase_sum) {
         phase_sum = add_rn(phase_sum, inc);  // pv.hpp:34 — never wrapped
         double s, c;
+        if (FAST) {
+            fast_sincos(phase_sum, s, c);
+        } else {
 #if defined(__CUDA_ARCH__)
-        sincos(phase_sum, &s, &c);
+            sincos(phase_sum, &s, &c);
 #else
-        s = sin(phase_sum);
-        c = cos(phase_sum);
+            s = sin(phase_sum);
+            c = cos(phase_sum);
 #endif
+        }
         return mk<double>(mul_rn(amp, c), mul_rn(amp, s));  // std::polar, pv.hpp:35
     }
 };
@@ -381,6 +492,7 @@ struct PvMath<float> {
         inc = tb.ratio * (expect + wrapped);
     }
     static TSB_HD double accumulate(double phase_sum, double inc) { return phase_sum + inc; }
+    template <bool FAST = true>
     static TSB_HD cpx<float> synth(float amp, double inc, double &phase_sum) {
         phase_sum += inc;
         // fp64 range reduction to [-pi/4, pi/4] + quadrant, then fp32 polynomials
@@ -409,6 +521,9 @@ struct PvMath<float> {
 
 // OUT32 (fp64 arithmetic only): the output row and the overlap tail are float32 and are combined exactly as the
 // reference's scheduler does (tinyspec.cpp:173-200): emitted sample = float(double(tail) + v), tail += float(v).
+#ifndef TSB_FAST_SYNTH_MAX_S
+#define TSB_FAST_SYNTH_MAX_S 2  // pair slots per thread up to which the fp64 synthesis uses fast_sincos (tuning)
+#endif
 template <typename real, int LOG2N, int PROG, bool OUT32 = false>
 struct Chain {
     static_assert(!OUT32 || sizeof(real) == 8, "OUT32 is the float32-output variant of the fp64 chain");
@@ -433,6 +548,10 @@ struct Chain {
     static constexpr int S = (HALF + T - 1) / T;             // pair slots per thread
     static constexpr int PASSES = RadixPlan<LOG2M>::passes;
     static constexpr bool IS_PV = PROG == PROG_PV_SHIFT;
+    // fp64 synthesis: the table-based branch-free sincos lets the compiler overlap the bins of a thread, which
+    // costs registers; with 8 or more bins of state per thread (N >= 4096) that tips the FFT passes into spilling
+    // (measured slower than CUDA's sincos there)
+    static constexpr bool FAST_SYNTH = S <= TSB_FAST_SYNTH_MAX_S;
     using C = cpx<real>;
     using Tables = ChainTables<real>;
     using SW = Swz<real>;
@@ -732,9 +851,9 @@ struct Chain {
             real amp;
             double inc;
             gather_bin<SIMPLE>(amp_x, inc_x, tb, k, amp, inc);
-            C Ya = PvMath<real>::synth(amp, inc, rg.phase_sum[2 * i]);
+            C Ya = PvMath<real>::template synth<FAST_SYNTH>(amp, inc, rg.phase_sum[2 * i]);
             gather_bin<SIMPLE>(amp_x, inc_x, tb, kb, amp, inc);
-            C Yb = PvMath<real>::synth(amp, inc, rg.phase_sum[2 * i + 1]);
+            C Yb = PvMath<real>::template synth<FAST_SYNTH>(amp, inc, rg.phase_sum[2 * i + 1]);
             if (!sp) {
                 merge_pair(H, tb, k, conj(Ya), conj(Yb));
             } else {
