@@ -200,18 +200,25 @@ TSB_HD void stockham_pass_io(int tid, const cpx<T> *twp, In in, Out out) {
         int j = tid + it * THREADS;
         if (NB % THREADS != 0 && j >= NB) break;
         cpx<T> v[R];
-#pragma unroll
-        for (int t = 0; t < R; t++) v[t] = in(j, t * NB);
         if (Ns > 1) {
+            // the twiddles come from global memory (L1): request them before the shared-memory inputs so that
+            // their longer latency runs behind those loads
             int jm = j & (Ns - 1);
             const cpx<T> *w = twp + TwLayout<LOG2M>::offset(P) + jm;
+            cpx<T> tw[R];
 #pragma unroll
-            for (int t = 1; t < R; t++) v[t] = cmul(v[t], TSB_LDG(&w[(t - 1) * Ns]));
+            for (int t = 1; t < R; t++) tw[t] = TSB_LDG(&w[(t - 1) * Ns]);
+#pragma unroll
+            for (int t = 0; t < R; t++) v[t] = in(j, t * NB);
+#pragma unroll
+            for (int t = 1; t < R; t++) v[t] = cmul(v[t], tw[t]);
             dftR<R>(v);
             int base = ((j - jm) * R) + jm;
 #pragma unroll
             for (int t = 0; t < R; t++) out(base, t * Ns, v[t]);
         } else {
+#pragma unroll
+            for (int t = 0; t < R; t++) v[t] = in(j, t * NB);
             dftR<R>(v);
 #pragma unroll
             for (int t = 0; t < R; t++) out(j * R, t, v[t]);
