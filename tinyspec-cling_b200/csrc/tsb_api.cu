@@ -126,6 +126,7 @@ TSB_API int tsb_ctx_trim(tsb_ctx *c) {
     if (c->scratch) cudaFree(c->scratch);
     c->scratch = nullptr;
     c->scratch_bytes = 0;
+    op_release_scratch(c->device);
     return TSB_OK;
 }
 TSB_API int tsb_ctx_sync(tsb_ctx *c) {

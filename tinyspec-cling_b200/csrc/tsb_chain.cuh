@@ -573,6 +573,10 @@ struct Chain {
     struct Regs {
         real last_phase[2 * S];
         double phase_sum[2 * S];
+        // simple shift maps (at most one source per destination): the sources of this thread's bins, two int16 per
+        // word, read once per launch — otherwise every synthesis phase starts by waiting for them (L1 latency
+        // in front of the dependent shared-memory reads)
+        uint32_t map_src[S];
     };
 
     // Forward pass p writes buf[p & 1] (pass 0 reads the ring), so the packed spectrum ends up in RB.
@@ -618,10 +622,19 @@ struct Chain {
             }
         }
     }
-    static TSB_HD void load_state(int tid, Smem &sm, Regs &rg, const ChainArgs &a, const SegInfo &sg) {
+    static TSB_HD void load_state(int tid, Smem &sm, Regs &rg, const Tables &tb, const ChainArgs &a, const SegInfo &sg) {
         for (int i = 0; i < 2 * S; i++) {
             rg.last_phase[i] = 0;
             rg.phase_sum[i] = 0;
+        }
+#pragma unroll
+        for (int i = 0; i < S; i++) {
+            int k = tid + T * i;
+            rg.map_src[i] = 0xffffffffu;
+            if (PROG == PROG_PV_SHIFT && tb.map1 && k < HALF) {
+                int kb = is_special(i, k) ? HALF : M - k;
+                rg.map_src[i] = ((uint32_t)TSB_LDG(&tb.map1[k]) & 0xffffu) | ((uint32_t)TSB_LDG(&tb.map1[kb]) << 16);
+            }
         }
         bool ld = a.load_state != 0;
         if (PROG == PROG_PV_SHIFT && ld) {
@@ -661,11 +674,11 @@ struct Chain {
             int kb = is_special(i, k) ? HALF : M - k;
             real amp;
             double inc;
-            if (tb.map1) gather_bin<true>(amp_x, inc_x, tb, k, amp, inc);
-            else gather_bin<false>(amp_x, inc_x, tb, k, amp, inc);
+            if (tb.map1) gather_bin<true>(amp_x, inc_x, tb, k, src_lo(rg.map_src[i]), amp, inc);
+            else gather_bin<false>(amp_x, inc_x, tb, k, 0, amp, inc);
             rg.phase_sum[2 * i] = PvMath<real>::accumulate(rg.phase_sum[2 * i], inc);
-            if (tb.map1) gather_bin<true>(amp_x, inc_x, tb, kb, amp, inc);
-            else gather_bin<false>(amp_x, inc_x, tb, kb, amp, inc);
+            if (tb.map1) gather_bin<true>(amp_x, inc_x, tb, kb, src_hi(rg.map_src[i]), amp, inc);
+            else gather_bin<false>(amp_x, inc_x, tb, kb, 0, amp, inc);
             rg.phase_sum[2 * i + 1] = PvMath<real>::accumulate(rg.phase_sum[2 * i + 1], inc);
         }
     }
@@ -809,10 +822,12 @@ struct Chain {
     // shift gather for destination bin k (rtlib/pv.hpp:70-78: amplitudes add in ascending source
     // order, the frequency of the last source wins; bins with no source are silent with freq 0).
     // SIMPLE: at most one source per destination (any upward shift) — a table lookup and two selects.
+    // `src1`: the bin's source from Regs::map_src (SIMPLE only).
     template <bool SIMPLE>
-    static TSB_HD void gather_bin(const real *amp_x, const double *inc_x, const Tables &tb, int k, real &amp, double &inc) {
+    static TSB_HD void gather_bin(const real *amp_x, const double *inc_x, const Tables &tb, int k, int src1, real &amp,
+                                  double &inc) {
         if (SIMPLE) {
-            int j = TSB_LDG(&tb.map1[k]);
+            int j = src1;
             int jj = j < 0 ? 0 : j;
             real a = amp_x[jj];
             double d = inc_x[jj];
@@ -831,6 +846,8 @@ struct Chain {
             inc = inc_x[j];
         }
     }
+    static TSB_HD int src_lo(uint32_t w) { return (int)(short)(w & 0xffffu); }
+    static TSB_HD int src_hi(uint32_t w) { return (int)w >> 16; }
     // ------------------------------------------------------------------ PV phase D: synthesis + C2R pre
     // (rtlib/pv.hpp:29-38 on the shifted bins, then Z = conj(Y) [1/2 folded into win_s])
     static TSB_HD void phase_pv_synth(int tid, Smem &sm, Regs &rg, const Tables &tb) {
@@ -850,9 +867,9 @@ struct Chain {
             int kb = sp ? HALF : M - k;
             real amp;
             double inc;
-            gather_bin<SIMPLE>(amp_x, inc_x, tb, k, amp, inc);
+            gather_bin<SIMPLE>(amp_x, inc_x, tb, k, src_lo(rg.map_src[i]), amp, inc);
             C Ya = PvMath<real>::template synth<FAST_SYNTH>(amp, inc, rg.phase_sum[2 * i]);
-            gather_bin<SIMPLE>(amp_x, inc_x, tb, kb, amp, inc);
+            gather_bin<SIMPLE>(amp_x, inc_x, tb, kb, src_hi(rg.map_src[i]), amp, inc);
             C Yb = PvMath<real>::template synth<FAST_SYNTH>(amp, inc, rg.phase_sum[2 * i + 1]);
             if (!sp) {
                 merge_pair(H, tb, k, conj(Ya), conj(Yb));
@@ -1082,7 +1099,7 @@ TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const t
         total = (int)sg.n_frames + (warm ? 1 : 0);
         hop_tab = a.hop_tab ? a.hop_tab + sg.first_frame - (warm ? 1 : 0) : nullptr;  // indexed by ff below
         ex.each([&](int tid, Regs &rg) {
-            CH::load_state(tid, sm, rg, a, sg);
+            CH::load_state(tid, sm, rg, tb, a, sg);
             CH::ring_fill(tid, lane, sm, a, in_off, N);
             CH::ring_wait();
         });

@@ -171,8 +171,10 @@ fft_tile_kernel(const cd *in, cd *out, RowAddr ia, RowAddr oa, long long rows, c
 struct FftPlanCache {
     std::map<int, cd *> pass_tw;                                 // log2 m -> device per-pass twiddles
     std::map<long long, std::pair<cd *, cd *>> bluestein;        // n -> (chirp c[n], FFT_L of the wrapped conj chirp)
-    cd *scratch = nullptr;
+    cd *scratch = nullptr;                                       // four-step intermediate
     size_t scratch_elems = 0;
+    cd *work = nullptr;                                          // Bluestein's padded rows
+    size_t work_elems = 0;
 };
 static std::map<int, FftPlanCache> g_cache;  // per device
 
@@ -188,6 +190,30 @@ static cudaError_t pass_twiddles(FftPlanCache &pc, int log2m, const cd **out) {
         it = pc.pass_tw.emplace(log2m, d).first;
     }
     *out = it->second;
+    return cudaSuccess;
+}
+// Both buffers grow on demand and stay (allocating gigabytes per call costs more than the transform); cudaFree
+// waits for the work that still uses the old block.  op_release_scratch gives them back.
+static cudaError_t ensure_work(FftPlanCache &pc, size_t elems, cd **out) {
+    if (pc.work_elems < elems) {
+        if (pc.work) cudaFree(pc.work);
+        pc.work = nullptr;
+        pc.work_elems = 0;
+        cudaError_t e = cudaMalloc(&pc.work, elems * sizeof(cd));
+        if (e != cudaSuccess) return e;
+        pc.work_elems = elems;
+    }
+    *out = pc.work;
+    return cudaSuccess;
+}
+cudaError_t op_release_scratch(int device) {
+    auto it = g_cache.find(device);
+    if (it == g_cache.end()) return cudaSuccess;
+    FftPlanCache &pc = it->second;
+    if (pc.scratch) cudaFree(pc.scratch);
+    if (pc.work) cudaFree(pc.work);
+    pc.scratch = pc.work = nullptr;
+    pc.scratch_elems = pc.work_elems = 0;
     return cudaSuccess;
 }
 static cudaError_t ensure_scratch(FftPlanCache &pc, size_t elems, cd **out) {
@@ -343,7 +369,7 @@ static cudaError_t fft_any(int device, const cd *in, cd *out, long long rows, lo
     }
     const cd *chirp = it->second.first, *bf = it->second.second;
     cd *a = nullptr;  // own work buffer (fft_pow2 may use the shared scratch for its four-step)
-    if ((e = cudaMallocAsync((void **)&a, (size_t)(rows * L) * sizeof(cd), st)) != cudaSuccess) return e;
+    if ((e = ensure_work(pc, (size_t)(rows * L), &a)) != cudaSuccess) return e;
     const int TB = 256;
     bluestein_pre<<<(unsigned)((rows * L + TB - 1) / TB), TB, 0, st>>>(in, a, chirp, rows, n, L);
     if ((e = fft_pow2(device, a, a, rows, L, false, 1.0, st, launches)) != cudaSuccess) return e;
@@ -351,8 +377,7 @@ static cudaError_t fft_any(int device, const cd *in, cd *out, long long rows, lo
     if ((e = fft_pow2(device, a, a, rows, L, true, 1.0 / (double)L, st, launches)) != cudaSuccess) return e;
     bluestein_post<<<(unsigned)((rows * n + TB - 1) / TB), TB, 0, st>>>(a, out, chirp, rows, n, L);
     if (launches) *launches += 3;
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    return cudaFreeAsync(a, st);
+    return cudaGetLastError();
 }
 
 cudaError_t op_fft_forward(int device, const double *in, double *out, long long rows, long long n, cudaStream_t st,

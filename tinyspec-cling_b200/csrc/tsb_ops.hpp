@@ -7,6 +7,8 @@
 namespace tsb {
 cudaError_t op_fft_forward(int device, const double *in, double *out, long long rows, long long n, cudaStream_t st,
                            long long *launches);
+// frees the per-device FFT work buffers (four-step intermediate, Bluestein rows)
+cudaError_t op_release_scratch(int device);
 cudaError_t op_frft(int device, const double *in, double *out, double *scratch_g, long long nch, long long n,
                     double exponent, cudaStream_t st, long long *launches);
 cudaError_t op_window(double *data, const double *wtab, long long nch, long long size, cudaStream_t st);
