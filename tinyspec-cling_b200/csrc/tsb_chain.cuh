@@ -30,8 +30,8 @@
 // Real-FFT mapping: the reference runs complex FFTs of real data.  Here the N
 // real samples are packed into M = N/2 complex points, transformed once, and split; with
 // X = R2C(x) (kernel e^-), frft(x,+1)[k] = conj(X[k])/sqrt(N), and Re(frft(Y,-1))[n] =
-// C2R(Z)[n]/sqrt(N) with Z[k] = (conj(Y[k]) + Y[N-k])/2.  1/sqrt(N) (and the 1/2 of the PV case,
-// where Y[k>=N/2] = 0 after shift) are folded into the window tables.
+// C2R(Z)[n]/sqrt(N) with Z[k] = (conj(Y[k]) + Y[N-k])/2.  1/sqrt(N) is folded into the window tables, the 1/2
+// of the PV case (Y[k>=N/2] = 0 after shift) into the amplitudes handed to the synthesis.
 #pragma once
 #include <cmath>
 #include <cstring>
@@ -79,7 +79,7 @@ struct ChainTables {
     const cpx<real> *tw;     // per-pass twiddle tables of the M-point FFT (TwLayout<LOG2M>)
     const cpx<real> *twn;    // [M/2+1]  exp(-2*pi*i*k/N)
     const real *win_a;       // [N]      analysis window / sqrt(N)
-    const real *win_s;       // [N]      synthesis window * c / sqrt(N), c = 1/2 (PV) or 1 (gain)
+    const real *win_s;       // [N]      synthesis window / sqrt(N) (the same table when the kinds are equal)
     // PROG_PV_SHIFT
     const double *expect;    // [M]      j*2.0*M_PI*hop/N, evaluated as rtlib/pv.hpp:40 does
     const uint32_t *map;     // [M]      (first << 16) | count into map_src: sources of destination bin k
@@ -811,10 +811,10 @@ struct Chain {
             real amp;
             double inc;
             PvMath<real>::analyze(k, Xa, rg.last_phase[2 * i], tb, N, amp, inc, sp);
-            amp_x[k] = amp;
+            amp_x[k] = (real)0.5 * amp;   // Y[k >= N/2] = 0 after shift, so Z = conj(Y)/2: exact scaling, done here
             inc_x[k] = inc;
             PvMath<real>::analyze(kb, Xb, rg.last_phase[2 * i + 1], tb, N, amp, inc, false);
-            amp_x[kb] = amp;
+            amp_x[kb] = (real)0.5 * amp;
             inc_x[kb] = inc;
             sched_fence();
         }
@@ -849,7 +849,7 @@ struct Chain {
     static TSB_HD int src_lo(uint32_t w) { return (int)(short)(w & 0xffffu); }
     static TSB_HD int src_hi(uint32_t w) { return (int)w >> 16; }
     // ------------------------------------------------------------------ PV phase D: synthesis + C2R pre
-    // (rtlib/pv.hpp:29-38 on the shifted bins, then Z = conj(Y) [1/2 folded into win_s])
+    // (rtlib/pv.hpp:29-38 on the shifted bins, then Z = conj(Y) [1/2 folded into the amplitudes])
     static TSB_HD void phase_pv_synth(int tid, Smem &sm, Regs &rg, const Tables &tb) {
         if (tb.map1) phase_pv_synth_t<true>(tid, sm, rg, tb);  // uniform: decided once per plan
         else phase_pv_synth_t<false>(tid, sm, rg, tb);

@@ -54,7 +54,7 @@ struct HostTables {
         t.tw = tw.data();
         t.twn = twn.data();
         t.win_a = win_a.data();
-        t.win_s = win_s.data();
+        t.win_s = win_s.empty() ? win_a.data() : win_s.data();
         t.expect = expect.data();
         t.map = map.data();
         t.map_src = map_src.data();
@@ -82,12 +82,13 @@ HostTables<real> build_tables(const PlanDesc &d) {
     for (int q = 0; q <= m / 2; q++) h.twn[q] = mk<real>((real)twn[2 * q], (real)twn[2 * q + 1]);
     std::vector<double> wa = window_table(d.win_in, n), ws = window_table(d.win_out, n);
     const double sqrtn = std::sqrt((double)n);
-    const double c = d.program == PROG_PV_SHIFT ? 0.5 : 1.0;
+    // Same window kind on both sides (always so for the PV): one table serves both passes (half the L1 footprint
+    // of the windows; the PV's 1/2 is applied to the amplitudes instead, an exact scaling).
     h.win_a.resize(n);
-    h.win_s.resize(n);
-    for (int i = 0; i < n; i++) {
-        h.win_a[i] = (real)(wa[i] / sqrtn);
-        h.win_s[i] = (real)(ws[i] * c / sqrtn);
+    for (int i = 0; i < n; i++) h.win_a[i] = (real)(wa[i] / sqrtn);
+    if (d.win_in != d.win_out) {
+        h.win_s.resize(n);
+        for (int i = 0; i < n; i++) h.win_s[i] = (real)(ws[i] / sqrtn);
     }
     h.hop = d.hop;
     h.rate = d.rate;
