@@ -73,6 +73,23 @@ TSB_HD void sched_fence() {
 #endif
 }
 
+// Pins a value's computation to this point of the instruction stream (keeps the optimiser from sinking it into a
+// conditional block).
+TSB_HD void keep_here(double &v) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("" : "+d"(v));
+#else
+    (void)v;
+#endif
+}
+TSB_HD void keep_here(float &v) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("" : "+f"(v));
+#else
+    (void)v;
+#endif
+}
+
 // Tables built once per plan on the host (tsb_host.cpp) and kept in device memory.
 template <typename real>
 struct ChainTables {
@@ -422,7 +439,9 @@ struct PvMath<double> {
                                double &amp, double &inc, bool dc) {
         double re = X.x, im = -X.y;  // frft(.,+1) of real data = conj(R2C)/sqrt(N)
         amp = sqrt_pos(add_rn(mul_rn(re, re), mul_rn(im, im)));  // abs(), pv.hpp:20
-        double phase = dc ? dc_phase(re, tb) : fast_atan2(im, re);  // arg(), pv.hpp:21 (dc: bin 0)
+        double pa = fast_atan2(im, re);
+        keep_here(pa);  // computed for every thread (no branch around it), bin 0 then takes its own value
+        double phase = dc ? dc_phase(re, tb) : pa;  // arg(), pv.hpp:21 (dc: bin 0)
         double diff = sub_rn(phase, last_phase);
         last_phase = phase;                                  // pv.hpp:23
         // phase_to_frequency, pv.hpp:39-45
@@ -475,12 +494,13 @@ struct PvMath<float> {
         float pw = fmaf(re, re, im * im);
         amp = pw * fast_rsqrtf(fmaxf(pw, 1e-37f));
         float phase = fast_atan2f(im, re);
+        keep_here(phase);
         double diff = (double)phase - (double)last_phase;
-        if (dc) {  // bin 0: keep the reference's (double) values, stored as a sign in the float state
+        {  // bin 0: keep the reference's (double) values, stored as a sign in the float state (selects, no branch)
             double lp = last_phase > 0.f ? tb.dc_pos : (last_phase < 0.f ? tb.dc_neg : 0.0);
             double ph = dc_phase((double)re, tb);
-            diff = ph - lp;
-            phase = (float)ph;
+            diff = dc ? ph - lp : diff;
+            phase = dc ? (float)ph : phase;
         }
         last_phase = phase;
         double expect = TSB_LDG(&tb.expect[j]);
@@ -768,7 +788,9 @@ struct Chain {
 
     // spectrum of the real frame at bins k and M-k (k != 0) from the packed transform Zc (see file header)
     static TSB_HD void split_pair(const C *Zc, const Tables &tb, int k, C &Xa, C &Xb) {
-        C a = Zc[SW::f(k)], b = conj(Zc[SW::f(M - k)]);
+        split_vals(Zc[SW::f(k)], conj(Zc[SW::f(M - k)]), tb, k, Xa, Xb);
+    }
+    static TSB_HD void split_vals(C a, C b, const Tables &tb, int k, C &Xa, C &Xb) {
         C e = mk<real>((real)0.5 * (a.x + b.x), (real)0.5 * (a.y + b.y));
         C d = a - b;
         C o = mk<real>((real)0.5 * d.y, (real)-0.5 * d.x);  // -i*d/2
@@ -778,14 +800,22 @@ struct Chain {
     }
     // C2R pre-processing for the pair (k, M-k), k != 0: Hermitian-half values Zk, Zp -> conj(G) entries
     static TSB_HD void merge_pair(C *H, const Tables &tb, int k, C Zk, C Zp) {
+        C hk, hp;
+        merge_vals(tb, k, Zk, Zp, hk, hp);
+        H[SW::f(k)] = hk;
+        H[SW::f(M - k)] = hp;
+    }
+    static TSB_HD void merge_vals(const Tables &tb, int k, C Zk, C Zp, C &hk, C &hp) {
         C ee = Zk + conj(Zp);
         C d = Zk - conj(Zp);
         C oo = cmul(d, conj(TSB_LDG(&tb.twn[k])));
-        H[SW::f(k)] = mk<real>(ee.x - oo.y, -ee.y - oo.x);
-        H[SW::f(M - k)] = mk<real>(ee.x + oo.y, ee.y - oo.x);
+        hk = mk<real>(ee.x - oo.y, -ee.y - oo.x);
+        hp = mk<real>(ee.x + oo.y, ee.y - oo.x);
     }
     // Only the first slot of thread 0 holds the irregular pair (bins 0 and M/2): the test is compile-time
-    // false for every other slot.
+    // false for every other slot.  In the PV phases slot 0 computes the regular pair for every thread and thread 0
+    // selects its values afterwards: a branch there would keep the compiler from overlapping the two bins of the
+    // slot (half of a thread's transcendental work when it owns two slots).
     static TSB_HD bool is_special(int i, int k) { return i == 0 && k == 0; }
 
     // ------------------------------------------------------------------ PV phase C: split + analysis
@@ -801,12 +831,13 @@ struct Chain {
             const bool sp = is_special(i, k);
             int kb = sp ? HALF : M - k;
             C Xa, Xb;
-            if (!sp) {
-                split_pair(Zc, tb, k, Xa, Xb);
+            if (i == 0) {
+                C za = Zc[SW::f(k)], zb = conj(Zc[SW::f(kb)]);  // thread 0: Z[0] and conj(Z[M/2]) = X[M/2]
+                split_vals(za, zb, tb, k, Xa, Xb);
+                Xa = sp ? mk<real>(za.x + za.y, 0) : Xa;         // X[0]
+                Xb = sp ? zb : Xb;
             } else {
-                C z0 = Zc[SW::f(0)], zh = Zc[SW::f(HALF)];
-                Xa = mk<real>(z0.x + z0.y, 0);  // X[0]
-                Xb = conj(zh);                  // X[M/2]
+                split_pair(Zc, tb, k, Xa, Xb);
             }
             real amp;
             double inc;
@@ -871,12 +902,14 @@ struct Chain {
             C Ya = PvMath<real>::template synth<FAST_SYNTH>(amp, inc, rg.phase_sum[2 * i]);
             gather_bin<SIMPLE>(amp_x, inc_x, tb, kb, src_hi(rg.map_src[i]), amp, inc);
             C Yb = PvMath<real>::template synth<FAST_SYNTH>(amp, inc, rg.phase_sum[2 * i + 1]);
-            if (!sp) {
-                merge_pair(H, tb, k, conj(Ya), conj(Yb));
+            if (i == 0) {
+                C hk, hp;
+                merge_vals(tb, k, conj(Ya), conj(Yb), hk, hp);
+                const real z0 = (real)2 * Ya.x;  // thread 0: Z[0] = Re Y[0] (not halved), Z[M] = 0
+                H[SW::f(k)] = sp ? mk<real>(z0, -z0) : hk;
+                H[SW::f(kb)] = sp ? mk<real>((real)2 * Yb.x, (real)-2 * Yb.y) : hp;  // 2*Z[M/2], Z = conj(Y)
             } else {
-                real z0 = (real)2 * Ya.x;  // Z[0] = Re Y[0] (not halved), Z[M] = 0
-                H[SW::f(0)] = mk<real>(z0, -z0);
-                H[SW::f(HALF)] = mk<real>((real)2 * Yb.x, (real)-2 * Yb.y);  // 2*Z[M/2], Z = conj(Y)
+                merge_pair(H, tb, k, conj(Ya), conj(Yb));
             }
             sched_fence();
         }
