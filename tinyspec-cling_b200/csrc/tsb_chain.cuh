@@ -102,6 +102,7 @@ struct ChainTables {
     const uint32_t *map;     // [M]      (first << 16) | count into map_src: sources of destination bin k
     const uint16_t *map_src; // source bins, ascending within each destination (rtlib/pv.hpp:70-78)
     const int16_t *map1;     // [M] or nullptr: when no destination has more than one source, that source (-1: none)
+    const uint8_t *src_used; // [M]      1 if some destination takes source bin j (the shift drops bins that land >= N/2)
     double hop;              // PhaseVocoder::hop() (rtinc/pv.hpp:50-53), may be fractional
     double rate;             // RATE
     double ratio;            // fn(x) = ratio*x applied to the frequencies (rtlib/pv.hpp:66)
@@ -597,6 +598,10 @@ struct Chain {
         // word, read once per launch — otherwise every synthesis phase starts by waiting for them (L1 latency
         // in front of the dependent shared-memory reads)
         uint32_t map_src[S];
+        // bit 2i / 2i+1: the shift uses source bin k / M-k of slot i; bit 16+2i / 16+2i+1: destination bin k / M-k
+        // of slot i has a source.  A source nobody takes only needs its phase on the last frame of a launch
+        // (last_phase is state), a destination without sources stays silent and keeps its phase_sum.
+        uint32_t used;
     };
 
     // Forward pass p writes buf[p & 1] (pass 0 reads the ring), so the packed spectrum ends up in RB.
@@ -654,6 +659,25 @@ struct Chain {
             if (PROG == PROG_PV_SHIFT && tb.map1 && k < HALF) {
                 int kb = is_special(i, k) ? HALF : M - k;
                 rg.map_src[i] = ((uint32_t)TSB_LDG(&tb.map1[k]) & 0xffffu) | ((uint32_t)TSB_LDG(&tb.map1[kb]) << 16);
+            }
+        }
+        rg.used = 0;
+        if (PROG == PROG_PV_SHIFT) {
+#pragma unroll
+            for (int i = 0; i < S; i++) {
+                int k = tid + T * i;
+                if (k >= HALF) continue;
+                int kb = is_special(i, k) ? HALF : M - k;
+                uint32_t f = (uint32_t)TSB_LDG(&tb.src_used[k]) | ((uint32_t)TSB_LDG(&tb.src_used[kb]) << 1);
+                uint32_t da, db;
+                if (tb.map1) {
+                    da = src_lo(rg.map_src[i]) >= 0;
+                    db = src_hi(rg.map_src[i]) >= 0;
+                } else {
+                    da = (TSB_LDG(&tb.map[k]) & 0xffffu) != 0;
+                    db = (TSB_LDG(&tb.map[kb]) & 0xffffu) != 0;
+                }
+                rg.used |= (f | (da << 16) | (db << 17)) << (2 * i);
             }
         }
         bool ld = a.load_state != 0;
@@ -820,34 +844,64 @@ struct Chain {
 
     // ------------------------------------------------------------------ PV phase C: split + analysis
     // (rtlib/pv.hpp:17-28 over the live bins 0..N/2-1; results go to the exchange arrays)
-    static TSB_HD void phase_pv_analyze(int tid, Smem &sm, Regs &rg, const Tables &tb) {
+    // `all`: analyse every bin (last frame of a launch, warm-up frame); otherwise only the sources the shift uses.
+    // Slots are taken two at a time and their k-side bins analysed together, then their (M-k)-side bins: an upward
+    // shift drops the upper sources, i.e. the (M-k) side of most pairs, and this grouping lets a thread skip them
+    // while the two bins it does analyse still overlap.
+    static TSB_HD void phase_pv_analyze(int tid, Smem &sm, Regs &rg, const Tables &tb, bool all) {
         const C *Zc = fwd_result(sm);
         double *inc_x = xch_inc(sm);
         real *amp_x = xch_amp(sm);
-#pragma unroll
-        for (int i = 0; i < S; i++) {
-            int k = tid + T * i;
-            if (HALF % T != 0 && k >= HALF) break;
-            const bool sp = is_special(i, k);
-            int kb = sp ? HALF : M - k;
-            C Xa, Xb;
+        auto split_slot = [&](int i, int k, C &Xa, C &Xb) {
             if (i == 0) {
-                C za = Zc[SW::f(k)], zb = conj(Zc[SW::f(kb)]);  // thread 0: Z[0] and conj(Z[M/2]) = X[M/2]
+                const bool sp = is_special(i, k);
+                C za = Zc[SW::f(k)], zb = conj(Zc[SW::f(sp ? HALF : M - k)]);  // thread 0: Z[0], conj(Z[M/2]) = X[M/2]
                 split_vals(za, zb, tb, k, Xa, Xb);
-                Xa = sp ? mk<real>(za.x + za.y, 0) : Xa;         // X[0]
+                Xa = sp ? mk<real>(za.x + za.y, 0) : Xa;  // X[0]
                 Xb = sp ? zb : Xb;
             } else {
                 split_pair(Zc, tb, k, Xa, Xb);
             }
+        };
+        auto analyze_bin = [&](int j, C X, real &last_phase, bool dc) {
             real amp;
             double inc;
-            PvMath<real>::analyze(k, Xa, rg.last_phase[2 * i], tb, N, amp, inc, sp);
-            amp_x[k] = (real)0.5 * amp;   // Y[k >= N/2] = 0 after shift, so Z = conj(Y)/2: exact scaling, done here
-            inc_x[k] = inc;
-            PvMath<real>::analyze(kb, Xb, rg.last_phase[2 * i + 1], tb, N, amp, inc, false);
-            amp_x[kb] = (real)0.5 * amp;
-            inc_x[kb] = inc;
+            PvMath<real>::analyze(j, X, last_phase, tb, N, amp, inc, dc);
+            amp_x[j] = (real)0.5 * amp;  // Y[k >= N/2] = 0 after shift, so Z = conj(Y)/2: exact scaling, done here
+            inc_x[j] = inc;
+        };
+        if constexpr (S == 1) {
+            int k = tid;
+            if (HALF % T != 0 && k >= HALF) return;
+            const bool sp = is_special(0, k);
+            if (!all && !(rg.used & 3u)) return;
+            C Xa, Xb;
+            split_slot(0, k, Xa, Xb);
+            analyze_bin(k, Xa, rg.last_phase[0], sp);
+            analyze_bin(sp ? HALF : M - k, Xb, rg.last_phase[1], false);
+        } else {
+#pragma unroll
+        for (int i = 0; i < S; i += 2) {
+            const int k0 = tid + T * i, k1 = tid + T * (i + 1);
+            const bool two = i + 1 < S;
+            const bool sp = is_special(i, k0);
+            const uint32_t u = rg.used >> (2 * i);
+            const bool need_a = all || (u & (two ? 5u : 1u)), need_b = all || (u & (two ? 10u : 2u));
+            if (need_a || need_b) {
+                C Xa0, Xb0, Xa1, Xb1;
+                split_slot(i, k0, Xa0, Xb0);
+                if (two) split_slot(i + 1, k1, Xa1, Xb1);
+                if (need_a) {
+                    analyze_bin(k0, Xa0, rg.last_phase[2 * i], sp);
+                    if (two) analyze_bin(k1, Xa1, rg.last_phase[2 * i + 2], false);
+                }
+                if (need_b) {
+                    analyze_bin(sp ? HALF : M - k0, Xb0, rg.last_phase[2 * i + 1], false);
+                    if (two) analyze_bin(M - k1, Xb1, rg.last_phase[2 * i + 3], false);
+                }
+            }
             sched_fence();
+        }
         }
     }
     // shift gather for destination bin k (rtlib/pv.hpp:70-78: amplitudes add in ascending source
@@ -1149,7 +1203,8 @@ TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const t
         for (int ff = 0; ff < total; ff++) {
             const int hop = hop_of(ff);
             if (CH::IS_PV) {
-                ex.each([&](int tid, Regs &rg) { CH::phase_pv_analyze(tid, sm, rg, tb); });
+                const bool all = ff + 1 == total;  // last_phase is state: the last frame of a launch analyses every bin
+                ex.each([&](int tid, Regs &rg) { CH::phase_pv_analyze(tid, sm, rg, tb, all); });
                 ex.each([&](int tid, Regs &rg) {
                     CH::phase_pv_synth(tid, sm, rg, tb);
                     CH::ring_wait();  // next frame's samples (requested a frame ago) are in the ring after this barrier
@@ -1182,7 +1237,8 @@ TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const t
         long long first = in_off + hop + N - cnt;
         FwdPasses<CH, 0, CH::PASSES>::run(ex, lane, sm, tb, a, in_off, first, cnt);
         if (CH::IS_PV) {
-            ex.each([&](int tid, Regs &rg) { CH::phase_pv_analyze(tid, sm, rg, tb); });
+            const bool all = is_warm || ff + 1 == total;
+            ex.each([&](int tid, Regs &rg) { CH::phase_pv_analyze(tid, sm, rg, tb, all); });
             if (prepass) {
                 if (is_warm) {
                     if (a.st_warm_phase) {

@@ -67,6 +67,11 @@ TSB_D int ldg(const uint16_t *p) {
     asm volatile("ld.global.nc.u16 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
+TSB_D int ldg(const uint8_t *p) {
+    int v;
+    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
 TSB_D long long ldg(const long long *p) {
     long long v;
     asm volatile("ld.global.nc.s64 %0, [%1];" : "=l"(v) : "l"(p));
@@ -77,6 +82,7 @@ template <typename T>
 inline T ldg(const T *p) { return *p; }
 inline int ldg(const int16_t *p) { return *p; }
 inline int ldg(const uint16_t *p) { return *p; }
+inline int ldg(const uint8_t *p) { return *p; }
 #endif
 template <typename T>
 TSB_HD cpx<T> mk(T x, T y) {

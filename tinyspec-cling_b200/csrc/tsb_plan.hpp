@@ -48,6 +48,7 @@ struct HostTables {
     std::vector<uint32_t> map;
     std::vector<uint16_t> map_src;
     std::vector<int16_t> map1;  // empty unless every destination has at most one source
+    std::vector<uint8_t> src_used;  // [M] 1 if some destination takes source bin j
     double hop, rate, ratio, size_over_hop, dc_pos, dc_neg;
     ChainTables<real> view() const {
         ChainTables<real> t;
@@ -59,6 +60,7 @@ struct HostTables {
         t.map = map.data();
         t.map_src = map_src.data();
         t.map1 = map1.empty() ? nullptr : map1.data();
+        t.src_used = src_used.data();
         t.hop = hop;
         t.rate = rate;
         t.ratio = ratio;
@@ -103,6 +105,9 @@ HostTables<real> build_tables(const PlanDesc &d) {
         fb[j] = d.fn_bins ? d.fn_bins[j] : centre * d.ratio;
     }
     build_shift_map(n, d.rate, fb.data(), h.map, h.map_src);
+    h.src_used.assign(m, 0);
+    for (uint32_t e : h.map)
+        for (uint32_t q = 0; q < (e & 0xffff); q++) h.src_used[h.map_src[(e >> 16) + q]] = 1;
     bool simple = true;
     for (uint32_t e : h.map) simple = simple && (e & 0xffff) <= 1;
     if (simple) {
