@@ -230,6 +230,7 @@ static int upload_tables(tsb_plan *p, const PlanDesc &d, ChainTables<real> &t) {
     if ((r = upload_vec(p, h.map_src, &t.map_src))) return r;
     if (!h.map1.empty() && (r = upload_vec(p, h.map1, &t.map1))) return r;
     if ((r = upload_vec(p, h.src_used, &t.src_used))) return r;
+    if (!h.dst_order.empty() && (r = upload_vec(p, h.dst_order, &t.dst_order))) return r;
     if ((r = upload_vec(p, h.gain, &t.gain))) return r;
     return TSB_OK;
 }

@@ -103,6 +103,8 @@ struct ChainTables {
     const uint16_t *map_src; // source bins, ascending within each destination (rtlib/pv.hpp:70-78)
     const int16_t *map1;     // [M] or nullptr: when no destination has more than one source, that source (-1: none)
     const uint8_t *src_used; // [M]      1 if some destination takes source bin j (the shift drops bins that land >= N/2)
+    const uint16_t *dst_order; // [M/2] or nullptr: destination pairs (k, M-k) in the order the threads take them —
+                             // pairs with a source first, so that whole slots of silent pairs are skipped
     double hop;              // PhaseVocoder::hop() (rtinc/pv.hpp:50-53), may be fractional
     double rate;             // RATE
     double ratio;            // fn(x) = ratio*x applied to the frequencies (rtlib/pv.hpp:66)
@@ -602,6 +604,7 @@ struct Chain {
         // of slot i has a source.  A source nobody takes only needs its phase on the last frame of a launch
         // (last_phase is state), a destination without sources stays silent and keeps its phase_sum.
         uint32_t used;
+        uint32_t dpair[(S + 1) / 2];  // destination pair of slot i (16 bits each): k of the synthesis side
     };
 
     // Forward pass p writes buf[p & 1] (pass 0 reads the ring), so the packed spectrum ends up in RB.
@@ -623,62 +626,78 @@ struct Chain {
     // ------------------------------------------------------------------ state in / out
     // state rows: registers <-> [row][M] arrays, thread `tid` owning bins (k, M-k) of its slots.  The register
     // arrays are passed by reference and indexed with unrolled constants so that they stay in registers.
-    template <typename V>
-    static TSB_HD void regs_from(int tid, const double *arr, long long row, V (&dst)[2 * S]) {
+    // kof(i): first bin of the pair held in slot i, or -1
+    template <typename V, class KOf>
+    static TSB_HD void regs_from(const double *arr, long long row, V (&dst)[2 * S], KOf kof) {
 #pragma unroll
         for (int i = 0; i < S; i++) {
-            int k = tid + T * i;
-            if (k < HALF) {
+            int k = kof(i);
+            if (k >= 0) {
                 int kb = k == 0 ? HALF : M - k;
                 dst[2 * i] = (V)arr[row * M + k];
                 dst[2 * i + 1] = (V)arr[row * M + kb];
             }
         }
     }
-    template <typename V>
-    static TSB_HD void regs_to(int tid, double *arr, long long row, const V (&src)[2 * S]) {
+    template <typename V, class KOf>
+    static TSB_HD void regs_to(double *arr, long long row, const V (&src)[2 * S], KOf kof) {
 #pragma unroll
         for (int i = 0; i < S; i++) {
-            int k = tid + T * i;
-            if (k < HALF) {
+            int k = kof(i);
+            if (k >= 0) {
                 int kb = k == 0 ? HALF : M - k;
                 arr[row * M + k] = (double)src[2 * i];
                 arr[row * M + kb] = (double)src[2 * i + 1];
             }
         }
     }
+    // source side (analysis, last_phase): thread tid, slot i holds the pair (k, M-k), k = tid + T*i
+    static TSB_HD int src_k(int tid, int i) {
+        int k = tid + T * i;
+        return k < HALF ? k : -1;
+    }
+    // destination side (synthesis, phase_sum): the plan may reorder the pairs (ChainTables::dst_order)
+    static TSB_HD int dst_k(const Regs &rg, int i) {
+        int k = (int)((rg.dpair[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+        return k < HALF ? k : -1;
+    }
+    template <typename V>
+    static TSB_HD void regs_from(int tid, const double *arr, long long row, V (&dst)[2 * S]) {
+        regs_from(arr, row, dst, [&](int i) { return src_k(tid, i); });
+    }
+    template <typename V>
+    static TSB_HD void regs_to(int tid, double *arr, long long row, const V (&src)[2 * S]) {
+        regs_to(arr, row, src, [&](int i) { return src_k(tid, i); });
+    }
     static TSB_HD void load_state(int tid, Smem &sm, Regs &rg, const Tables &tb, const ChainArgs &a, const SegInfo &sg) {
         for (int i = 0; i < 2 * S; i++) {
             rg.last_phase[i] = 0;
             rg.phase_sum[i] = 0;
         }
+        for (int i = 0; i < (S + 1) / 2; i++) rg.dpair[i] = 0xffffffffu;
+        rg.used = 0;
 #pragma unroll
         for (int i = 0; i < S; i++) {
-            int k = tid + T * i;
             rg.map_src[i] = 0xffffffffu;
-            if (PROG == PROG_PV_SHIFT && tb.map1 && k < HALF) {
-                int kb = is_special(i, k) ? HALF : M - k;
+            const int q = tid + T * i;
+            if (PROG != PROG_PV_SHIFT || q >= HALF) continue;
+            // destination pair of this slot
+            const int k = (HALF % T == 0 && tb.dst_order) ? (int)TSB_LDG(&tb.dst_order[q]) : q;
+            rg.dpair[i >> 1] = (rg.dpair[i >> 1] & ~(0xffffu << (16 * (i & 1)))) | ((uint32_t)k << (16 * (i & 1)));
+            const int kb = k == 0 ? HALF : M - k;
+            uint32_t da, db;
+            if (tb.map1) {
                 rg.map_src[i] = ((uint32_t)TSB_LDG(&tb.map1[k]) & 0xffffu) | ((uint32_t)TSB_LDG(&tb.map1[kb]) << 16);
+                da = src_lo(rg.map_src[i]) >= 0;
+                db = src_hi(rg.map_src[i]) >= 0;
+            } else {
+                da = (TSB_LDG(&tb.map[k]) & 0xffffu) != 0;
+                db = (TSB_LDG(&tb.map[kb]) & 0xffffu) != 0;
             }
-        }
-        rg.used = 0;
-        if (PROG == PROG_PV_SHIFT) {
-#pragma unroll
-            for (int i = 0; i < S; i++) {
-                int k = tid + T * i;
-                if (k >= HALF) continue;
-                int kb = is_special(i, k) ? HALF : M - k;
-                uint32_t f = (uint32_t)TSB_LDG(&tb.src_used[k]) | ((uint32_t)TSB_LDG(&tb.src_used[kb]) << 1);
-                uint32_t da, db;
-                if (tb.map1) {
-                    da = src_lo(rg.map_src[i]) >= 0;
-                    db = src_hi(rg.map_src[i]) >= 0;
-                } else {
-                    da = (TSB_LDG(&tb.map[k]) & 0xffffu) != 0;
-                    db = (TSB_LDG(&tb.map[kb]) & 0xffffu) != 0;
-                }
-                rg.used |= (f | (da << 16) | (db << 17)) << (2 * i);
-            }
+            // source pair of this slot
+            const int qb = is_special(i, q) ? HALF : M - q;
+            uint32_t f = (uint32_t)TSB_LDG(&tb.src_used[q]) | ((uint32_t)TSB_LDG(&tb.src_used[qb]) << 1);
+            rg.used |= (f | (da << 16) | (db << 17)) << (2 * i);
         }
         bool ld = a.load_state != 0;
         if (PROG == PROG_PV_SHIFT && ld) {
@@ -689,7 +708,7 @@ struct Chain {
             } else {
                 if (sg.warm && a.st_warm_phase) regs_from(tid, a.st_warm_phase, sg.row, rg.last_phase);
                 else if (a.st_last_phase) regs_from(tid, a.st_last_phase, sg.row, rg.last_phase);
-                if (a.st_phase_sum) regs_from(tid, a.st_phase_sum, sg.row, rg.phase_sum);
+                if (a.st_phase_sum) regs_from(a.st_phase_sum, sg.row, rg.phase_sum, [&](int i) { return dst_k(rg, i); });
             }
         }
         for (int i = tid; i < N; i += T) {
@@ -701,7 +720,7 @@ struct Chain {
     static TSB_HD void store_state(int tid, Smem &sm, Regs &rg, const ChainArgs &a, const SegInfo &sg, long long out_pos) {
         if (PROG == PROG_PV_SHIFT && a.st_last_phase && a.st_phase_sum) {
             regs_to(tid, a.st_last_phase, sg.row, rg.last_phase);
-            regs_to(tid, a.st_phase_sum, sg.row, rg.phase_sum);
+            regs_to(a.st_phase_sum, sg.row, rg.phase_sum, [&](int i) { return dst_k(rg, i); });
         }
         if (a.st_ola && a.mode == 0)
             for (int i = tid; i < N; i += T) a.st_ola[sg.row * N + i] = (double)sm.ola[(int)((out_pos + i) & (N - 1))];
@@ -713,8 +732,8 @@ struct Chain {
         const real *amp_x = xch_amp(sm);
 #pragma unroll
         for (int i = 0; i < S; i++) {
-            int k = tid + T * i;
-            if (HALF % T != 0 && k >= HALF) break;
+            int k = dst_k(rg, i);
+            if (HALF % T != 0 && k < 0) break;
             int kb = is_special(i, k) ? HALF : M - k;
             real amp;
             double inc;
@@ -946,10 +965,16 @@ struct Chain {
         const real *amp_x = xch_amp(sm);
 #pragma unroll
         for (int i = 0; i < S; i++) {
-            int k = tid + T * i;
-            if (HALF % T != 0 && k >= HALF) break;
+            int k = dst_k(rg, i);
+            if (HALF % T != 0 && k < 0) break;
             const bool sp = is_special(i, k);
             int kb = sp ? HALF : M - k;
+            if (!((rg.used >> (16 + 2 * i)) & 3u)) {
+                // neither bin has a source: silent, phase_sum unchanged (rtlib/pv.hpp:34 adds 0)
+                H[SW::f(k)] = mk<real>(0, 0);
+                H[SW::f(kb)] = mk<real>(0, 0);
+                continue;
+            }
             real amp;
             double inc;
             gather_bin<SIMPLE>(amp_x, inc_x, tb, k, src_lo(rg.map_src[i]), amp, inc);

@@ -49,6 +49,7 @@ struct HostTables {
     std::vector<uint16_t> map_src;
     std::vector<int16_t> map1;  // empty unless every destination has at most one source
     std::vector<uint8_t> src_used;  // [M] 1 if some destination takes source bin j
+    std::vector<uint16_t> dst_order;  // [M/2] destination pairs, those with a source first; empty = natural order
     double hop, rate, ratio, size_over_hop, dc_pos, dc_neg;
     ChainTables<real> view() const {
         ChainTables<real> t;
@@ -61,6 +62,7 @@ struct HostTables {
         t.map_src = map_src.data();
         t.map1 = map1.empty() ? nullptr : map1.data();
         t.src_used = src_used.data();
+        t.dst_order = dst_order.empty() ? nullptr : dst_order.data();
         t.hop = hop;
         t.rate = rate;
         t.ratio = ratio;
@@ -108,6 +110,20 @@ HostTables<real> build_tables(const PlanDesc &d) {
     h.src_used.assign(m, 0);
     for (uint32_t e : h.map)
         for (uint32_t q = 0; q < (e & 0xffff); q++) h.src_used[h.map_src[(e >> 16) + q]] = 1;
+    // Destination pairs (k, M-k) without any source are silent: when there are many (x2 leaves every odd bin
+    // empty), hand the pairs out with the sourced ones first — thread t takes entries t, t+T, ... — so that
+    // whole slots are silent for every thread and the synthesis skips them.  Pair 0 (bins 0 and M/2) stays first.
+    {
+        const int half = m / 2;
+        auto sourced = [&](int k) { return (h.map[k] & 0xffff) != 0; };
+        std::vector<uint16_t> with, without;
+        for (int k = 1; k < half; k++) (sourced(k) || sourced(m - k) ? with : without).push_back((uint16_t)k);
+        if ((int)without.size() >= half / 4) {
+            h.dst_order.push_back(0);
+            h.dst_order.insert(h.dst_order.end(), with.begin(), with.end());
+            h.dst_order.insert(h.dst_order.end(), without.begin(), without.end());
+        }
+    }
     bool simple = true;
     for (uint32_t e : h.map) simple = simple && (e & 0xffff) <= 1;
     if (simple) {
