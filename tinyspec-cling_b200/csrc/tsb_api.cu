@@ -225,7 +225,6 @@ static int upload_tables(tsb_plan *p, const PlanDesc &d, ChainTables<real> &t) {
     if ((r = upload_vec(p, h.win_a, &t.win_a))) return r;
     if (h.win_s.empty()) t.win_s = t.win_a;  // same window on both sides: one table
     else if ((r = upload_vec(p, h.win_s, &t.win_s))) return r;
-    if ((r = upload_vec(p, h.expect, &t.expect))) return r;
     if ((r = upload_vec(p, h.map, &t.map))) return r;
     if ((r = upload_vec(p, h.map_src, &t.map_src))) return r;
     if (!h.map1.empty() && (r = upload_vec(p, h.map1, &t.map1))) return r;

@@ -98,7 +98,7 @@ struct ChainTables {
     const real *win_a;       // [N]      analysis window / sqrt(N)
     const real *win_s;       // [N]      synthesis window / sqrt(N) (the same table when the kinds are equal)
     // PROG_PV_SHIFT
-    const double *expect;    // [M]      j*2.0*M_PI*hop/N, evaluated as rtlib/pv.hpp:40 does
+    double inv_n;            // 1/N (exact)
     const uint32_t *map;     // [M]      (first << 16) | count into map_src: sources of destination bin k
     const uint16_t *map_src; // source bins, ascending within each destination (rtlib/pv.hpp:70-78)
     const int16_t *map1;     // [M] or nullptr: when no destination has more than one source, that source (-1: none)
@@ -422,6 +422,14 @@ TSB_HD void fast_sincos(double x, double &sn, double &cs) {
     cs = fma(-S, sr, fma(C, cm, C));
 }
 
+// Expected phase advance of bin j, `bin * 2.0 * M_PI * hop / size` evaluated left to right as rtlib/pv.hpp:40 does
+// (size is a power of two: the division is an exact scaling).  Computed, not tabulated: a table of N/2 doubles
+// per plan is what pushed the kernel's constant data past the L1 that is left beside the shared memory.
+template <typename real>
+TSB_HD double expected_advance(int j, const ChainTables<real> &tb) {
+    return mul_rn(mul_rn((double)(2 * j), TSB_PI), tb.hop) * tb.inv_n;
+}
+
 // The DC bin of a real frame is real, so its phase sits exactly on the branch cut of arg() and on the
 // wrap boundary of phase_to_frequency whenever its sign changes.  In the reference the value fed to
 // arg() carries a ~1e-16 imaginary leak of the same sign as the bin (pow(i,2) is inexact in
@@ -448,7 +456,7 @@ struct PvMath<double> {
         double diff = sub_rn(phase, last_phase);
         last_phase = phase;                                  // pv.hpp:23
         // phase_to_frequency, pv.hpp:39-45
-        double delta = sub_rn(diff, TSB_LDG(&tb.expect[j]));
+        double delta = sub_rn(diff, expected_advance(j, tb));
         int qpd = wrap_quotient(delta);  // (int)(delta / M_PI)
         qpd += qpd >= 0 ? (qpd & 1) : -(qpd & 1);
         double t = sub_rn(delta, mul_rn(TSB_PI, (double)qpd));
@@ -506,7 +514,7 @@ struct PvMath<float> {
             phase = dc ? (float)ph : phase;
         }
         last_phase = phase;
-        double expect = TSB_LDG(&tb.expect[j]);
+        double expect = expected_advance(j, tb);
         double delta = diff - expect;
         int qpd = d2i_rz(delta * (1.0 / TSB_PI));
         if (qpd >= 0) qpd += qpd & 1;

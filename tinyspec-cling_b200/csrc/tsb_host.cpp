@@ -119,13 +119,4 @@ std::vector<double> pass_twiddle_table(int m) {
     return t;
 }
 
-std::vector<double> expect_table(int n, double hop, int count) {
-    std::vector<double> e(count);
-    for (int j = 0; j < count; j++) {
-        size_t bin = (size_t)j, size = (size_t)n;
-        e[j] = bin * 2.0 * M_PI * hop / size;
-    }
-    return e;
-}
-
 }  // namespace tsb

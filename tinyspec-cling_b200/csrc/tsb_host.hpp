@@ -60,7 +60,5 @@ std::vector<double> twiddle_table(int m, int count);
 // concatenated (re,im interleaved).  Matches TwLayout<log2 m>.
 std::vector<double> pass_twiddle_table(int m);
 
-// j*2.0*M_PI*hop/size as rtlib/pv.hpp:40 evaluates it, j < count
-std::vector<double> expect_table(int n, double hop, int count);
 
 }  // namespace tsb

@@ -44,7 +44,6 @@ template <typename real>
 struct HostTables {
     std::vector<cpx<real>> tw, twn;
     std::vector<real> win_a, win_s, gain;
-    std::vector<double> expect;
     std::vector<uint32_t> map;
     std::vector<uint16_t> map_src;
     std::vector<int16_t> map1;  // empty unless every destination has at most one source
@@ -57,7 +56,7 @@ struct HostTables {
         t.twn = twn.data();
         t.win_a = win_a.data();
         t.win_s = win_s.empty() ? win_a.data() : win_s.data();
-        t.expect = expect.data();
+        t.inv_n = 1.0 / (double)win_a.size();
         t.map = map.data();
         t.map_src = map_src.data();
         t.map1 = map1.empty() ? nullptr : map1.data();
@@ -100,7 +99,6 @@ HostTables<real> build_tables(const PlanDesc &d) {
     h.size_over_hop = (size_t)n / d.hop;  // size/hop(), rtlib/pv.hpp:44
     h.dc_pos = dc_phase_const(n, 1.0);
     h.dc_neg = dc_phase_const(n, -1.0);
-    h.expect = expect_table(n, d.hop, m);
     std::vector<double> fb(m);
     for (int j = 0; j < m; j++) {
         double centre = j / (double)(size_t)n * d.rate;  // rtlib/pv.hpp:61
