@@ -583,6 +583,15 @@ struct Chain {
     // costs registers; with 8 or more bins of state per thread (N >= 4096) that tips the FFT passes into spilling
     // (measured slower than CUDA's sincos there)
     static constexpr bool FAST_SYNTH = S <= TSB_FAST_SYNTH_MAX_S;
+    // radix-8 twiddles: 0 = all seven from the table, 1 = w, w^2, w^4 from the table and the rest by products,
+    // 2 = only w from the table
+#ifndef TSB_TW_DERIVE64
+#define TSB_TW_DERIVE64 2
+#endif
+#ifndef TSB_TW_DERIVE32
+#define TSB_TW_DERIVE32 0
+#endif
+    static constexpr int TW_DERIVE = sizeof(real) == 8 ? TSB_TW_DERIVE64 : TSB_TW_DERIVE32;
     using C = cpx<real>;
     using Tables = ChainTables<real>;
     using SW = Swz<real>;
@@ -819,7 +828,7 @@ struct Chain {
                     C w = TSB_LDG(wa + a + c);
                     return mk<real>((real)q.x * w.x, (real)q.y * w.y);
                 };
-                stockham_pass_io<real, LOG2M, NT, P>(tid, tb.tw, in, out);
+                stockham_pass_io<real, LOG2M, NT, P, decltype(in), decltype(out), TW_DERIVE>(tid, tb.tw, in, out);
             } else {
                 auto in = [&](int a, int c) {
                     int m = a + c;
@@ -828,12 +837,12 @@ struct Chain {
                     C w = TSB_LDG(wa + m);
                     return mk<real>((real)x0 * w.x, (real)x1 * w.y);
                 };
-                stockham_pass_io<real, LOG2M, NT, P>(tid, tb.tw, in, out);
+                stockham_pass_io<real, LOG2M, NT, P, decltype(in), decltype(out), TW_DERIVE>(tid, tb.tw, in, out);
             }
         } else {
             const C *src = sm.buf[(P - 1) & 1];
             auto in = [&](int a, int c) { return ld_sw(src, a, c); };
-            stockham_pass_io<real, LOG2M, NT, P>(tid, tb.tw, in, out);
+            stockham_pass_io<real, LOG2M, NT, P, decltype(in), decltype(out), TW_DERIVE>(tid, tb.tw, in, out);
         }
     }
 
@@ -1037,7 +1046,7 @@ struct Chain {
         if (P < PASSES - 1) {
             C *dst = inv_buffer(sm, P + 1);
             auto out = [&](int x, int c, C v) { st_sw(dst, x, c, v); };
-            stockham_pass_io<real, LOG2M, NT, P>(tid, tb.tw, in, out);
+            stockham_pass_io<real, LOG2M, NT, P, decltype(in), decltype(out), TW_DERIVE>(tid, tb.tw, in, out);
         } else {
             otype *dstg = reinterpret_cast<otype *>(a.out) + (long long)lane * a.out_stride + out_pos;
             const C *ws = reinterpret_cast<const C *>(tb.win_s);
@@ -1069,7 +1078,7 @@ struct Chain {
                     if (2 * m < emit_end) *reinterpret_cast<OC *>(dstg + 2 * m) = mk<otype>(emit_val(t.x, vx), emit_val(t.y, vy));
                     *slot = mk<otype>(done ? (otype)0 : tail_val(t.x, vx), done ? (otype)0 : tail_val(t.y, vy));
                 };
-                stockham_pass_io<real, LOG2M, NT, P>(tid, tb.tw, in, out);
+                stockham_pass_io<real, LOG2M, NT, P, decltype(in), decltype(out), TW_DERIVE>(tid, tb.tw, in, out);
             } else {
                 auto out = [&](int x, int c, C f) {
                     const int m = x + c;
@@ -1088,7 +1097,7 @@ struct Chain {
                         sm.ola[slot] = acc;
                     }
                 };
-                stockham_pass_io<real, LOG2M, NT, P>(tid, tb.tw, in, out);
+                stockham_pass_io<real, LOG2M, NT, P, decltype(in), decltype(out), TW_DERIVE>(tid, tb.tw, in, out);
             }
             // hop larger than the frame: nothing overlaps those positions (tinyspec.cpp:184-191)
             for (int n = N + tid; n < hop; n += NT)

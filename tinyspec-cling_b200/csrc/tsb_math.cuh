@@ -193,7 +193,7 @@ struct TwLayout {
 // radix-R DFT and hands out(base, t*Ns, value) with base = (j/Ns)*Ns*R + (j%Ns).  `in` / `out` are
 // functors so that the first pass can read (and window) the input ring and the last pass can feed the
 // overlap-add directly.  `twp` is the per-pass twiddle table (TwLayout).
-template <typename T, int LOG2M, int THREADS, int P, class In, class Out>
+template <typename T, int LOG2M, int THREADS, int P, class In, class Out, int TW_DERIVE = 0>
 TSB_HD void stockham_pass_io(int tid, const cpx<T> *twp, In in, Out out) {
     using RP = RadixPlan<LOG2M>;
     constexpr int M = 1 << LOG2M;
@@ -212,8 +212,25 @@ TSB_HD void stockham_pass_io(int tid, const cpx<T> *twp, In in, Out out) {
             int jm = j & (Ns - 1);
             const cpx<T> *w = twp + TwLayout<LOG2M>::offset(P) + jm;
             cpx<T> tw[R];
+            if (TW_DERIVE >= 1 && R == 8) {
+                // fewer table reads (the L1/shared-memory data pipe is the busiest unit of the fp64 kernel): powers
+                // of the loaded twiddles by complex multiplication, at most two products deep
+                tw[1] = TSB_LDG(&w[0]);
+                if (TW_DERIVE >= 2) {
+                    tw[2] = cmul(tw[1], tw[1]);
+                    tw[4] = cmul(tw[2], tw[2]);
+                } else {
+                    tw[2] = TSB_LDG(&w[Ns]);
+                    tw[4] = TSB_LDG(&w[3 * Ns]);
+                }
+                tw[3] = cmul(tw[1], tw[2]);
+                tw[5] = cmul(tw[1], tw[4]);
+                tw[6] = cmul(tw[2], tw[4]);
+                tw[7] = cmul(tw[3], tw[4]);
+            } else {
 #pragma unroll
-            for (int t = 1; t < R; t++) tw[t] = TSB_LDG(&w[(t - 1) * Ns]);
+                for (int t = 1; t < R; t++) tw[t] = TSB_LDG(&w[(t - 1) * Ns]);
+            }
 #pragma unroll
             for (int t = 0; t < R; t++) v[t] = in(j, t * NB);
 #pragma unroll

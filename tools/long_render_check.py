@@ -16,12 +16,19 @@ from oracle import orc
 ap = argparse.ArgumentParser()
 ap.add_argument("--seconds", type=float, default=600.0)
 ap.add_argument("--ratio", type=float, default=1.5)
+ap.add_argument("--cache", default=None, help="npz path: reuse the oracle's result between runs (comparing library builds)")
 args = ap.parse_args()
 n, hop, ch = 1024, 256, 2
 L = int(args.seconds * 48000)
 x = orc.gen_signal(0, ch, L)
 t0 = time.time()
-ref = orc.render_pv(x, n, 0.25, args.ratio)
+if args.cache and os.path.exists(args.cache):
+    z = np.load(args.cache)
+    ref = {"frames": int(z["frames"]), "ola64": z["ola64"], "phase_sum": z["phase_sum"]}
+else:
+    ref = orc.render_pv(x, n, 0.25, args.ratio)
+    if args.cache:
+        np.savez(args.cache, frames=ref["frames"], ola64=ref["ola64"], phase_sum=ref["phase_sum"])
 t_cpu = time.time() - t0
 F = ref["frames"]
 ctx = tsb200.Context(0)
