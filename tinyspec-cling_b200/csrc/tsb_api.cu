@@ -351,9 +351,9 @@ TSB_API int tsb_chain_render_host(tsb_ctx *c, tsb_plan *p, const tsb_chain_args 
     const int64_t n = p->desc.n, m = n / 2, lanes = a->lanes, F = a->n_frames;
     const size_t osz = p->desc.precision == TSB_F64 ? 8 : 4;
     const size_t in_bytes = (size_t)lanes * a->in_stride * 4, out_bytes = (size_t)lanes * a->out_stride * osz;
-    // chunks: enough lanes each to keep copies large (>= 256 MB) and at most 16 chunks
+    // chunks: enough lanes each to keep copies large (>= 256 MB) and at most 32 chunks
     int64_t nc = (int64_t)((in_bytes + out_bytes) / (512ull << 20));
-    nc = nc < 1 ? 1 : (nc > 16 ? 16 : nc);
+    nc = nc < 1 ? 1 : (nc > 32 ? 32 : nc);
     if (const char *ev = getenv("TSB_HOST_CHUNKS")) nc = atoi(ev) > 0 ? atoi(ev) : nc;  // tuning
     if (nc > lanes) nc = lanes;
     const bool trace = getenv("TSB_HOST_TRACE") != nullptr;
@@ -423,9 +423,32 @@ TSB_API int tsb_chain_render_host(tsb_ctx *c, tsb_plan *p, const tsb_chain_args 
     CU(cudaStreamWaitEvent(s_in, setup, 0));
     cudaStream_t saved = c->stream;
     int rc = TSB_OK;
+    // Chunk sizes ramp up at the start and down at the end (weights 1,2,3,4,...,4,3,2,1): the download cannot start
+    // before the first chunk is uploaded and rendered, and nothing overlaps the last chunk's render and download,
+    // so those two chunks are kept small; a lane takes the same time to render however few lanes share the launch.
+    std::vector<int64_t> chunk(nc, 0);
+    {
+        std::vector<int64_t> wgt(nc);
+        int64_t wsum = 0;
+        for (int64_t k = 0; k < nc; k++) {
+            int64_t edge = k < nc - 1 - k ? k : nc - 1 - k;
+            wgt[k] = edge < 3 ? edge + 1 : 4;
+            wsum += wgt[k];
+        }
+        int64_t given = 0;
+        for (int64_t k = 0; k < nc; k++) {
+            chunk[k] = lanes * wgt[k] / wsum;
+            given += chunk[k];
+        }
+        for (int64_t k = nc / 2; given < lanes; k = (k + 1) % nc) {  // remainder to the middle chunks
+            chunk[k]++;
+            given++;
+        }
+    }
     int64_t l0 = 0;
     for (int64_t k = 0; k < nc && rc == TSB_OK; k++) {
-        int64_t cnt = lanes / nc + (k < lanes % nc ? 1 : 0);
+        int64_t cnt = chunk[k];
+        if (cnt == 0) continue;
         cudaEvent_t in_done = res.ev(), k_done = res.ev();
         cudaStream_t s_k = c->host_streams[2 + k];
         cudaError_t e = cudaMemcpyAsync(din + (size_t)l0 * a->in_stride, a->in + (size_t)l0 * a->in_stride,
