@@ -49,7 +49,14 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.mark_at = index, [], None, 0
+
+    def mark(self):
+        """rows from here on belong to the load being measured (nvidia-smi is already looping by then)"""
+        self.mark_at = len(self.rows)
+
+    def count(self):
+        return len(self.rows) - self.mark_at
 
     def start(self):
         try:
@@ -68,7 +75,7 @@ class ClockSampler:
         if self.proc:
             self.proc.terminate()
         sm, mx, reasons = [], 0, set()
-        for r in self.rows:
+        for r in self.rows[self.mark_at:]:
             f = [v.strip() for v in r.split(",")]
             try:
                 sm.append(float(f[0]))
@@ -228,11 +235,13 @@ def main():
     x = x_all[:lanes]
 
     def timed(plan, xin, out, steps, warmup, sampler=None):
+        if sampler:
+            sampler.start()  # nvidia-smi takes a few hundred ms to deliver its first row: start it before the warm-up
         for _ in range(warmup):
             plan.render(xin, F, HOP, out=out)
         barrier()
         if sampler:
-            sampler.start()
+            sampler.mark()
         l0 = ctx.launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -240,8 +249,19 @@ def main():
             plan.render(xin, F, HOP, out=out)
         e1.record()
         barrier()
-        clocks = sampler.stop() if sampler else None
-        return max_over_ranks(e0.elapsed_time(e1)), ctx.launches - l0, clocks
+        ms, launches = e0.elapsed_time(e1), ctx.launches - l0
+        clocks = None
+        if sampler:
+            # a timed region shorter than a few sampling periods may have caught no row: keep the same launch
+            # running (untimed) until there are three, so the clocks are always those under this load
+            extra, t_end = 0, time.time() + 3.0
+            while sampler.count() < 3 and time.time() < t_end:
+                plan.render(xin, F, HOP, out=out)
+                torch.cuda.synchronize()
+                extra += 1
+            clocks = sampler.stop()
+            clocks["window"] = "timed region" if not extra else f"timed region + {extra} identical untimed launches"
+        return max_over_ranks(ms), launches, clocks
 
     def device_leg(precision, xin, steps, warmup, sampler=None):
         plan = tsb200.Plan(ctx, N_FRAME, precision=precision, program="pv", hop=HOP, rate=RATE, ratio=SHIFT)
