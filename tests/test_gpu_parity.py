@@ -65,6 +65,13 @@ CASES = [  # n, hop_ratio, shift, channels, samples, stream
     (64, 1.6, 1.5, 2, 9000, 1),         # hop larger than the frame (tinyspec.cpp:184-191), fractional
     (128, 1.0, 2.0, 2, 9000, 1),        # hop equal to the frame: no overlap at all
     (256, 0.3, 1.5, 2, 9000, 1),        # odd hops 76/77
+    # shift maps that exercise the used-bin bookkeeping: halving (two sources per destination, the upper half of
+    # the destinations silent and reordered), x3 and x4 (most sources dropped, most destinations silent)
+    (1024, 0.25, 0.5, 2, 30000, 2),
+    (1024, 0.25, 3.0, 2, 30000, 3),
+    (512, 0.25, 4.0, 1, 20000, 4),
+    (2048, 0.25, 2.0, 2, 40000, 0),
+    (4096, 0.25, 0.5, 1, 40000, 1),
 ]
 
 
@@ -118,8 +125,10 @@ def test_pv_segments_bit_identical(env):
     sch = tsb.schedule_const(x.shape[0], n, hop)
     F = sch["n_frames"]
     xd = torch.from_numpy(np.ascontiguousarray(x.T)).cuda()
-    for precision in ("f64", "f32"):
-        plan = tsb.Plan(env["ctx"], n, precision=precision, program="pv", hop=hop, ratio=1.5)
+    # x2 and x0.5: bins the shift does not use are analysed only on the last frame of each launch, and the state
+    # handed over must still be the reference's
+    for precision, ratio in (("f64", 1.5), ("f32", 1.5), ("f64", 2.0), ("f32", 2.0), ("f64", 0.5)):
+        plan = tsb.Plan(env["ctx"], n, precision=precision, program="pv", hop=hop, ratio=ratio)
         whole = plan.render(xd, F, hop).clone()
         st = {k: torch.zeros((ch, w), dtype=torch.float64, device="cuda") for k, w in
               (("last_phase", n // 2), ("phase_sum", n // 2), ("ola", n))}

@@ -36,7 +36,9 @@ def test_stockham_fft(lg):
 
 @pytest.mark.parametrize("n,hr,shift,ch,samples,stream", [
     (1024, 0.25, 2.0, 2, 14000, 0), (256, 0.25, 1.5, 2, 8000, 0), (64, 0.25, 0.5, 1, 5000, 5),
-    (4096, 0.25, 1.5, 1, 24000, 0), (8192, 0.25, 1.5, 1, 36000, 2), (512, 0.5, 1.2, 1, 9000, 0)])
+    (4096, 0.25, 1.5, 1, 24000, 0), (8192, 0.25, 1.5, 1, 36000, 2), (512, 0.5, 1.2, 1, 9000, 0),
+    # used-bin bookkeeping: halving (two sources per destination, silent upper destinations, reordered pairs), x3
+    (1024, 0.25, 0.5, 1, 14000, 2), (1024, 0.25, 3.0, 1, 14000, 3), (512, 0.25, 4.0, 1, 9000, 4)])
 def test_pv_chain(n, hr, shift, ch, samples, stream):
     x = orc.gen_signal(stream, ch, samples)
     ref = orc.render_pv(x, n, hr, shift)
