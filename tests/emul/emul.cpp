@@ -151,3 +151,14 @@ extern "C" int emul_fft(int precision, int log2m, const double *in, double *out)
     }
     return -1;
 }
+
+// The branch-free fp64 kernels of the PV stages (host build of the same source), element-wise over arrays.
+extern "C" void emul_pv_math(long long n, const double *y, const double *x, double *atan2_out, double *sqrt_out,
+                             int *wrap_out, double *sin_out, double *cos_out) {
+    for (long long i = 0; i < n; i++) {
+        atan2_out[i] = fast_atan2(y[i], x[i]);
+        sqrt_out[i] = sqrt_pos(fabs(x[i]));
+        wrap_out[i] = wrap_quotient(x[i]);
+        fast_sincos(y[i], sin_out[i], cos_out[i]);
+    }
+}

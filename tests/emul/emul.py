@@ -22,12 +22,25 @@ def lib():
                                                                              C.c_longlong, C.c_int, P, P, P, P,
                                                                              C.c_int, C.c_int]
         _lib.emul_fft.argtypes = [C.c_int, C.c_int, P, P]
+        _lib.emul_pv_math.argtypes = [C.c_longlong, P, P, P, P, P, P, P]
+        _lib.emul_pv_math.restype = None
         _lib.emul_chain_render_ex.argtypes = _lib.emul_chain_render.argtypes + [C.c_int, C.c_int, C.c_int, P]
     return _lib
 
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def pv_math(y, x):
+    """(fast_atan2(y, x), sqrt_pos(|x|), wrap_quotient(x), fast_sincos(y)) element-wise: the fp64 kernels of the PV stages"""
+    y = np.ascontiguousarray(y, np.float64)
+    x = np.ascontiguousarray(x, np.float64)
+    n = y.size
+    at, sq, sn, cs = (np.empty(n) for _ in range(4))
+    wr = np.empty(n, np.int32)
+    lib().emul_pv_math(n, _p(y), _p(x), _p(at), _p(sq), _p(wr), _p(sn), _p(cs))
+    return at, sq, wr, sn, cs
 
 
 WIN = {"none": 0, None: 0, "hann": 1, "sqrt_hann": 2}

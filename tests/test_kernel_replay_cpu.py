@@ -126,3 +126,35 @@ def test_gain_chain_float32_output_is_the_reference_stream():
     want = ref["stream"][:out.shape[1]].T
     assert np.count_nonzero(out != want) <= 1e-3 * out.size
     assert np.abs(out.astype(np.float64) - want).max() <= 2.0 ** -23 * np.abs(want).max()
+
+
+def test_fp64_pv_math_kernels():
+    """The branch-free replacements of atan2 / sqrt / (int)(x/M_PI) / sincos in the fp64 chain, against libm."""
+    rng = np.random.default_rng(5)
+    n = 400000
+    mag = 10.0 ** rng.integers(-6, 6, n)
+    x = (rng.random(n) - 0.5) * mag
+    y = (rng.random(n) - 0.5) * 10.0 ** rng.integers(-6, 6, n)
+    y[::1000] = x[::1000] * (np.arange(n)[::1000] // 1000 % 65) / 64.0      # on the table points
+    at, sq, wr, sn, cs = emul.pv_math(y, x)
+    want = np.arctan2(y, x)
+    ulp = np.spacing(np.abs(want))
+    assert np.max(np.abs(at - want) / ulp) <= 2.0
+    assert np.array_equal(sq, np.sqrt(np.abs(x)))                          # correctly rounded
+    # the wrap needs the reference's exact truncated quotient, also on and next to multiples of pi
+    d = np.concatenate([x, np.pi * np.arange(-300, 300), np.nextafter(np.pi * np.arange(-300, 300), 1e9),
+                        np.nextafter(np.pi * np.arange(-300, 300), -1e9)])
+    _, _, wr, _, _ = emul.pv_math(d, d)
+    assert np.array_equal(wr, np.trunc(d / np.pi).astype(np.int32))
+    # sincos of unreduced phases up to 1e9 rad (a one-hour render reaches 8e8): absolute error ~1 ulp of 1
+    ph = (rng.random(n) - 0.5) * 2.0 * 10.0 ** rng.integers(-3, 10, n)
+    _, _, _, sn, cs = emul.pv_math(ph, ph)
+    ld = ph.astype(np.longdouble)
+    assert np.max(np.abs(sn - np.sin(ld).astype(np.float64))) < 2.3e-16
+    assert np.max(np.abs(cs - np.cos(ld).astype(np.float64))) < 2.3e-16
+    # signs and zeros as libm has them
+    yy = np.array([0.0, -0.0, 0.0, -0.0, 1.0, -1.0, 0.0, -0.0])
+    xx = np.array([-0.0, -0.0, 0.0, 0.0, -0.0, 0.0, -2.0, -2.0])
+    at, sq, _, _, _ = emul.pv_math(yy, xx)
+    assert np.array_equal(at, np.arctan2(yy, xx)) and np.array_equal(np.signbit(at), np.signbit(np.arctan2(yy, xx)))
+    assert sq[0] == 0.0

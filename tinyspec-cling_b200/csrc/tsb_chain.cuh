@@ -248,11 +248,11 @@ TSB_HD double sqrt_pos(double x) {
     g = fma(fma(-g, g, xs), h, g);
     return x > 0.0 ? g : 0.0;
 }
-// atan(i/64), i = 0..65, correctly rounded
+// atan(i/64), i = 0..65, correctly rounded (128 slots: the index is masked, so that a NaN input cannot read outside)
 #if defined(__CUDA_ARCH__)
-static __device__ const double k_atan_tab[66] = {
+static __device__ const double k_atan_tab[128] = {
 #else
-static const double k_atan_tab[66] = {
+static const double k_atan_tab[128] = {
 #endif
     0.0, 0.015623728620476831, 0.031239833430268277,
     0.046840712915969654, 0.06241880999595735, 0.0779666338315423,
@@ -286,9 +286,11 @@ TSB_HD double fast_atan2(double y, double x) {
     const double q0 = a * rcp_seed(bs);                       // ~20 bits of a/b
     const double m = q0 * 64.0 + 6755399441055744.0;          // round to nearest integer in the low word
 #if defined(__CUDA_ARCH__)
-    const int i = __double2loint(m);
+    const int i = __double2loint(m) & 127;
 #else
-    const int i = (int)(long long)(m - 6755399441055744.0);
+    uint64_t mbits;
+    memcpy(&mbits, &m, 8);
+    const int i = (int)(mbits & 127);
 #endif
     const double c = (m - 6755399441055744.0) * 0.015625;
     const double t = div_pos(fma(-c, bs, a), fma(c, a, bs));
