@@ -306,6 +306,8 @@ def main():
         # the reference hands float32 to JACK (tinyspec.cpp:43,173-200): the fp64 chain delivers that stream type
         # (TSB_F64_OUT32: same arithmetic and PV state as the device leg, float32 tail/output as the reference's)
         eprec = "f64o32" if (args.precision == "f64" and args.e2e_out == "f32") else args.precision
+        # pinned buffers on the NUMA node next to this rank's GPU (several ranks share the host)
+        bound = None if os.environ.get("TSB_NO_NUMA_BIND") else tsb200.bind_host_to_gpu(local)
         plan = tsb200.Plan(ctx, N_FRAME, precision=eprec, program="pv", hop=HOP, rate=RATE, ratio=SHIFT)
         xh = torch.empty((lanes, L), dtype=torch.float32, pin_memory=True)
         xh.copy_(x)
@@ -322,6 +324,7 @@ def main():
         line["e2e"] = {"value": frames_all / (ems * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": lanes * L * 4,
                        "d2h_bytes_per_step": lanes * F * HOP * oh.element_size(), "ms_per_step": ems, "steps": esteps,
                        "out_dtype": str(oh.dtype).replace("torch.", ""), "arithmetic": args.precision,
+                       "host_cpus_bound": len(bound) if bound else None,
                        "api": "tsb_chain_render_host (pinned host buffers; upload + kernel + download inside the timed region)"}
         del oh, xh
         ctx.trim()  # the context keeps the staging rows between calls: release them for the legs below

@@ -131,6 +131,30 @@ def shift_map(n, rate, fn_bins):
     return dest
 
 
+def bind_host_to_gpu(device=0):
+    """Restrict the calling process to the CPUs next to GPU `device` (NVML's CPU affinity of the device) so that
+    pinned host buffers allocated afterwards sit on that NUMA node: the host-buffer render moves its data at PCIe
+    rate, and with several ranks on one box a remote node's memory and the socket interconnect become the limit.
+    Returns the CPU set used, or None when NVML / the platform gives nothing (nothing is changed then)."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(device)
+        bus_id = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus_id.encode())
+        words = ((os.cpu_count() or 64) + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        use = cpus & os.sched_getaffinity(0)
+        if not use:
+            return None
+        os.sched_setaffinity(0, use)
+        return sorted(use)
+    except Exception:
+        return None
+
+
 class Context:
     """One device + one CUDA stream: stream="torch" (default) runs on torch's current stream of that device,
     stream="new" on a stream the context creates and owns, an int is taken as a cudaStream_t."""
