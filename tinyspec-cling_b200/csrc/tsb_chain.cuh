@@ -25,7 +25,7 @@
 //     ola[N]     real    overlap-add accumulator, slot = absolute output position mod N
 //     buf[2][M]  complex<real>, ping-pong FFT buffers (M = N/2), XOR-swizzled (Swz<real>); the idle one doubles
 //                as the PV stage's phase-increment (and, in fp64, amplitude) exchange array
-//     amp_own[M] real    PV amplitude exchange array (fp32 PV only)
+//     amp_own[M] real    PV amplitude exchange array (fp32 PV, not pipelined; pipelined it lives in ibuf[1])
 //
 // Real-FFT mapping: the reference runs complex FFTs of real data.  Here the N
 // real samples are packed into M = N/2 complex points, transformed once, and split; with
@@ -609,7 +609,7 @@ struct Chain {
         C ibuf[PIPE ? 2 : 1][PIPE ? M : 1];
         // PV amplitude exchange array: fp32 needs its own (the spare FFT buffer is filled by the M fp64
         // increments); in fp64 the spare buffer (16*M bytes) holds both, so nothing extra is reserved.
-        real amp_own[(PROG == PROG_PV_SHIFT && sizeof(real) == 4) ? M : 1];
+        real amp_own[(PROG == PROG_PV_SHIFT && sizeof(real) == 4 && !PIPE) ? M : 1];
     };
     // Per-thread state that lives in registers for the whole launch.
     struct Regs {
@@ -634,7 +634,9 @@ struct Chain {
     // PV exchange arrays (between the analysis and the synthesis phase)
     static TSB_HD double *xch_inc(Smem &sm) { return reinterpret_cast<double *>(fwd_spare(sm)); }
     static TSB_HD real *xch_amp(Smem &sm) {
-        return sizeof(real) == 4 ? sm.amp_own : reinterpret_cast<real *>(xch_inc(sm) + M);
+        // fp32 pipelined: the second inverse buffer is idle between the last and the first inverse pass
+        return sizeof(real) == 4 ? (PIPE ? reinterpret_cast<real *>(sm.ibuf[PIPE ? 1 : 0]) : sm.amp_own)
+                                 : reinterpret_cast<real *>(xch_inc(sm) + M);
     }
     // The inverse transform starts from H: PV writes it over the consumed spectrum (RB), the gain program
     // into the spare buffer (no barrier between its split and merge).  Inverse pass p reads IB(p), writes IB(p+1).
