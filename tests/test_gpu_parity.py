@@ -100,6 +100,26 @@ def test_pv_vs_oracle(env, case, precision):
         assert (dps > 1).sum() == 0, f"{int((dps > 1).sum())} wrap flips"
 
 
+@pytest.mark.parametrize("name,ratio", [("pv_cfg1_60s_tail", 2.0), ("pv_cfg3_shape", 1.5)])
+def test_full_size_render_vs_reference_binary(env, golden, name, ratio):
+    """BASELINE configs[0] at full length (60 s, 11,239 frames) and cfg3's 8 x 4096 shape, against the tail of the
+    float32 stream and the final PhaseVocoder state the compiled, unmodified reference produced — with the mode
+    that delivers the reference's own stream type (fp64 arithmetic, float32 tail and narrowing)."""
+    g = golden(name)
+    n, ch, samples, stream = (int(v) for v in g["meta"])
+    x = env["orc"].gen_signal(stream, ch, samples)
+    out, F, st = run_pv(env, x, n, 0.25, ratio, "f64o32")
+    P = int(g["stream_len"][0]) // ch
+    assert F * (n // 4) == P
+    tail, want = out[:, P - 8192:P].T, g["stream"]
+    assert (tail == want).mean() > 0.999
+    assert np.abs(tail.astype(np.float64) - want).max() <= 2.0 ** -23 * np.abs(want).max()
+    if int(g["frame"][-1]) == F - 1:
+        m = n // 2
+        assert np.abs(st["phase_sum"] - g["phase_sum"][-1][:, :m]).max() < 1e-6   # of up to 1e7 rad
+        assert np.abs(st["last_phase"] - g["last_phase"][-1][:, :m]).max() < 1e-9
+
+
 @pytest.mark.parametrize("name", ["pv_cfg1_short", "pv_x1p5_n256", "pv_down_n512_fracthop"])
 def test_pv_vs_golden(env, golden, name):
     """Directly against what the compiled, unmodified reference produced."""
