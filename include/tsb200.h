@@ -137,23 +137,30 @@ int tsb_chain_render_host(tsb_ctx *ctx, tsb_plan *plan, const tsb_chain_args *ar
  * phase_sum (a running sum of per-frame increments) and the overlap tail.  A render of n_frames frames is cut
  * into time segments that run concurrently (one CTA per segment and lane):
  *   pre-pass  every segment analyses its frames (plus one warm-up frame before it, to obtain last_phase) and
- *             sums its phase increments per bin — no synthesis, no output;
- *   scan      segment s starts from phase_sum = carry-in + the totals of segments 0..s-1, added in order;
+ *             stores the increment each frame adds to each bin's phase_sum — no synthesis, no output;
+ *   scan      per bin, the stored increments are added one frame at a time in frame order, from the carry-in:
+ *             exactly the additions of the sequential render, so every segment starts from the very phase_sum the
+ *             sequential render has there (summing per-segment totals first would regroup them and drift);
  *   main      the full chain per segment from that state, each segment starting with an empty overlap tail;
  *   fix-up    segment s-1's overlap tail is added onto the head of segment s's output, in a fixed order.
- * The result equals tsb_chain_render's up to the regrouping of those floating-point additions (~ulp(phase_sum)).
+ * phase_sum / last_phase are bit-identical to tsb_chain_render's at every frame; the samples differ only where a
+ * tail was added afterwards (the same four addends in another order, ~1 ulp of the sample).
  * This is what lets ONE long stream fill a GPU, and what a multi-GPU time split is built from: rank g renders a
  * block of frames (its input must start one warm-up frame earlier: `warmup` = 1 and args->in_off0 - warm_hop >= 0),
- * pre-passes it, exchanges block totals (tsb_timepar_prepass gives the block's total and final last_phase),
- * sets args' state_phase_sum to the sum of earlier blocks and renders; the final overlap tail (state_ola) goes to
- * rank g+1, which adds it at the head of its output with tsb_add_tail. */
+ * pre-passes it, takes the running phase_sum from rank g-1 (tsb_timepar_scan: carry in, carry out — a chain of
+ * short steps over the ranks), renders, and hands its final overlap tail (state_ola) to rank g+1, which adds it at
+ * the head of its output with tsb_add_tail.  Scratch: lanes * n_frames * n/2 doubles for the stored increments. */
 typedef struct tsb_timepar tsb_timepar;
 /* args is copied (device pointers must stay valid); host_hop_tab = host copy of args->hop_tab (NULL iff hop_tab is NULL) */
 int tsb_timepar_create(tsb_ctx *ctx, tsb_plan *plan, const tsb_chain_args *args, const int32_t *host_hop_tab,
                        int32_t n_segments, int32_t warmup, int32_t warm_hop, tsb_timepar **tp);
 int tsb_timepar_segments(tsb_timepar *tp);   /* segments actually used (each must emit at least n samples) */
-/* block_total / block_last_phase: device [lanes][n/2] float64, may be NULL */
+/* block_total (the block's increments summed from zero) / block_last_phase: device [lanes][n/2] float64, may be NULL */
 int tsb_timepar_prepass(tsb_timepar *tp, double *block_total, double *block_last_phase);
+/* carry_in: device [lanes][n/2] phase_sum before the block's first frame (NULL: args->state_phase_sum, or zeros);
+ * carry_out (may be NULL) receives the phase_sum after its last frame.  Optional: tsb_timepar_render runs it with
+ * carry_in = NULL when it was not called. */
+int tsb_timepar_scan(tsb_timepar *tp, const double *carry_in, double *carry_out);
 /* initial state = args->state_* (NULL or load_state 0: reset state); they receive the final state */
 int tsb_timepar_render(tsb_timepar *tp);
 int tsb_timepar_destroy(tsb_timepar *tp);

@@ -75,6 +75,7 @@ extern "C" int emul_chain_render(int precision, int log2n, int program, int win_
     a.st_last_phase = st_last_phase; a.st_phase_sum = st_phase_sum; a.st_ola = st_ola;
     a.load_state = load_state; a.lanes = lanes;
     a.n_seg = 0; a.seg_tab = nullptr; a.mode = 0; a.st_warm_phase = nullptr;
+    a.st_inc = nullptr; a.inc_frames = 0;
     if (precision == 0)
         return program == PROG_PV_SHIFT ? by_size<float, PROG_PV_SHIFT>(log2n, d, a) : by_size<float, PROG_GAIN>(log2n, d, a);
     if (precision == 2)
@@ -90,7 +91,7 @@ extern "C" int emul_chain_render_ex(int precision, int log2n, int program, int w
                                     long long out_stride, long long out_len, long long n_frames, long long in_off0,
                                     long long out_off0, int hop, const int *hop_tab, double *st_last_phase,
                                     double *st_phase_sum, double *st_ola, int load_state, int lanes, int mode, int warm,
-                                    int warm_hop, double *st_warm_phase) {
+                                    int warm_hop, double *st_warm_phase, double *st_inc) {
     PlanDesc d;
     d.n = 1 << log2n;
     d.program = program;
@@ -110,6 +111,7 @@ extern "C" int emul_chain_render_ex(int precision, int log2n, int program, int w
     a.st_last_phase = st_last_phase; a.st_phase_sum = st_phase_sum; a.st_ola = st_ola;
     a.load_state = load_state; a.lanes = lanes;
     a.n_seg = 1; a.seg_tab = seg; a.mode = mode; a.st_warm_phase = st_warm_phase;
+    a.st_inc = st_inc; a.inc_frames = n_frames;
     if (precision == 0)
         return program == PROG_PV_SHIFT ? by_size<float, PROG_PV_SHIFT>(log2n, d, a) : by_size<float, PROG_GAIN>(log2n, d, a);
     return program == PROG_PV_SHIFT ? by_size<double, PROG_PV_SHIFT>(log2n, d, a) : by_size<double, PROG_GAIN>(log2n, d, a);

@@ -24,7 +24,7 @@ def lib():
         _lib.emul_fft.argtypes = [C.c_int, C.c_int, P, P]
         _lib.emul_pv_math.argtypes = [C.c_longlong, P, P, P, P, P, P, P]
         _lib.emul_pv_math.restype = None
-        _lib.emul_chain_render_ex.argtypes = _lib.emul_chain_render.argtypes + [C.c_int, C.c_int, C.c_int, P]
+        _lib.emul_chain_render_ex.argtypes = _lib.emul_chain_render.argtypes + [C.c_int, C.c_int, C.c_int, P, P]
     return _lib
 
 
@@ -80,7 +80,7 @@ class ReplayBackend:
     def __init__(self, n, hop, ratio, precision="f64", rate=48000.0):
         self.n, self.hop, self.ratio, self.precision, self.rate = n, hop, ratio, precision, rate
 
-    def _call(self, x, n_frames, in_off0, out_len, mode, warm, state, warm_phase, load):
+    def _call(self, x, n_frames, in_off0, out_len, mode, warm, state, warm_phase, load, inc=None):
         lanes, L = x.shape
         dt = np.float64 if self.precision == "f64" else np.float32
         out = np.zeros((lanes, max(out_len, 1)), dt)
@@ -88,7 +88,7 @@ class ReplayBackend:
                                        self.rate, self.ratio, None, None, _p(x), L, L, _p(out), out.shape[1], out_len,
                                        n_frames, in_off0, 0, int(self.hop), None, _p(state["last_phase"]),
                                        _p(state["phase_sum"]), _p(state["ola"]), int(load), lanes, mode, int(warm),
-                                       int(self.hop), _p(warm_phase))
+                                       int(self.hop), _p(warm_phase), _p(inc))
         assert r == 0
         return out
 
@@ -98,10 +98,25 @@ class ReplayBackend:
         self._x, self._nf, self._off, self._warm = np.ascontiguousarray(x, np.float32), n_frames, in_off0, warm
         self._wp = np.zeros((lanes, m))
         st = dict(last_phase=np.zeros((lanes, m)), phase_sum=np.zeros((lanes, m)), ola=np.zeros((lanes, self.n)))
-        self._call(self._x, n_frames, in_off0, 0, 1, warm, st, self._wp, True)
+        self._inc = np.zeros((lanes, max(n_frames, 1), m))
+        self._call(self._x, n_frames, in_off0, 0, 1, warm, st, self._wp, True, self._inc)
         return st["phase_sum"].copy()
 
-    def render(self, carry):
+    def zero_carry(self):
+        return np.zeros((self._x.shape[0], self.n // 2))
+
+    def scan(self, carry):
+        """the running sum after this block, from the sum before it: the block's increments added frame by frame,
+        exactly the additions of the sequential render (tsb_timepar_scan)"""
+        ps = np.ascontiguousarray(carry, np.float64).copy()
+        self._carry = ps.copy()
+        for f in range(self._nf):
+            ps = ps + self._inc[:, f, :]
+        return ps
+
+    def render(self, carry=None):
+        if carry is None:
+            carry = self._carry
         lanes = self._x.shape[0]
         m = self.n // 2
         st = dict(last_phase=np.zeros((lanes, m)), phase_sum=np.ascontiguousarray(carry, np.float64).copy(),

@@ -73,3 +73,12 @@ def test_time_sharded_render_gloo(world):
     want = ref["ola64"][:got.shape[1]].T
     assert got.shape[1] == ref["frames"] * HOP
     assert np.abs(got - want).max() <= 1e-9 * np.abs(want).max()
+    # The phase carry travels down the ranks as the exact running sum, so every block starts from the state the
+    # one-process render has there: the samples are identical except where a block's overlap tail was added
+    # afterwards (the same addends in another order).
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul"))
+    import emul
+    seq, _ = emul.chain_render(orc.gen_signal(0, CH, SAMPLES).T, N, HOP, ref["frames"], precision="f64", ratio=RATIO)
+    same = got == seq
+    assert same.mean() > 1 - 1.01 * (world - 1) * N / got.shape[1]
+    assert np.abs(got - seq).max() <= 4 * np.finfo(np.float64).eps * np.abs(seq).max()

@@ -78,6 +78,7 @@ def _load():
     L.tsb_timepar_create.argtypes = [P, P, C.POINTER(_ChainArgs), P, I32, I32, I32, C.POINTER(P)]
     L.tsb_timepar_segments.argtypes = [P]
     L.tsb_timepar_prepass.argtypes = [P, P, P]
+    L.tsb_timepar_scan.argtypes = [P, P, P]
     L.tsb_timepar_render.argtypes = [P]
     L.tsb_timepar_destroy.argtypes = [P]
     L.tsb_chain_render_timepar.argtypes = [P, P, C.POINTER(_ChainArgs), P, I32]
@@ -424,6 +425,18 @@ class TimePar:
         last = torch.zeros((lanes, m), dtype=torch.float64, device=self.out.device)
         _check(_load().tsb_timepar_prepass(self.h, tot.data_ptr(), last.data_ptr()))
         return tot, last
+
+    def scan(self, carry_in=None):
+        """phase_sum after the block's last frame, from the phase_sum before its first (CUDA float64 [lanes, n/2];
+        None: the state given at creation, or zeros): the block's stored increments added frame by frame."""
+        import torch
+        lanes, m = self.out.shape[0], self.plan.n // 2
+        if carry_in is not None:
+            assert carry_in.is_cuda and carry_in.dtype == torch.float64 and carry_in.shape == (lanes, m) and carry_in.is_contiguous()
+        out = torch.empty((lanes, m), dtype=torch.float64, device=self.out.device)
+        _check(_load().tsb_timepar_scan(self.h, None if carry_in is None else carry_in.data_ptr(), out.data_ptr()))
+        self._carry_in = carry_in
+        return out
 
     def render(self):
         _check(_load().tsb_timepar_render(self.h))

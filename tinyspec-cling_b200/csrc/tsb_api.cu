@@ -312,6 +312,7 @@ static ChainArgs to_args(const tsb_chain_args *a) {
     k.st_last_phase = a->state_last_phase; k.st_phase_sum = a->state_phase_sum; k.st_ola = a->state_ola;
     k.load_state = a->load_state; k.lanes = a->lanes;
     k.n_seg = 0; k.seg_tab = nullptr; k.mode = 0; k.st_warm_phase = nullptr;
+    k.st_inc = nullptr; k.inc_frames = 0;
     return k;
 }
 TSB_API int tsb_chain_render(tsb_ctx *c, tsb_plan *p, const tsb_chain_args *a) {
@@ -656,9 +657,10 @@ struct tsb_timepar {
     std::vector<long long> seg;  // [n_seg][6]
     long long *d_seg = nullptr, *d_pos = nullptr;
     double *d_last = nullptr, *d_sum = nullptr, *d_warm = nullptr, *d_ola = nullptr;
+    double *d_inc = nullptr;  // [lanes][n_frames][m] per-frame increments of every destination bin (pre-pass)
     char *block = nullptr;   // one allocation holding all of the above
     bool from_pool = false;
-    bool prepassed = false;
+    bool prepassed = false, scanned = false;
 };
 TSB_API int tsb_timepar_destroy(tsb_timepar *tp) {
     if (!tp) return TSB_OK;
@@ -727,7 +729,9 @@ TSB_API int tsb_timepar_create(tsb_ctx *c, tsb_plan *p, const tsb_chain_args *a,
     size_t rows = (size_t)nseg * tp->lanes;
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t b_seg = al(tp->seg.size() * 8), b_pos = al((size_t)nseg * 8), b_m = al(rows * tp->m * 8), b_n = al(rows * tp->n * 8);
-    const size_t total = b_seg + b_pos + 3 * b_m + b_n;
+    const bool pv = p->desc.program == TSB_PROG_PV_SHIFT;
+    const size_t b_inc = pv ? al(tp->lanes * (size_t)(F > 0 ? F : 1) * tp->m * 8) : 0;
+    const size_t total = b_seg + b_pos + 3 * b_m + b_n + b_inc;
     // one block for everything; the context keeps it for the next call (allocation costs as much as the render of
     // a single stream).  Reuse is safe in stream order; a second live tsb_timepar gets its own block.
     if (!c->tp_pool_busy) {
@@ -754,7 +758,8 @@ TSB_API int tsb_timepar_create(tsb_ctx *c, tsb_plan *p, const tsb_chain_args *a,
     tp->d_last = (double *)q; q += b_m;
     tp->d_sum = (double *)q; q += b_m;
     tp->d_warm = (double *)q; q += b_m;
-    tp->d_ola = (double *)q;
+    tp->d_ola = (double *)q; q += b_n;
+    tp->d_inc = pv ? (double *)q : nullptr;
     CU(cudaMemcpyAsync(tp->d_seg, tp->seg.data(), tp->seg.size() * 8, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(tp->d_pos, pos.data(), (size_t)nseg * 8, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));  // seg / pos are host temporaries
@@ -772,6 +777,8 @@ static int timepar_launch(tsb_timepar *tp, int mode) {
     k.st_phase_sum = tp->d_sum;
     k.st_ola = tp->d_ola;
     k.st_warm_phase = tp->d_warm;
+    k.st_inc = mode == 1 ? tp->d_inc : nullptr;
+    k.inc_frames = tp->args.n_frames;
     k.load_state = 1;
     chain_launch_fn fn = launcher(p->log2n);
     if (!fn) return fail(TSB_EUNSUPPORTED, "no kernel for frame size 2^%d", p->log2n);
@@ -799,17 +806,43 @@ TSB_API int tsb_timepar_prepass(tsb_timepar *tp, double *block_total, double *bl
         if (block_last_phase) CU(cudaMemsetAsync(block_last_phase, 0, tp->lanes * tp->m * 8, c->stream));
         CU(cudaMemsetAsync(tp->d_sum, 0, rows * tp->m * 8, c->stream));
         tp->prepassed = true;
+        tp->scanned = true;  // no phase state: every segment starts from zeros
         return TSB_OK;
     }
     CU(cudaMemsetAsync(tp->d_last, 0, rows * tp->m * 8, c->stream));
     int r = seed_rows(tp, tp->d_last, tp->args.state_last_phase, tp->m);
     if (r) return r;
     if ((r = timepar_launch(tp, 1))) return r;
-    if (block_total) CU(op_timepar_scan(tp->d_sum, nullptr, block_total, (long long)tp->lanes, (long long)tp->m, tp->n_seg, c->stream));
+    if (block_total)
+        CU(op_timepar_scan(tp->d_inc, tp->args.n_frames, tp->d_seg, tp->n_seg, nullptr, nullptr, block_total, (long long)tp->lanes,
+                           (long long)tp->m, c->stream));
     if (block_last_phase)
         CU(cudaMemcpyAsync(block_last_phase, tp->d_last + (rows - tp->lanes) * tp->m, tp->lanes * tp->m * 8,
                            cudaMemcpyDeviceToDevice, c->stream));
     tp->prepassed = true;
+    tp->scanned = false;
+    if (block_total) c->launches++;
+    return TSB_OK;
+}
+TSB_API int tsb_timepar_scan(tsb_timepar *tp, const double *carry_in, double *carry_out) {
+    if (!tp) return fail(TSB_EINVAL, "null argument");
+    if (!tp->prepassed) return fail(TSB_EINVAL, "tsb_timepar_scan before tsb_timepar_prepass");
+    tsb_ctx *c = tp->ctx;
+    CU(cudaSetDevice(c->device));
+    const tsb_chain_args &a = tp->args;
+    if (tp->plan->desc.program != TSB_PROG_PV_SHIFT || a.n_frames == 0 || tp->lanes == 0) {
+        if (carry_out) {
+            if (carry_in) CU(cudaMemcpyAsync(carry_out, carry_in, tp->lanes * tp->m * 8, cudaMemcpyDeviceToDevice, c->stream));
+            else CU(cudaMemsetAsync(carry_out, 0, tp->lanes * tp->m * 8, c->stream));
+        }
+        tp->scanned = true;
+        return TSB_OK;
+    }
+    const double *base = carry_in ? carry_in : ((a.state_phase_sum && a.load_state) ? a.state_phase_sum : nullptr);
+    CU(op_timepar_scan(tp->d_inc, a.n_frames, tp->d_seg, tp->n_seg, base, tp->d_sum, carry_out, (long long)tp->lanes,
+                       (long long)tp->m, c->stream));
+    c->launches++;
+    tp->scanned = true;
     return TSB_OK;
 }
 TSB_API int tsb_timepar_render(tsb_timepar *tp) {
@@ -820,9 +853,9 @@ TSB_API int tsb_timepar_render(tsb_timepar *tp) {
     if (tp->args.n_frames == 0 || tp->lanes == 0) return TSB_OK;
     const size_t rows = (size_t)tp->n_seg * tp->lanes;
     const tsb_chain_args &a = tp->args;
-    const double *base = (a.state_phase_sum && a.load_state) ? a.state_phase_sum : nullptr;
-    CU(op_timepar_scan(tp->d_sum, base, nullptr, (long long)tp->lanes, (long long)tp->m, tp->n_seg, c->stream));
-    int r = seed_rows(tp, tp->d_last, a.state_last_phase, tp->m);  // segment 0 without warm-up starts from the caller's phases
+    int r;
+    if (!tp->scanned && (r = tsb_timepar_scan(tp, nullptr, nullptr))) return r;
+    r = seed_rows(tp, tp->d_last, a.state_last_phase, tp->m);  // segment 0 without warm-up starts from the caller's phases
     if (r) return r;
     CU(cudaMemsetAsync(tp->d_ola, 0, rows * tp->n * 8, c->stream));
     if ((r = seed_rows(tp, tp->d_ola, a.state_ola, tp->n))) return r;

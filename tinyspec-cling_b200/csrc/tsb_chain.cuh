@@ -141,6 +141,8 @@ struct ChainArgs {
     const long long *seg_tab;  // [n_seg][6]: first_frame, n_frames, in_off0, out_off0, warm-up flag, hop of the frame before
     int mode;                  // 0: full chain; 1: pre-pass (analysis + shift + increment accumulation only, no output)
     double *st_warm_phase;     // pre-pass out / main in: [rows][M] last_phase after the warm-up frame (segments with warm-up)
+    double *st_inc;            // pre-pass out (or nullptr): [lanes][inc_frames][M] the increment every frame adds to the
+    long long inc_frames;      //   phase_sum of every destination bin, frames numbered as in hop_tab / seg_tab
 };
 
 // What one CTA works on.
@@ -748,7 +750,8 @@ struct Chain {
     }
     // pre-pass "synthesis": only the phase accumulation of rtlib/pv.hpp:34 (same order of additions as the
     // full kernel), so that a segment's total increment per bin is known before anything is synthesised
-    static TSB_HD void phase_pv_accumulate(int tid, Smem &sm, Regs &rg, const Tables &tb) {
+    // inc_row: where this frame's increments go, [M] (or nullptr)
+    static TSB_HD void phase_pv_accumulate(int tid, Smem &sm, Regs &rg, const Tables &tb, double *inc_row) {
         const double *inc_x = xch_inc(sm);
         const real *amp_x = xch_amp(sm);
 #pragma unroll
@@ -761,9 +764,11 @@ struct Chain {
             if (tb.map1) gather_bin<true>(amp_x, inc_x, tb, k, src_lo(rg.map_src[i]), amp, inc);
             else gather_bin<false>(amp_x, inc_x, tb, k, 0, amp, inc);
             rg.phase_sum[2 * i] = PvMath<real>::accumulate(rg.phase_sum[2 * i], inc);
+            if (inc_row) inc_row[k] = inc;
             if (tb.map1) gather_bin<true>(amp_x, inc_x, tb, kb, src_hi(rg.map_src[i]), amp, inc);
             else gather_bin<false>(amp_x, inc_x, tb, kb, 0, amp, inc);
             rg.phase_sum[2 * i + 1] = PvMath<real>::accumulate(rg.phase_sum[2 * i + 1], inc);
+            if (inc_row) inc_row[kb] = inc;
         }
     }
 
@@ -1221,8 +1226,10 @@ TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const t
     const int *hop_tab;
     bool prepass, warm;
     int warm_hop;
+    long long first_frame;
     {
         SegInfo sg = seg_info<CH>(a, lane, seg);
+        first_frame = sg.first_frame;
         prepass = CH::IS_PV && a.mode == 1;
         warm = prepass && sg.warm;
         warm_hop = sg.warm_hop;
@@ -1292,7 +1299,9 @@ TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const t
                         ex.each([&](int tid, Regs &rg) { CH::regs_to(tid, a.st_warm_phase, row, rg.last_phase); });
                     }
                 } else {
-                    ex.each([&](int tid, Regs &rg) { CH::phase_pv_accumulate(tid, sm, rg, tb); });
+                    double *inc_row = a.st_inc ? a.st_inc + ((long long)lane * a.inc_frames + first_frame + ff - (warm ? 1 : 0)) * CH::M
+                                               : nullptr;
+                    ex.each([&](int tid, Regs &rg) { CH::phase_pv_accumulate(tid, sm, rg, tb, inc_row); });
                 }
                 ex.each([&](int, Regs &) { CH::ring_wait(); });
                 in_off += hop;

@@ -546,29 +546,75 @@ cudaError_t op_pv_shift(const double *tmp, double *pvdata, const double *fn_freq
 }
 
 // ------------------------------------------------------------------ time-parallel PV bookkeeping
-// Per (lane, bin): turn the segments' total increments sum[s] into each segment's starting phase_sum, in
-// segment order — carry_0 = base, carry_{s+1} = carry_s + total_s — the same left-to-right additions the
-// sequential render performs, regrouped per segment.  total_out (optional) receives the sum over all segments.
-__global__ void timepar_scan_kernel(double *sum, const double *base, double *total_out, long long lanes, long long m,
-                                    int n_seg) {
-    long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (idx >= lanes * m) return;
-    double c = base ? base[idx] : 0.0, tot = 0.0;
-    for (int s = 0; s < n_seg; s++) {
-        double t = sum[(long long)s * lanes * m + idx];
-        if (total_out) tot = __dadd_rn(tot, t);
-        else {
-            sum[(long long)s * lanes * m + idx] = c;
-            c = __dadd_rn(c, t);
+// Per (lane, bin): the running phase_sum of the sequential render, from the increments the pre-pass stored
+// (inc[lane][frame][bin]): sum_rows[s] receives the value at the start of segment s, carry_out the value after the
+// last frame.  The additions are the reference's own — one per frame, in frame order, from `base` — so the
+// time-parallel render starts every segment from exactly the state the sequential render has there (summing
+// per-segment totals first regroups them and drifts by ~ulp(phase_sum) per regrouping: 1e-7 of peak at 10 min).
+// A CTA owns SCAN_BINS consecutive bins of one lane: all its threads stream the increments through shared memory
+// (cp.async, tiles of SCAN_TILE frames, double-buffered: the chain of additions is short, the 8 bytes per frame
+// and bin are what takes time), one thread per bin then adds a tile's frames in order.
+constexpr int SCAN_BINS = 16, SCAN_TILE = 128, SCAN_THREADS = 256;
+__global__ void __launch_bounds__(SCAN_THREADS)
+timepar_scan_kernel(const double *inc, long long inc_frames, const long long *seg_tab, int n_seg, const double *base,
+                    double *sum_rows, double *carry_out, long long lanes, long long m) {
+    __shared__ __align__(16) double tile[2][SCAN_TILE][SCAN_BINS];
+    const long long bin_blocks = (m + SCAN_BINS - 1) / SCAN_BINS;
+    const long long lane = blockIdx.x / bin_blocks, bin0 = (blockIdx.x % bin_blocks) * SCAN_BINS;
+    const int tid = threadIdx.x, b = tid % SCAN_BINS, r0 = tid / SCAN_BINS;
+    const bool bin_ok = bin0 + b < m;
+    const double *src = inc + lane * inc_frames * m + bin0 + b;
+    // frames covered: the segments are consecutive, [first_0, first_last + cnt_last)
+    const long long f_begin = seg_tab[0], f_end = seg_tab[6 * (n_seg - 1)] + seg_tab[6 * (n_seg - 1) + 1];
+    auto fetch = [&](int buf, long long f0) {
+        for (int r = r0; r < SCAN_TILE; r += SCAN_THREADS / SCAN_BINS) {
+            const long long f = f0 + r;
+            if (bin_ok && f < f_end) {
+                unsigned dst = (unsigned)__cvta_generic_to_shared(&tile[buf][r][b]);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src + f * m) : "memory");
+            }
         }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    const long long idx = lane * m + bin0 + b;
+    double c = (tid < SCAN_BINS && bin_ok && base) ? base[idx] : 0.0;
+    int s = 0;
+    long long next_start = f_begin;
+    fetch(0, f_begin);
+    int buf = 0;
+    for (long long f0 = f_begin; f0 < f_end; f0 += SCAN_TILE, buf ^= 1) {
+        fetch(buf ^ 1, f0 + SCAN_TILE);  // (an empty group past the end)
+        asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        __syncthreads();
+        if (tid < SCAN_BINS && bin_ok) {
+            const int cnt = (int)((f_end - f0) < SCAN_TILE ? (f_end - f0) : SCAN_TILE);
+            int r = 0;
+            while (r < cnt) {
+                if (f0 + r == next_start) {  // a segment starts here: it starts from the sum so far
+                    if (sum_rows) sum_rows[(long long)s * lanes * m + idx] = c;
+                    s++;
+                    next_start = s < n_seg ? seg_tab[6 * s] : -1;
+                }
+                // up to the next segment start (or the end of the tile) nothing but the additions: the loads do
+                // not depend on the sum, so the compiler batches them ahead of the dependent chain
+                const int stop = (next_start > f0 + r && next_start < f0 + cnt) ? (int)(next_start - f0) : cnt;
+#pragma unroll 8
+                for (; r < stop; r++) c = __dadd_rn(c, tile[buf][r][b]);
+            }
+        }
+        __syncthreads();
     }
-    if (total_out) total_out[idx] = tot;
+    if (tid < SCAN_BINS && bin_ok) {
+        for (; s < n_seg; s++)  // (segments without frames)
+            if (sum_rows) sum_rows[(long long)s * lanes * m + idx] = c;
+        if (carry_out) carry_out[idx] = c;
+    }
 }
-cudaError_t op_timepar_scan(double *sum, const double *base, double *total_out, long long lanes, long long m, int n_seg,
-                            cudaStream_t st) {
-    if (lanes * m == 0) return cudaSuccess;
-    const int TB = 128;
-    timepar_scan_kernel<<<(unsigned)((lanes * m + TB - 1) / TB), TB, 0, st>>>(sum, base, total_out, lanes, m, n_seg);
+cudaError_t op_timepar_scan(const double *inc, long long inc_frames, const long long *seg_tab, int n_seg, const double *base,
+                            double *sum_rows, double *carry_out, long long lanes, long long m, cudaStream_t st) {
+    if (lanes * m == 0 || n_seg <= 0) return cudaSuccess;
+    const long long grid = ((m + SCAN_BINS - 1) / SCAN_BINS) * lanes;
+    timepar_scan_kernel<<<(unsigned)grid, SCAN_THREADS, 0, st>>>(inc, inc_frames, seg_tab, n_seg, base, sum_rows, carry_out, lanes, m);
     return cudaGetLastError();
 }
 // out[lane][pos + i] += tail[lane][i] (i < n): a segment's overlap tail lands on the head of the next segment's

@@ -23,8 +23,8 @@ cudaError_t op_gather(const float *in, long long in_stride, long long in_len, lo
 cudaError_t op_overlap_add(const double *frame, long long osize, long long hop, float *out, long long out_stride,
                            long long out_len, long long out_off, const float *tail_in, float *tail_out, long long tail_cap,
                            long long tail_len, long long new_tail_len, long long lanes, cudaStream_t st);
-cudaError_t op_timepar_scan(double *sum, const double *base, double *total_out, long long lanes, long long m, int n_seg,
-                            cudaStream_t st);
+cudaError_t op_timepar_scan(const double *inc, long long inc_frames, const long long *seg_tab, int n_seg, const double *base,
+                            double *sum_rows, double *carry_out, long long lanes, long long m, cudaStream_t st);
 cudaError_t op_add_tails(void *out, int is_f64, long long out_stride, long long out_len, const long long *pos_tab,
                          int n_tails, const double *tails, long long lanes, long long n, cudaStream_t st);
 }  // namespace tsb

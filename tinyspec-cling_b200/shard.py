@@ -3,12 +3,15 @@
 * by stream: lanes never interact, so rank r simply renders streams split_streams(S, world, r): no collective.
 * by time segment, for one long render (BASELINE cfg3): rank r owns a contiguous block of frames.  Three things
   cross a block boundary: the input halo (the block's first frame needs one warm-up frame before
-  it, and its last frame reaches frame-hop samples past the block's own hops), the per-bin phase carry (an
-  exclusive scan of the blocks' total phase increments) and the overlap tail (frame-hop samples that land on the
-  next block's head).  The scan is one all_gather of [lanes, n/2] float64 per rank; the tail is one neighbour
-  send/recv; both are KBs..MBs, latency-bound, and go over NCCL (NVLink P2P).
+  it, and its last frame reaches frame-hop samples past the block's own hops), the per-bin phase carry and the
+  overlap tail (frame-hop samples that land on the next block's head).  The carry is the running phase_sum itself:
+  every rank pre-passes its block concurrently (storing each frame's increments), then the sum travels down the
+  ranks — rank r receives it, adds its block's increments one frame at a time (tsb_timepar_scan, ~0.1 ms) and
+  passes it on — so that every block starts from exactly the state the sequential render has there; summing block
+  totals first would regroup the additions and drift by ~ulp(phase_sum) per block and segment.  Carry and tail
+  are [lanes, n/2] / [lanes, n] float64 neighbour messages, latency-bound, over NCCL (NVLink P2P).
 
-The device work sits behind a small backend interface (prepass / render / add_tail) so that the orchestration
+The device work sits behind a small backend interface (prepass / scan / render / add_tail) so that the orchestration
 can be exercised with gloo on CPU ranks against a replay of the kernel (tests/test_shard_gloo.py).
 """
 import numpy as np
@@ -46,32 +49,29 @@ def plan_time_blocks(sch, n, world):
     return blocks
 
 
-def exclusive_carry(totals, rank):
-    """Phase carry into block `rank`: totals of the earlier blocks added in block order (the sequential render's
-    left-to-right additions, regrouped per block)."""
-    carry = np.zeros_like(np.asarray(totals[0])) if not hasattr(totals[0], "clone") else totals[0].clone().zero_()
-    for q in range(rank):
-        carry = carry + totals[q]
-    return carry
-
-
 def render_time_sharded(backend, x_block, block, dist, device_tensor=None):
     """One rank's part of a time-sharded render.  `x_block` holds input samples [block.in_lo, block.in_hi) of every
     lane; returns this rank's output samples [block.out_lo, block.out_hi).
 
-    backend.prepass(x, n_frames, in_off0, warm) -> block total increments [lanes, n/2]
-    backend.render(carry) -> (out [lanes, out_hi-out_lo], tail [lanes, n])
+    backend.prepass(x, n_frames, in_off0, warm)   analyses the block, keeps every frame's increments
+    backend.scan(carry_in [lanes, n/2]) -> carry_out: the running phase_sum after the block, exact
+    backend.render() -> (out [lanes, out_hi-out_lo], tail [lanes, n])
     backend.add_tail(out, tail) -> out with the previous block's tail added at its head
     `dist` is torch.distributed (nccl on GPUs, gloo in the CPU test); device_tensor(t) moves a numpy array or
     tensor to the tensor type the process group communicates (identity by default)."""
     import torch
     rank, world = dist.get_rank(), dist.get_world_size()
     to_t = device_tensor or (lambda a: a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a)))
-    total = to_t(backend.prepass(x_block, block["n_frames"], block["in_off0"], block["warm"]))
-    gathered = [torch.empty_like(total) for _ in range(world)]
-    dist.all_gather(gathered, total)                       # [lanes, n/2] float64 per rank
-    carry = exclusive_carry(gathered, rank)
-    out, tail = backend.render(carry)
+    backend.prepass(x_block, block["n_frames"], block["in_off0"], block["warm"])
+    # the running phase_sum travels down the ranks: receive, add this block's increments in frame order, pass on
+    zero = backend.zero_carry()
+    carry = to_t(zero)
+    if rank > 0:
+        dist.recv(carry, rank - 1)
+    carry_out = backend.scan(carry if torch.is_tensor(zero) else carry.numpy())
+    if rank + 1 < world:
+        dist.send(to_t(carry_out), rank + 1)
+    out, tail = backend.render()
     tail_t = to_t(tail)
     reqs = []
     if rank + 1 < world:
@@ -101,11 +101,15 @@ class GpuBackend:
         self.tp = self.plan.timepar(x, n_frames, self.hop, self.n_segments, in_off0=in_off0, out_off0=0,
                                     hop_tab=self.hop_tab, state=self.state, load_state=True, warmup=warm,
                                     warm_hop=self.hop)
-        total, _ = self.tp.prepass()
-        return total
+        self.tp.prepass()
 
-    def render(self, carry):
-        self.state["phase_sum"].copy_(carry)
+    def zero_carry(self):
+        return self.state["phase_sum"].clone().zero_()
+
+    def scan(self, carry):
+        return self.tp.scan(carry.contiguous())
+
+    def render(self):
         out = self.tp.render()
         return out, self.state["ola"]
 
