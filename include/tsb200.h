@@ -161,6 +161,9 @@ int tsb_timepar_prepass(tsb_timepar *tp, double *block_total, double *block_last
  * carry_out (may be NULL) receives the phase_sum after its last frame.  Optional: tsb_timepar_render runs it with
  * carry_in = NULL when it was not called. */
 int tsb_timepar_scan(tsb_timepar *tp, const double *carry_in, double *carry_out);
+/* The same for lanes lane0 .. lane0+n_lanes-1 only (carry_in / carry_out: [n_lanes][n/2]): lanes are independent, so
+ * a chain of ranks can hand the sums on lane by lane and overlap their scans.  The caller covers every lane. */
+int tsb_timepar_scan_lanes(tsb_timepar *tp, int32_t lane0, int32_t n_lanes, const double *carry_in, double *carry_out);
 /* initial state = args->state_* (NULL or load_state 0: reset state); they receive the final state */
 int tsb_timepar_render(tsb_timepar *tp);
 int tsb_timepar_destroy(tsb_timepar *tp);

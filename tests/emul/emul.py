@@ -105,13 +105,17 @@ class ReplayBackend:
     def zero_carry(self):
         return np.zeros((self._x.shape[0], self.n // 2))
 
-    def scan(self, carry):
-        """the running sum after this block, from the sum before it: the block's increments added frame by frame,
-        exactly the additions of the sequential render (tsb_timepar_scan)"""
+    def scan(self, carry, lane0=0, n_lanes=None):
+        """the running sum of lanes lane0.. after this block, from the sum before it: the block's increments added
+        frame by frame, exactly the additions of the sequential render (tsb_timepar_scan_lanes)"""
+        lanes = self._x.shape[0]
+        n_lanes = lanes - lane0 if n_lanes is None else n_lanes
         ps = np.ascontiguousarray(carry, np.float64).copy()
-        self._carry = ps.copy()
+        if not hasattr(self, "_carry"):
+            self._carry = np.zeros((lanes, self.n // 2))
+        self._carry[lane0:lane0 + n_lanes] = ps
         for f in range(self._nf):
-            ps = ps + self._inc[:, f, :]
+            ps = ps + self._inc[lane0:lane0 + n_lanes, f, :]
         return ps
 
     def render(self, carry=None):

@@ -319,7 +319,8 @@ def test_timepar_two_blocks_like_two_gpus(env):
     tp1.prepass()
     carry = tp0.scan()                       # running sum after block 0 ...
     assert torch.equal(carry, tot0)          # ... which from a zero start is also its total
-    end = tp1.scan(carry)                    # ... is where block 1 starts
+    # ... is where block 1 starts; handed on lane by lane, as a chain of ranks does
+    end = torch.cat([tp1.scan(carry[c:c + 1].contiguous(), c, 1) for c in range(ch)])
     tp1.render()
     tp0.render()
     plan.add_tail(out, int(sch["out_off"][F0]), st0["ola"])

@@ -79,6 +79,7 @@ def _load():
     L.tsb_timepar_segments.argtypes = [P]
     L.tsb_timepar_prepass.argtypes = [P, P, P]
     L.tsb_timepar_scan.argtypes = [P, P, P]
+    L.tsb_timepar_scan_lanes.argtypes = [P, I32, I32, P, P]
     L.tsb_timepar_render.argtypes = [P]
     L.tsb_timepar_destroy.argtypes = [P]
     L.tsb_chain_render_timepar.argtypes = [P, P, C.POINTER(_ChainArgs), P, I32]
@@ -426,16 +427,19 @@ class TimePar:
         _check(_load().tsb_timepar_prepass(self.h, tot.data_ptr(), last.data_ptr()))
         return tot, last
 
-    def scan(self, carry_in=None):
-        """phase_sum after the block's last frame, from the phase_sum before its first (CUDA float64 [lanes, n/2];
-        None: the state given at creation, or zeros): the block's stored increments added frame by frame."""
+    def scan(self, carry_in=None, lane0=0, n_lanes=None):
+        """phase_sum after the block's last frame, from the phase_sum before its first (CUDA float64 [n_lanes, n/2];
+        None: the state given at creation, or zeros): the block's stored increments added frame by frame.
+        lane0 / n_lanes restrict it to some lanes (a chain of ranks hands the sums on lane by lane)."""
         import torch
         lanes, m = self.out.shape[0], self.plan.n // 2
+        n_lanes = lanes - lane0 if n_lanes is None else n_lanes
         if carry_in is not None:
-            assert carry_in.is_cuda and carry_in.dtype == torch.float64 and carry_in.shape == (lanes, m) and carry_in.is_contiguous()
-        out = torch.empty((lanes, m), dtype=torch.float64, device=self.out.device)
-        _check(_load().tsb_timepar_scan(self.h, None if carry_in is None else carry_in.data_ptr(), out.data_ptr()))
-        self._carry_in = carry_in
+            assert carry_in.is_cuda and carry_in.dtype == torch.float64 and carry_in.shape == (n_lanes, m) and carry_in.is_contiguous()
+        out = torch.empty((n_lanes, m), dtype=torch.float64, device=self.out.device)
+        _check(_load().tsb_timepar_scan_lanes(self.h, int(lane0), int(n_lanes), None if carry_in is None else carry_in.data_ptr(),
+                                              out.data_ptr()))
+        self._keep_carry = carry_in
         return out
 
     def render(self):

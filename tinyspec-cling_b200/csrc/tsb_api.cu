@@ -815,7 +815,7 @@ TSB_API int tsb_timepar_prepass(tsb_timepar *tp, double *block_total, double *bl
     if ((r = timepar_launch(tp, 1))) return r;
     if (block_total)
         CU(op_timepar_scan(tp->d_inc, tp->args.n_frames, tp->d_seg, tp->n_seg, nullptr, nullptr, block_total, (long long)tp->lanes,
-                           (long long)tp->m, c->stream));
+                           (long long)tp->m, 0, (long long)tp->lanes, c->stream));
     if (block_last_phase)
         CU(cudaMemcpyAsync(block_last_phase, tp->d_last + (rows - tp->lanes) * tp->m, tp->lanes * tp->m * 8,
                            cudaMemcpyDeviceToDevice, c->stream));
@@ -824,26 +824,34 @@ TSB_API int tsb_timepar_prepass(tsb_timepar *tp, double *block_total, double *bl
     if (block_total) c->launches++;
     return TSB_OK;
 }
-TSB_API int tsb_timepar_scan(tsb_timepar *tp, const double *carry_in, double *carry_out) {
+TSB_API int tsb_timepar_scan_lanes(tsb_timepar *tp, int32_t lane0, int32_t n_lanes, const double *carry_in, double *carry_out) {
     if (!tp) return fail(TSB_EINVAL, "null argument");
     if (!tp->prepassed) return fail(TSB_EINVAL, "tsb_timepar_scan before tsb_timepar_prepass");
+    if (lane0 < 0 || n_lanes < 0 || (size_t)lane0 + (size_t)n_lanes > tp->lanes)
+        return fail(TSB_EINVAL, "lanes %d..%d out of range (0..%zu)", lane0, lane0 + n_lanes, tp->lanes);
     tsb_ctx *c = tp->ctx;
     CU(cudaSetDevice(c->device));
     const tsb_chain_args &a = tp->args;
-    if (tp->plan->desc.program != TSB_PROG_PV_SHIFT || a.n_frames == 0 || tp->lanes == 0) {
-        if (carry_out) {
-            if (carry_in) CU(cudaMemcpyAsync(carry_out, carry_in, tp->lanes * tp->m * 8, cudaMemcpyDeviceToDevice, c->stream));
-            else CU(cudaMemsetAsync(carry_out, 0, tp->lanes * tp->m * 8, c->stream));
+    const size_t bytes = (size_t)n_lanes * tp->m * 8;
+    if (tp->plan->desc.program != TSB_PROG_PV_SHIFT || a.n_frames == 0 || n_lanes == 0) {
+        if (carry_out && bytes) {
+            if (carry_in) CU(cudaMemcpyAsync(carry_out, carry_in, bytes, cudaMemcpyDeviceToDevice, c->stream));
+            else CU(cudaMemsetAsync(carry_out, 0, bytes, c->stream));
         }
         tp->scanned = true;
         return TSB_OK;
     }
-    const double *base = carry_in ? carry_in : ((a.state_phase_sum && a.load_state) ? a.state_phase_sum : nullptr);
+    const double *base = carry_in;
+    if (!base && a.state_phase_sum && a.load_state) base = a.state_phase_sum + (size_t)lane0 * tp->m;
     CU(op_timepar_scan(tp->d_inc, a.n_frames, tp->d_seg, tp->n_seg, base, tp->d_sum, carry_out, (long long)tp->lanes,
-                       (long long)tp->m, c->stream));
+                       (long long)tp->m, lane0, n_lanes, c->stream));
     c->launches++;
     tp->scanned = true;
     return TSB_OK;
+}
+TSB_API int tsb_timepar_scan(tsb_timepar *tp, const double *carry_in, double *carry_out) {
+    if (!tp) return fail(TSB_EINVAL, "null argument");
+    return tsb_timepar_scan_lanes(tp, 0, (int32_t)tp->lanes, carry_in, carry_out);
 }
 TSB_API int tsb_timepar_render(tsb_timepar *tp) {
     if (!tp) return fail(TSB_EINVAL, "null argument");

@@ -557,10 +557,11 @@ cudaError_t op_pv_shift(const double *tmp, double *pvdata, const double *fn_freq
 constexpr int SCAN_BINS = 16, SCAN_TILE = 128, SCAN_THREADS = 256;
 __global__ void __launch_bounds__(SCAN_THREADS)
 timepar_scan_kernel(const double *inc, long long inc_frames, const long long *seg_tab, int n_seg, const double *base,
-                    double *sum_rows, double *carry_out, long long lanes, long long m) {
+                    double *sum_rows, double *carry_out, long long lanes, long long m, long long lane0) {
     __shared__ __align__(16) double tile[2][SCAN_TILE][SCAN_BINS];
     const long long bin_blocks = (m + SCAN_BINS - 1) / SCAN_BINS;
-    const long long lane = blockIdx.x / bin_blocks, bin0 = (blockIdx.x % bin_blocks) * SCAN_BINS;
+    // lanes lane0 .. lane0 + gridDim.x / bin_blocks - 1; base / carry_out are indexed from lane0
+    const long long sub = blockIdx.x / bin_blocks, lane = lane0 + sub, bin0 = (blockIdx.x % bin_blocks) * SCAN_BINS;
     const int tid = threadIdx.x, b = tid % SCAN_BINS, r0 = tid / SCAN_BINS;
     const bool bin_ok = bin0 + b < m;
     const double *src = inc + lane * inc_frames * m + bin0 + b;
@@ -576,8 +577,8 @@ timepar_scan_kernel(const double *inc, long long inc_frames, const long long *se
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     };
-    const long long idx = lane * m + bin0 + b;
-    double c = (tid < SCAN_BINS && bin_ok && base) ? base[idx] : 0.0;
+    const long long idx = lane * m + bin0 + b, sidx = sub * m + bin0 + b;
+    double c = (tid < SCAN_BINS && bin_ok && base) ? base[sidx] : 0.0;
     int s = 0;
     long long next_start = f_begin;
     fetch(0, f_begin);
@@ -607,14 +608,16 @@ timepar_scan_kernel(const double *inc, long long inc_frames, const long long *se
     if (tid < SCAN_BINS && bin_ok) {
         for (; s < n_seg; s++)  // (segments without frames)
             if (sum_rows) sum_rows[(long long)s * lanes * m + idx] = c;
-        if (carry_out) carry_out[idx] = c;
+        if (carry_out) carry_out[sidx] = c;
     }
 }
 cudaError_t op_timepar_scan(const double *inc, long long inc_frames, const long long *seg_tab, int n_seg, const double *base,
-                            double *sum_rows, double *carry_out, long long lanes, long long m, cudaStream_t st) {
-    if (lanes * m == 0 || n_seg <= 0) return cudaSuccess;
-    const long long grid = ((m + SCAN_BINS - 1) / SCAN_BINS) * lanes;
-    timepar_scan_kernel<<<(unsigned)grid, SCAN_THREADS, 0, st>>>(inc, inc_frames, seg_tab, n_seg, base, sum_rows, carry_out, lanes, m);
+                            double *sum_rows, double *carry_out, long long lanes, long long m, long long lane0,
+                            long long n_lanes, cudaStream_t st) {
+    if (n_lanes * m == 0 || n_seg <= 0) return cudaSuccess;
+    const long long grid = ((m + SCAN_BINS - 1) / SCAN_BINS) * n_lanes;
+    timepar_scan_kernel<<<(unsigned)grid, SCAN_THREADS, 0, st>>>(inc, inc_frames, seg_tab, n_seg, base, sum_rows, carry_out, lanes, m,
+                                                                 lane0);
     return cudaGetLastError();
 }
 // out[lane][pos + i] += tail[lane][i] (i < n): a segment's overlap tail lands on the head of the next segment's

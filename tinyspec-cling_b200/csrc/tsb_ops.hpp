@@ -24,7 +24,8 @@ cudaError_t op_overlap_add(const double *frame, long long osize, long long hop, 
                            long long out_len, long long out_off, const float *tail_in, float *tail_out, long long tail_cap,
                            long long tail_len, long long new_tail_len, long long lanes, cudaStream_t st);
 cudaError_t op_timepar_scan(const double *inc, long long inc_frames, const long long *seg_tab, int n_seg, const double *base,
-                            double *sum_rows, double *carry_out, long long lanes, long long m, cudaStream_t st);
+                            double *sum_rows, double *carry_out, long long lanes, long long m, long long lane0,
+                            long long n_lanes, cudaStream_t st);
 cudaError_t op_add_tails(void *out, int is_f64, long long out_stride, long long out_len, const long long *pos_tab,
                          int n_tails, const double *tails, long long lanes, long long n, cudaStream_t st);
 }  // namespace tsb

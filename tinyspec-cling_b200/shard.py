@@ -54,7 +54,7 @@ def render_time_sharded(backend, x_block, block, dist, device_tensor=None):
     lane; returns this rank's output samples [block.out_lo, block.out_hi).
 
     backend.prepass(x, n_frames, in_off0, warm)   analyses the block, keeps every frame's increments
-    backend.scan(carry_in [lanes, n/2]) -> carry_out: the running phase_sum after the block, exact
+    backend.scan(carry_in [k, n/2], lane0, k) -> carry_out: the running phase_sum of those lanes after the block
     backend.render() -> (out [lanes, out_hi-out_lo], tail [lanes, n])
     backend.add_tail(out, tail) -> out with the previous block's tail added at its head
     `dist` is torch.distributed (nccl on GPUs, gloo in the CPU test); device_tensor(t) moves a numpy array or
@@ -64,13 +64,19 @@ def render_time_sharded(backend, x_block, block, dist, device_tensor=None):
     to_t = device_tensor or (lambda a: a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a)))
     backend.prepass(x_block, block["n_frames"], block["in_off0"], block["warm"])
     # the running phase_sum travels down the ranks: receive, add this block's increments in frame order, pass on
+    # ... lane by lane (lanes are independent): while this rank adds lane c, the next one already works on lane c-1
     zero = backend.zero_carry()
-    carry = to_t(zero)
-    if rank > 0:
-        dist.recv(carry, rank - 1)
-    carry_out = backend.scan(carry if torch.is_tensor(zero) else carry.numpy())
-    if rank + 1 < world:
-        dist.send(to_t(carry_out), rank + 1)
+    is_t = torch.is_tensor(zero)
+    sends = []
+    for c in range(zero.shape[0]):
+        carry = to_t(zero[c:c + 1]).clone()
+        if rank > 0:
+            dist.recv(carry, rank - 1)
+        carry_out = backend.scan(carry if is_t else carry.numpy(), c, 1)
+        if rank + 1 < world:
+            sends.append(dist.isend(to_t(carry_out), rank + 1))
+    for r in sends:
+        r.wait()
     out, tail = backend.render()
     tail_t = to_t(tail)
     reqs = []
@@ -106,8 +112,8 @@ class GpuBackend:
     def zero_carry(self):
         return self.state["phase_sum"].clone().zero_()
 
-    def scan(self, carry):
-        return self.tp.scan(carry.contiguous())
+    def scan(self, carry, lane0=0, n_lanes=None):
+        return self.tp.scan(carry.contiguous(), lane0, n_lanes)
 
     def render(self):
         out = self.tp.render()
