@@ -871,7 +871,7 @@ TSB_API int tsb_timepar_render(tsb_timepar *tp) {
     if (tp->n_seg > 1)
         CU(op_add_tails(a.out, tp->plan->desc.precision == TSB_F64, a.out_stride, a.out_len, tp->d_pos + 1, tp->n_seg - 1,
                         tp->d_ola, (long long)tp->lanes, (long long)tp->n, c->stream));
-    c->launches += tp->n_seg > 1 ? 2 : 1;
+    if (tp->n_seg > 1) c->launches++;  // the tail fix-up (pre-pass, scan and chain count themselves)
     const size_t lastrow = rows - tp->lanes;
     if (a.state_last_phase) CU(cudaMemcpyAsync(a.state_last_phase, tp->d_last + lastrow * tp->m, tp->lanes * tp->m * 8, cudaMemcpyDeviceToDevice, c->stream));
     if (a.state_phase_sum) CU(cudaMemcpyAsync(a.state_phase_sum, tp->d_sum + lastrow * tp->m, tp->lanes * tp->m * 8, cudaMemcpyDeviceToDevice, c->stream));

@@ -20,7 +20,7 @@ struct Options {
     int streams = 1, precision = TSB_F64, device = 0;
     std::string mode = "fused", in_path, out_path;
     long long max_frames = -1;
-    bool timing = false, out_f64 = false;
+    bool timing = false, out_f64 = false, timepar = true;
 };
 inline Options parse_args(int argc, char **argv) {
     Options o;
@@ -38,11 +38,12 @@ inline Options parse_args(int argc, char **argv) {
         else if (a == "--in") o.in_path = next();
         else if (a == "--out") o.out_path = next();
         else if (a == "--out-f64") o.out_f64 = true;
+        else if (a == "--no-timepar") o.timepar = false;
         else if (a == "--max-frames") o.max_frames = atoll(next().c_str());
         else if (a == "--device") o.device = atoi(next().c_str());
         else if (a == "--timing") o.timing = true;
         else fatal("unknown argument " + a + "\nusage: ts_render [--seconds S] [--rate R] [--streams N] [--precision f32|f64] "
-                   "[--mode fused|immediate] [--in planar.f32] [--out planar.f32] [--out-f64] [--max-frames K] [--timing]");
+                   "[--mode fused|immediate] [--in planar.f32] [--out planar.f32] [--out-f64] [--no-timepar] [--max-frames K] [--timing]");
     }
     if (o.mode != "fused" && o.mode != "immediate") fatal("--mode must be fused or immediate");
     return o;
@@ -100,7 +101,7 @@ struct Renderer {
     std::vector<float> host_in;    // planar [lanes_in][in_len]
     std::vector<float> host_out;   // planar [lanes_out][out_cap]
     std::vector<double> host_out64;
-    long long frames = 0, launches0 = 0;
+    long long frames = 0, launches0 = 0, timepar_launches = 0;
     double wall = 0;
 
     explicit Renderer(const Options &o) : opt(o) {}
@@ -276,7 +277,22 @@ struct Renderer {
         a.state_ola = (double *)d_ola.d;
         a.load_state = 1;  // arrays were zeroed above when the state does not carry over
         a.lanes = (int32_t)lanes;
-        check(tsb_chain_render(rt.context(), plan, &a), "tsb_chain_render");
+        // A few lanes cannot fill the GPU frame after frame (a lane is one CTA walking its frames in order): cut the
+        // run into concurrent time segments instead.  PV state comes out bit-identical to the sequential launch, the
+        // samples differ by the order of the four overlap-add addends right after a segment start.
+        const int64_t frames_run = (int64_t)p.hops.size();
+        const size_t inc_bytes = lanes * (size_t)frames_run * (n / 2) * 8;
+        int32_t nseg = (int32_t)((148 * 4 + lanes - 1) / lanes);
+        if (nseg > frames_run / 16) nseg = (int32_t)(frames_run / 16);
+        // (not for the float32-stream mode: there the tail added after the fact would round differently from the
+        // reference's float tail, one float32 step in the samples right after a segment start)
+        if (opt.timepar && chain_precision() != TSB_F64_OUT32 && nseg >= 2 && inc_bytes <= ((size_t)4 << 30)) {
+            check(tsb_chain_render_timepar(rt.context(), plan, &a, constant ? nullptr : p.hops.data(), nseg),
+                  "tsb_chain_render_timepar");
+            timepar_launches++;
+        } else {
+            check(tsb_chain_render(rt.context(), plan, &a), "tsb_chain_render");
+        }
         rt.sync();  // p.hops is about to go away
         state_valid = true;
         state_pv = k.pv;
@@ -408,9 +424,10 @@ struct Renderer {
         }
         if (opt.timing)
             printf("{\"frames\": %lld, \"wall_s\": %.6f, \"streams\": %d, \"lanes\": %zu, \"out_samples_per_lane\": %lld, "
-                   "\"mode\": \"%s\", \"precision\": \"%s\", \"gpu_launches\": %lld}\n",
+                   "\"mode\": \"%s\", \"precision\": \"%s\", \"gpu_launches\": %lld, \"time_parallel_renders\": %lld}\n",
                    frames, wall, opt.streams, lanes_out, (long long)out_pos, opt.mode.c_str(),
-                   opt.precision == TSB_F32 ? "f32" : "f64", (long long)(tsb_launch_count(rt.ctx) - launches0));
+                   opt.precision == TSB_F32 ? "f32" : "f64", (long long)(tsb_launch_count(rt.ctx) - launches0),
+                   timepar_launches);
         for (auto &kv : plans) tsb_plan_destroy(kv.second);
         return 0;
     }
