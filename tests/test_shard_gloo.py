@@ -1,6 +1,6 @@
-"""The N>1 path on CPU: two gloo ranks run the time-sharded render orchestration (shard.py: halo, phase-carry
-all_gather, overlap-tail send/recv) over a CPU replay of the kernel, and the stitched result is checked against
-the oracle.  Also the stream split and block planning."""
+"""The N>1 path on CPU: two and three gloo ranks run the time-sharded render orchestration (shard.py: halo, the
+running phase_sum handed down the ranks, overlap-tail send/recv) over a CPU replay of the kernel, and the stitched
+result is checked against the oracle and the one-process render.  Also the stream split and block planning."""
 import os
 import socket
 import sys

@@ -1,6 +1,7 @@
 """tools/cfg3_timeshard.py — BASELINE cfg3 on N GPUs of one box: phase-vocoder pitch shift x1.5, frame 4096,
-hop 1024, 8 channels, ONE long render split by time segment across ranks (shard.py: input halo, phase-carry
-all_gather, overlap-tail send/recv over NCCL), every rank's block itself cut into concurrent time segments.
+hop 1024, 8 channels, ONE long render split by time segment across ranks (shard.py: input halo, the running
+phase_sum handed down the ranks, overlap-tail send/recv over NCCL), every rank's block itself cut into concurrent
+time segments.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
       tools/cfg3_timeshard.py --seconds 3600 [--precision f64] [--check-seconds 30]
