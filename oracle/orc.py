@@ -151,6 +151,27 @@ class PV:
     def shift(self, ratio):
         lib().orc_pv_shift_scale(self.h, ratio)
 
+    def shift_map(self, fn_bins, ratio):
+        """PhaseVocoder::shift (rtlib/pv.hpp:56-79) with fn given by its values on the bin centres (`fn_bins`,
+        size/2 of them, what decides the destination bin, :72) and fn(freq) = ratio*freq on the frequencies (:66) —
+        the two things a fused plan is built from.  Pure-Python scatter in the reference's order: ascending j,
+        amplitudes add, the frequency of the last writer wins, bins >= size/2 end up zero."""
+        nch, size = lib().orc_pv_nch(self.h), lib().orc_pv_size(self.h)
+        ptr = lib().orc_pv_data(self.h)
+        d = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(nch * size * 2,)).reshape(nch, size, 2)
+        rate, half = self._rate.value, size // 2
+        tmp = d.copy()
+        d[:] = 0.0
+        for i in range(nch):
+            for j in range(half):
+                q = fn_bins[j] / rate * size
+                if not (-2147483648.0 < q < 2147483648.0):
+                    continue
+                k = int(q)  # truncation toward zero, :72
+                if 0 <= k < half:
+                    d[i, k, 0] += tmp[i, j, 0]
+                    d[i, k, 1] = tmp[i, j, 1] * ratio
+
     def synthesize(self):
         nch, size = lib().orc_pv_nch(self.h), lib().orc_pv_size(self.h)
         out = np.empty((nch, size), np.float64)

@@ -464,3 +464,47 @@ def test_f64_out32_stream_and_timepar(env):
     tp = tp.cpu().numpy()
     assert tp.dtype == np.float32
     assert np.abs(tp.astype(np.float64) - whole).max() <= 4 * 2.0 ** -23 * np.abs(whole).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["reverse", "random", "sparse"])
+def test_pv_arbitrary_bin_map(env, kind):
+    """Bin maps a linear shift never produces (a permutation, random collisions and drops, a few survivors) through
+    the plan's used-source flags, destination order and multi-source gather, against a frame-by-frame composition of
+    the oracle's PhaseVocoder steps (oracle PV.shift_map = rtlib/pv.hpp:56-79 with fn given on the bin centres)."""
+    torch, tsb, orc = env["torch"], env["tsb"], env["orc"]
+    n, hop, ch = 1024, 256, 2
+    half, rate = n // 2, 48000.0
+    centre = np.arange(half) / n * rate
+    rng = np.random.default_rng(11)
+    if kind == "reverse":
+        fb, ratio = centre[::-1].copy() + 1.0, 1.0
+    elif kind == "random":
+        fb, ratio = rng.integers(-20, half + 40, half) / n * rate + 1.0, 1.3
+    else:
+        fb = np.full(half, 1e9)
+        keep = rng.choice(half, 30, replace=False)
+        fb[keep] = centre[rng.choice(half, 30, replace=False)] + 1.0
+        ratio = 0.8
+    x = orc.gen_signal(7, ch, 2048 + n + 30 * hop)
+    F = orc.n_frames(x.shape[0], n, hop)
+    pv = orc.PV(float(hop), rate)
+    want = np.zeros((ch, F * hop + n))
+    for f in range(F):
+        o = 2048 + f * hop
+        pv.analyze(np.ascontiguousarray(x[o:o + n].T, np.float64))
+        pv.shift_map(fb, ratio)
+        want[:, f * hop:f * hop + n] += pv.synthesize()
+    want = want[:, :F * hop]
+    xd = torch.from_numpy(np.ascontiguousarray(x.T)).cuda()
+    for precision in ("f64", "f32"):
+        plan = tsb.Plan(env["ctx"], n, precision=precision, program="pv", hop=hop, ratio=ratio, fn_bins=fb)
+        st = {k: torch.zeros((ch, w), dtype=torch.float64, device="cuda") for k, w in
+              (("last_phase", half), ("phase_sum", half), ("ola", n))}
+        out = plan.render(xd, F, hop, state=st).cpu().numpy()
+        if precision == "f64":
+            assert maxrel(out, want) <= F64_MAXREL
+            assert np.abs(st["phase_sum"].cpu().numpy() - pv.phase_sum[:, :half]).max() < 1e-8
+            assert np.abs(st["last_phase"].cpu().numpy() - pv.last_phase[:, :half]).max() < 1e-10
+        else:
+            assert rmsrel(out, want) <= F32_RMSREL

@@ -158,3 +158,45 @@ def test_fp64_pv_math_kernels():
     at, sq, _, _, _ = emul.pv_math(yy, xx)
     assert np.array_equal(at, np.arctan2(yy, xx)) and np.array_equal(np.signbit(at), np.signbit(np.arctan2(yy, xx)))
     assert sq[0] == 0.0
+
+
+def _oracle_render_with_map(x, n, hop, fn_bins, ratio, rate=48000.0):
+    """Frame by frame with the oracle's PhaseVocoder steps and an arbitrary bin map (what `fn_bins` + `ratio` of a
+    fused plan mean): tinyspec.cpp:135-200 schedule (constant integer hop), float64 overlap-add."""
+    L, ch = x.shape
+    F = orc.n_frames(L, n, hop)
+    pv = orc.PV(float(hop), rate)
+    out = np.zeros((ch, F * hop + n))
+    for f in range(F):
+        o = 2048 + f * hop
+        pv.analyze(np.ascontiguousarray(x[o:o + n].T, np.float64))
+        pv.shift_map(fn_bins, ratio)
+        out[:, f * hop:f * hop + n] += pv.synthesize()
+    return out[:, :F * hop], F, pv
+
+
+@pytest.mark.parametrize("kind", ["reverse", "random", "sparse"])
+def test_pv_chain_arbitrary_bin_map(kind):
+    """Bin maps a linear shift never produces — a permutation, random collisions and drops, a few survivors — through
+    the plan's used-source flags, destination order and multi-source gather."""
+    n, hop, ch = 256, 64, 1
+    half, rate = n // 2, 48000.0
+    centre = np.arange(half) / n * rate
+    rng = np.random.default_rng(11)
+    if kind == "reverse":
+        fb, ratio = centre[::-1].copy() + 1.0, 1.0
+    elif kind == "random":
+        fb, ratio = rng.integers(-20, half + 40, half) / n * rate + 1.0, 1.3
+    else:
+        fb = np.full(half, 1e9)
+        keep = rng.choice(half, 9, replace=False)
+        fb[keep] = centre[rng.choice(half, 9, replace=False)] + 1.0
+        ratio = 0.8
+    x = orc.gen_signal(7, ch, 2048 + n + 40 * hop)
+    want, F, pv = _oracle_render_with_map(x, n, hop, fb, ratio)
+    out, st = emul.chain_render(x.T, n, hop, F, precision="f64", ratio=ratio, fn_bins=fb)
+    assert maxrel(out, want) < 1e-11
+    assert np.abs(st["phase_sum"] - pv.phase_sum[:, :half]).max() < 1e-8
+    assert np.abs(st["last_phase"] - pv.last_phase[:, :half]).max() < 1e-11
+    out32, _ = emul.chain_render(x.T, n, hop, F, precision="f32", ratio=ratio, fn_bins=fb)
+    assert rmsrel(out32, want) < 1e-5
