@@ -919,11 +919,18 @@ struct Chain {
             int k = tid;
             if (HALF % T != 0 && k >= HALF) return;
             const bool sp = is_special(0, k);
-            if (!all && !(rg.used & 3u)) return;
+            const bool need_a = all || (rg.used & 1u), need_b = all || (rg.used & 2u);
+            if (!need_a && !need_b) return;
             C Xa, Xb;
             split_slot(0, k, Xa, Xb);
-            analyze_bin(k, Xa, rg.last_phase[0], sp);
-            analyze_bin(sp ? HALF : M - k, Xb, rg.last_phase[1], false);
+            if (need_a && need_b) {  // (one pair per thread: the two bins overlap only when both are wanted)
+                analyze_bin(k, Xa, rg.last_phase[0], sp);
+                analyze_bin(sp ? HALF : M - k, Xb, rg.last_phase[1], false);
+            } else if (need_a) {
+                analyze_bin(k, Xa, rg.last_phase[0], sp);
+            } else {
+                analyze_bin(sp ? HALF : M - k, Xb, rg.last_phase[1], false);
+            }
         } else {
 #pragma unroll
         for (int i = 0; i < S; i += 2) {
