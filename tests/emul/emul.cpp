@@ -91,7 +91,7 @@ extern "C" int emul_chain_render_ex(int precision, int log2n, int program, int w
                                     long long out_stride, long long out_len, long long n_frames, long long in_off0,
                                     long long out_off0, int hop, const int *hop_tab, double *st_last_phase,
                                     double *st_phase_sum, double *st_ola, int load_state, int lanes, int mode, int warm,
-                                    int warm_hop, double *st_warm_phase, double *st_inc) {
+                                    int warm_hop, double *st_warm_phase, double *st_inc, int lead) {
     PlanDesc d;
     d.n = 1 << log2n;
     d.program = program;
@@ -102,7 +102,7 @@ extern "C" int emul_chain_render_ex(int precision, int log2n, int program, int w
     d.ratio = ratio;
     d.fn_bins = fn_bins;
     d.gain = gain;
-    long long seg[6] = {0, n_frames, in_off0, out_off0, warm, warm_hop};
+    long long seg[SEG_COLS] = {0, n_frames, in_off0, out_off0, warm, warm_hop, lead, 0};
     ChainArgs a;
     a.in = in; a.in_stride = in_stride; a.in_len = in_len;
     a.out = out; a.out_stride = out_stride; a.out_len = out_len;
@@ -114,6 +114,9 @@ extern "C" int emul_chain_render_ex(int precision, int log2n, int program, int w
     a.st_inc = st_inc; a.inc_frames = n_frames;
     if (precision == 0)
         return program == PROG_PV_SHIFT ? by_size<float, PROG_PV_SHIFT>(log2n, d, a) : by_size<float, PROG_GAIN>(log2n, d, a);
+    if (precision == 2)
+        return program == PROG_PV_SHIFT ? by_size<double, PROG_PV_SHIFT, true>(log2n, d, a)
+                                        : by_size<double, PROG_GAIN, true>(log2n, d, a);
     return program == PROG_PV_SHIFT ? by_size<double, PROG_PV_SHIFT>(log2n, d, a) : by_size<double, PROG_GAIN>(log2n, d, a);
 }
 

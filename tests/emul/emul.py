@@ -24,7 +24,7 @@ def lib():
         _lib.emul_fft.argtypes = [C.c_int, C.c_int, P, P]
         _lib.emul_pv_math.argtypes = [C.c_longlong, P, P, P, P, P, P, P]
         _lib.emul_pv_math.restype = None
-        _lib.emul_chain_render_ex.argtypes = _lib.emul_chain_render.argtypes + [C.c_int, C.c_int, C.c_int, P, P]
+        _lib.emul_chain_render_ex.argtypes = _lib.emul_chain_render.argtypes + [C.c_int, C.c_int, C.c_int, P, P, C.c_int]
     return _lib
 
 
@@ -73,6 +73,23 @@ def chain_render(x, n, hop, n_frames, precision="f64", program="pv", ratio=2.0, 
     return out, state
 
 
+def segment_render(x, n, hop, ratio, in_off0, n_frames, lead, warm, mode, state, warm_phase, inc=None, precision="f64",
+                   out_len=None):
+    """One time segment as the kernel runs it (ChainArgs::seg_tab row): `n_frames` frames from input offset `in_off0`,
+    the first `lead` of them lead-in frames, optionally preceded by a warm-up frame; mode 1 = pre-pass."""
+    x = np.ascontiguousarray(x, np.float32)
+    lanes, L = x.shape
+    dt = np.float64 if precision == "f64" else np.float32
+    out_len = n_frames * hop if out_len is None else out_len
+    out = np.zeros((lanes, max(out_len, 1)), dt)
+    r = lib().emul_chain_render_ex({"f32": 0, "f64": 1, "f64o32": 2}[precision], int(np.log2(n)), 0, 2, 2, float(hop), 48000.0,
+                                   ratio, None, None, _p(x), L, L, _p(out), out.shape[1], out_len, n_frames, in_off0, 0,
+                                   int(hop), None, _p(state["last_phase"]), _p(state["phase_sum"]), _p(state["ola"]), 1,
+                                   lanes, mode, int(warm), int(hop), _p(warm_phase), _p(inc), int(lead))
+    assert r == 0
+    return out
+
+
 class ReplayBackend:
     """CPU stand-in for the device side of tinyspec-cling_b200/shard.py (kernel phases replayed thread by thread),
     so the multi-rank orchestration can be tested with gloo in a container without a GPU."""
@@ -88,7 +105,7 @@ class ReplayBackend:
                                        self.rate, self.ratio, None, None, _p(x), L, L, _p(out), out.shape[1], out_len,
                                        n_frames, in_off0, 0, int(self.hop), None, _p(state["last_phase"]),
                                        _p(state["phase_sum"]), _p(state["ola"]), int(load), lanes, mode, int(warm),
-                                       int(self.hop), _p(warm_phase), _p(inc))
+                                       int(self.hop), _p(warm_phase), _p(inc), 0)
         assert r == 0
         return out
 

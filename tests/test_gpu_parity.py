@@ -260,10 +260,10 @@ def test_errors_are_loud(env):
 @pytest.mark.parametrize("n,hr,shift,ch,samples,nseg", [(1024, 0.25, 2.0, 2, 96000, 37), (1024, 0.25, 1.5, 1, 480000, 444),
                                                         (4096, 0.25, 1.5, 8, 120000, 5), (512, 0.2003, 0.75, 1, 40000, 16)])
 def test_timepar_matches_sequential_and_oracle(env, precision, n, hr, shift, ch, samples, nseg):
-    """Segments of one stream rendered concurrently (pre-pass, scan, main, tail fix-up) give the sequential
-    render: the scan adds the stored increments frame by frame like the sequential render does, so the PV state is
-    bit-identical (both precisions) and the samples differ only where a segment's overlap tail was added
-    afterwards (the same addends in another order)."""
+    """Segments of one stream rendered concurrently give the sequential render bit for bit — samples, PV state and
+    overlap tail, both precisions: the scan adds the stored increments frame by frame like the sequential render
+    does, and every segment replays silently the frames whose output overlaps its first one, which rebuilds the
+    tail it starts with."""
     torch, tsb, orc = env["torch"], env["tsb"], env["orc"]
     x = orc.gen_signal(1, ch, samples)
     sch = tsb.schedule_const(samples, n, n * hr)
@@ -282,10 +282,8 @@ def test_timepar_matches_sequential_and_oracle(env, precision, n, hr, shift, ch,
     peak = np.abs(seq).max()
     assert torch.equal(s_par["phase_sum"], s_seq["phase_sum"])
     assert torch.equal(s_par["last_phase"], s_seq["last_phase"])
-    eps = np.finfo(par.dtype).eps
-    assert np.abs(par.astype(np.float64) - seq).max() <= 4 * eps * peak
-    assert (par == seq).mean() > 1 - 1.01 * nseg * n / seq.shape[1]
-    assert np.abs(s_par["ola"].cpu().numpy() - s_seq["ola"].cpu().numpy()).max() <= 4 * eps * peak
+    assert np.array_equal(par, seq)
+    assert torch.equal(s_par["ola"], s_seq["ola"])
     if precision == "f64" and samples <= 120000:
         ref = orc.render_pv(x, n, hr, shift)
         assert maxrel(par, ref["ola64"][:par.shape[1]].T) <= F64_MAXREL
@@ -330,7 +328,7 @@ def test_timepar_two_blocks_like_two_gpus(env):
     assert torch.equal(end, st["phase_sum"]) and torch.equal(st1["phase_sum"], st["phase_sum"])
     d = np.abs(out.cpu().numpy() - whole.cpu().numpy())
     assert d.max() <= 4 * np.finfo(np.float64).eps * float(whole.abs().max())
-    assert (d == 0).mean() > 1 - 1.01 * 48 * n / whole.shape[1]
+    assert (d == 0).mean() > 1 - 1.01 * n / whole.shape[1]   # only block 0's tail is added afterwards
 
 
 @pytest.mark.parametrize("n,hr,precision", [(1024, 0.25, "f64"), (512, 0.2003, "f32"), (64, 1.6, "f64")])
@@ -359,8 +357,8 @@ def test_streaming_front_end_bit_identical(env, n, hr, precision):
 
 
 def test_timepar_gain_program(env):
-    """Without a phase vocoder only the overlap tail crosses segments: the time-parallel render of the spectral-gain
-    chain differs from the sequential one by the regrouping of at most four additions per sample."""
+    """Without a phase vocoder only the overlap tail crosses segments, and the lead-in frames rebuild it: the
+    time-parallel render of the spectral-gain chain is the sequential one bit for bit."""
     torch, tsb, orc = env["torch"], env["tsb"], env["orc"]
     n, hop = 2048, 512
     x = orc.gen_signal(0, 2, 150000)
@@ -371,7 +369,7 @@ def test_timepar_gain_program(env):
     seq = plan.render(xd, sch["n_frames"], hop).clone()
     par = plan.render_timepar(xd, sch["n_frames"], hop, 40)
     torch.cuda.synchronize()
-    assert float((par - seq).abs().max()) <= 1e-15 * float(seq.abs().max()) * 4
+    assert torch.equal(par, seq)
     ref = orc.render_filter(x, n, 0.25, gain)
     assert maxrel(par.cpu().numpy(), ref["ola64"][:par.shape[1]].T) <= 1e-12
 
@@ -456,14 +454,14 @@ def test_f64_out32_stream_and_timepar(env):
     parts = [st.process(np.ascontiguousarray(x[p:p + 5000].T)) for p in range(0, samples, 5000)]
     got = np.concatenate(parts, axis=1)
     assert got.dtype == np.float32 and np.array_equal(got, whole)
-    # time-parallel: the tails of earlier segments are added afterwards (regrouped float32 additions)
+    # time-parallel: every segment rebuilds its float32 overlap tail from its lead-in frames: the same samples
     xd = torch.from_numpy(np.ascontiguousarray(x.T)).cuda()
     sch = tsb.schedule_const(samples, n, n * hr)
     tp = plan.render_timepar(xd, F, int(sch["hop"][0]), in_off0=int(sch["in_off"][0]), n_segments=16)
     torch.cuda.synchronize()
     tp = tp.cpu().numpy()
     assert tp.dtype == np.float32
-    assert np.abs(tp.astype(np.float64) - whole).max() <= 4 * 2.0 ** -23 * np.abs(whole).max()
+    assert np.array_equal(tp, whole)
 
 
 @pytest.mark.gpu

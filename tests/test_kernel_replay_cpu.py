@@ -200,3 +200,39 @@ def test_pv_chain_arbitrary_bin_map(kind):
     assert np.abs(st["last_phase"] - pv.last_phase[:, :half]).max() < 1e-11
     out32, _ = emul.chain_render(x.T, n, hop, F, precision="f32", ratio=ratio, fn_bins=fb)
     assert rmsrel(out32, want) < 1e-5
+
+
+@pytest.mark.parametrize("precision", ["f64", "f64o32", "f32"])
+def test_time_segment_with_lead_in_frames_is_the_sequential_render(precision):
+    """A time segment that replays, silently, the frames whose output overlaps its first frame starts with the very
+    overlap tail (and, through the pre-pass and the frame-by-frame scan, the very phase state) the sequential
+    render has there: its samples are bit-identical, float32 tail arithmetic included."""
+    n, hop, ratio, ch = 256, 64, 1.5, 2
+    x = orc.gen_signal(3, ch, 2048 + n + 47 * hop).T
+    F = orc.n_frames(x.shape[1], n, hop)
+    seq, st_seq = emul.chain_render(x, n, hop, F, precision=precision, ratio=ratio)
+    first, lead = 20, n // hop - 1              # segment 1 emits frames [20, F); frames 17..19 are its lead-in
+    m = n // 2
+    zeros = lambda: dict(last_phase=np.zeros((ch, m)), phase_sum=np.zeros((ch, m)), ola=np.zeros((ch, n)))
+    f0 = first - lead
+    # pre-pass of both segments: per-frame increments (segment 1: warm-up frame 16, lead-in 17..19 analysed only)
+    wp0, wp1 = np.zeros((ch, m)), np.zeros((ch, m))
+    inc0 = np.zeros((ch, first, m))              # segment 0's own frames 0..19 (contiguous [lanes][frames][bins] blocks)
+    emul.segment_render(x, n, hop, ratio, 2048, first, 0, False, 1, zeros(), wp0, inc0, precision)
+    inc1 = np.zeros((ch, F - f0, m))
+    emul.segment_render(x, n, hop, ratio, 2048 + f0 * hop, F - f0, lead, True, 1, zeros(), wp1, inc1, precision)
+    assert np.all(inc1[:, :lead] == 0)           # lead-in increments are not stored again
+    inc = np.concatenate([inc0, inc1[:, lead:]], axis=1)
+    # scan: the sequential additions, noted where segment 1 starts processing
+    ps = np.zeros((ch, m))
+    for f in range(f0):
+        ps = ps + inc[:, f]
+    # main pass of segment 1 from (last_phase after frame 16, phase_sum before frame 17, empty tail)
+    st1 = zeros()
+    st1["phase_sum"][:] = ps
+    out1 = emul.segment_render(x, n, hop, ratio, 2048 + f0 * hop, F - f0, lead, True, 0, st1, wp1, None, precision,
+                               out_len=(F - f0) * hop)
+    assert np.all(out1[:, :lead * hop] == 0)     # nothing is emitted for the lead-in frames
+    assert np.array_equal(out1[:, lead * hop:], seq[:, first * hop:])
+    for k in ("last_phase", "phase_sum", "ola"):
+        assert np.array_equal(st1[k], st_seq[k])

@@ -654,7 +654,7 @@ struct tsb_timepar {
     tsb_chain_args args;
     int n_seg, warmup, warm_hop;
     size_t lanes, n, m;
-    std::vector<long long> seg;  // [n_seg][6]
+    std::vector<long long> seg;  // [n_seg][SEG_COLS]
     long long *d_seg = nullptr, *d_pos = nullptr;
     double *d_last = nullptr, *d_sum = nullptr, *d_warm = nullptr, *d_ola = nullptr;
     double *d_inc = nullptr;  // [lanes][n_frames][m] per-frame increments of every destination bin (pre-pass)
@@ -706,24 +706,38 @@ TSB_API int tsb_timepar_create(tsb_ctx *c, tsb_plan *p, const tsb_chain_args *a,
     if (F > 0 && nseg > F / min_frames) nseg = F / min_frames;
     if (nseg < 1) nseg = 1;
     tp->n_seg = (int)nseg;
-    tp->seg.assign(6 * nseg, 0);
+    tp->seg.assign((size_t)SEG_COLS * nseg, 0);
     std::vector<long long> pos(nseg, 0);
-    int64_t in_off = a->in_off0, out_off = a->out_off0, f = 0;
+    auto hop_of = [&](int64_t fr) { return (int64_t)(host_hop_tab ? host_hop_tab[fr] : a->hop); };
+    // offsets of every frame of the block (and one past the end)
+    std::vector<int64_t> in_at((size_t)F + 1), out_at((size_t)F + 1);
+    in_at[0] = a->in_off0;
+    out_at[0] = a->out_off0;
+    for (int64_t fr = 0; fr < F; fr++) {
+        in_at[fr + 1] = in_at[fr] + hop_of(fr);
+        out_at[fr + 1] = out_at[fr] + hop_of(fr);
+    }
+    int64_t f = 0;
     for (int64_t s = 0; s < nseg; s++) {
         int64_t cnt = F / nseg + (s < F % nseg ? 1 : 0);
-        long long *t = &tp->seg[6 * s];
-        t[0] = f;
-        t[1] = cnt;
-        t[2] = in_off;
-        t[3] = out_off;
-        t[4] = s == 0 ? (warmup ? 1 : 0) : 1;
-        t[5] = s == 0 ? warm_hop : (host_hop_tab ? host_hop_tab[f - 1] : a->hop);
-        pos[s] = out_off;
-        for (int64_t i = 0; i < cnt; i++) {
-            int64_t h = host_hop_tab ? host_hop_tab[f + i] : a->hop;
-            in_off += h;
-            out_off += h;
-        }
+        // lead-in: the earlier frames whose output reaches into this segment's first frame (N/hop - 1 of them for a
+        // constant hop).  The segment replays them silently, so it starts with the overlap tail the sequential
+        // render has there; segment 0 of the block has none (it starts the render, or takes its tail from the
+        // block before: tsb_add_tail)
+        int64_t lead = 0;
+        while (s > 0 && lead < f && out_at[f - lead - 1] + (int64_t)tp->n > out_at[f]) lead++;
+        if (lead > f - 1) lead = f > 0 ? f - 1 : 0;  // keep one frame before it for the warm-up analysis (segments hold
+                                                    // at least n/hop_min frames, so this never bites)
+        const int64_t f0 = f - lead;
+        long long *t = &tp->seg[(size_t)SEG_COLS * s];
+        t[0] = f0;
+        t[1] = cnt + lead;
+        t[2] = in_at[f0];
+        t[3] = out_at[f0];
+        t[4] = f0 == 0 ? (warmup ? 1 : 0) : 1;
+        t[5] = f0 == 0 ? warm_hop : hop_of(f0 - 1);
+        t[6] = lead;
+        pos[s] = out_at[f];
         f += cnt;
     }
     size_t rows = (size_t)nseg * tp->lanes;
@@ -868,10 +882,7 @@ TSB_API int tsb_timepar_render(tsb_timepar *tp) {
     CU(cudaMemsetAsync(tp->d_ola, 0, rows * tp->n * 8, c->stream));
     if ((r = seed_rows(tp, tp->d_ola, a.state_ola, tp->n))) return r;
     if ((r = timepar_launch(tp, 0))) return r;
-    if (tp->n_seg > 1)
-        CU(op_add_tails(a.out, tp->plan->desc.precision == TSB_F64, a.out_stride, a.out_len, tp->d_pos + 1, tp->n_seg - 1,
-                        tp->d_ola, (long long)tp->lanes, (long long)tp->n, c->stream));
-    if (tp->n_seg > 1) c->launches++;  // the tail fix-up (pre-pass, scan and chain count themselves)
+    // (no tail fix-up between the segments: each one rebuilt the tail it starts with from its lead-in frames)
     const size_t lastrow = rows - tp->lanes;
     if (a.state_last_phase) CU(cudaMemcpyAsync(a.state_last_phase, tp->d_last + lastrow * tp->m, tp->lanes * tp->m * 8, cudaMemcpyDeviceToDevice, c->stream));
     if (a.state_phase_sum) CU(cudaMemcpyAsync(a.state_phase_sum, tp->d_sum + lastrow * tp->m, tp->lanes * tp->m * 8, cudaMemcpyDeviceToDevice, c->stream));

@@ -138,17 +138,22 @@ struct ChainArgs {
     // P of the first frame, warm-up}: with warm-up the CTA first analyses the frame BEFORE the segment
     // (input offset I - prev_hop) only to obtain last_phase.
     int n_seg;                 // 0 or 1: the whole launch is one segment described by the fields above
-    const long long *seg_tab;  // [n_seg][6]: first_frame, n_frames, in_off0, out_off0, warm-up flag, hop of the frame before
+    const long long *seg_tab;  // [n_seg][SEG_COLS]: first_frame, n_frames, in_off0, out_off0, warm-up flag, hop of the frame
+                               // before, lead-in frames (see SegInfo)
     int mode;                  // 0: full chain; 1: pre-pass (analysis + shift + increment accumulation only, no output)
     double *st_warm_phase;     // pre-pass out / main in: [rows][M] last_phase after the warm-up frame (segments with warm-up)
     double *st_inc;            // pre-pass out (or nullptr): [lanes][inc_frames][M] the increment every frame adds to the
     long long inc_frames;      //   phase_sum of every destination bin, frames numbered as in hop_tab / seg_tab
 };
 
-// What one CTA works on.
+// What one CTA works on.  A segment that does not start the render begins with the frames whose output overlaps
+// its first own frame (`lead` of them, N/hop - 1 for a constant hop): the pre-pass only analyses them (their
+// increments belong to the previous segment), the main pass renders them without emitting anything — that
+// rebuilds, with the sequential render's own arithmetic, the overlap tail the segment starts with.
 struct SegInfo {
-    long long first_frame, n_frames, in_off0, out_off0;
+    long long first_frame, n_frames, in_off0, out_off0;  // first processed frame (a lead-in frame if lead > 0), count incl. lead
     int warm, warm_hop;
+    int lead;
     long long row;  // state row = segment * lanes + lane
 };
 
@@ -1056,7 +1061,7 @@ struct Chain {
     // positions are complete (tinyspec.cpp:173-182) and leave the chip, the rest is the tail (194-200).
     template <int P, int NT = T>
     static TSB_HD void inv_pass(int tid, int lane, Smem &sm, const Tables &tb, const ChainArgs &a, long long out_pos,
-                                int hop) {
+                                int hop, bool emit) {
         const C *src = inv_buffer(sm, P);
         auto in = [&](int x, int c) { return ld_sw(src, x, c); };
         if (P < PASSES - 1) {
@@ -1069,7 +1074,8 @@ struct Chain {
             const int ob = (int)(out_pos & (N - 1));
             // samples of this frame that may be written: n < lim (everything when the row has room)
             const long long room = a.out_len - out_pos;
-            const int lim = room >= (long long)N + hop ? 0x7fffffff : (room < 0 ? 0 : (int)room);
+            // (a lead-in frame of a time segment writes nothing: it only rebuilds the overlap tail)
+            const int lim = !emit ? 0 : (room >= (long long)N + hop ? 0x7fffffff : (room < 0 ? 0 : (int)room));
             // one output sample: `done` positions leave the chip, the others stay in the tail.  OUT32 follows the
             // reference's types: the finished sample is the float of (float tail + double value) (:180), the tail
             // accumulates the value narrowed first, in float (:195-197).
@@ -1146,18 +1152,19 @@ template <class CH, int P, int END>
 struct InvPasses {
     template <class Exec>
     static TSB_HD void run(Exec &ex, int lane, typename CH::Smem &sm, const typename CH::Tables &tb, const ChainArgs &a,
-                           long long out_pos, int hop) {
+                           long long out_pos, int hop, bool emit) {
         ex.each([&](int tid, typename CH::Regs &) {
-            CH::template inv_pass<P>(tid, lane, sm, tb, a, out_pos, hop);
+            CH::template inv_pass<P>(tid, lane, sm, tb, a, out_pos, hop, emit);
             if (P == END - 1) CH::ring_wait();
         });
-        InvPasses<CH, P + 1, END>::run(ex, lane, sm, tb, a, out_pos, hop);
+        InvPasses<CH, P + 1, END>::run(ex, lane, sm, tb, a, out_pos, hop, emit);
     }
 };
 template <class CH, int END>
 struct InvPasses<CH, END, END> {
     template <class Exec>
-    static TSB_HD void run(Exec &, int, typename CH::Smem &, const typename CH::Tables &, const ChainArgs &, long long, int) {}
+    static TSB_HD void run(Exec &, int, typename CH::Smem &, const typename CH::Tables &, const ChainArgs &, long long, int,
+                           bool) {}
 };
 
 // Software-pipelined pass pairs (CH::PIPE): in one barrier interval the first T0 threads run forward pass P of
@@ -1168,7 +1175,7 @@ struct PipePasses {
     template <class Exec>
     static TSB_HD void run(Exec &ex, int lane, typename CH::Smem &sm, const typename CH::Tables &tb, const ChainArgs &a,
                            bool have_next, long long next_in_off, long long fetch_first, int fetch_cnt, bool have_cur,
-                           long long out_pos, int hop) {
+                           long long out_pos, int hop, bool emit) {
         ex.each([&](int tid, typename CH::Regs &) {
             if (tid < CH::T0) {
                 if (have_next) {
@@ -1181,18 +1188,18 @@ struct PipePasses {
                     if (P == END - 1 && fetch_cnt > 0) CH::template ring_fill<CH::T0>(tid, lane, sm, a, fetch_first, fetch_cnt);
                 }
             } else if (have_cur) {
-                CH::template inv_pass<P, CH::T0>(tid - CH::T0, lane, sm, tb, a, out_pos, hop);
+                CH::template inv_pass<P, CH::T0>(tid - CH::T0, lane, sm, tb, a, out_pos, hop, emit);
             }
         });
         PipePasses<CH, P + 1, END>::run(ex, lane, sm, tb, a, have_next, next_in_off, fetch_first, fetch_cnt, have_cur,
-                                        out_pos, hop);
+                                        out_pos, hop, emit);
     }
 };
 template <class CH, int END>
 struct PipePasses<CH, END, END> {
     template <class Exec>
     static TSB_HD void run(Exec &, int, typename CH::Smem &, const typename CH::Tables &, const ChainArgs &, bool, long long,
-                           long long, int, bool, long long, int) {}
+                           long long, int, bool, long long, int, bool) {}
 };
 
 // The whole launch for one (segment, lane).  `Exec::each(f)` runs f(tid, regs) for every thread of the lane and
@@ -1202,13 +1209,14 @@ template <class CH>
 TSB_HD SegInfo seg_info(const ChainArgs &a, int lane, int seg) {
     SegInfo sg;
     if (a.seg_tab) {
-        const long long *t = a.seg_tab + 6 * (long long)seg;
+        const long long *t = a.seg_tab + SEG_COLS * (long long)seg;
         sg.first_frame = TSB_LDG(&t[0]);
         sg.n_frames = TSB_LDG(&t[1]);
         sg.in_off0 = TSB_LDG(&t[2]);
         sg.out_off0 = TSB_LDG(&t[3]);
         sg.warm = (int)TSB_LDG(&t[4]);
         sg.warm_hop = (int)TSB_LDG(&t[5]);
+        sg.lead = (int)TSB_LDG(&t[6]);
     } else {
         sg.first_frame = 0;
         sg.n_frames = a.n_frames;
@@ -1216,6 +1224,7 @@ TSB_HD SegInfo seg_info(const ChainArgs &a, int lane, int seg) {
         sg.out_off0 = a.out_off0;
         sg.warm = 0;
         sg.warm_hop = 0;
+        sg.lead = 0;
     }
     sg.row = (long long)seg * a.lanes + lane;
     return sg;
@@ -1234,9 +1243,11 @@ TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const t
     bool prepass, warm;
     int warm_hop;
     long long first_frame;
+    int lead;
     {
         SegInfo sg = seg_info<CH>(a, lane, seg);
         first_frame = sg.first_frame;
+        lead = sg.lead;
         prepass = CH::IS_PV && a.mode == 1;
         warm = prepass && sg.warm;
         warm_hop = sg.warm_hop;
@@ -1258,7 +1269,8 @@ TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const t
         if (total > 0) {
             int hop0 = hop_of(0);
             int cnt = total > 1 ? (hop0 < N ? hop0 : N) : 0;
-            PipePasses<CH, 0, CH::PASSES>::run(ex, lane, sm, tb, a, true, in_off, in_off + hop0 + N - cnt, cnt, false, out_pos, 0);
+            PipePasses<CH, 0, CH::PASSES>::run(ex, lane, sm, tb, a, true, in_off, in_off + hop0 + N - cnt, cnt, false, out_pos, 0,
+                                               false);
         }
         for (int ff = 0; ff < total; ff++) {
             const int hop = hop_of(ff);
@@ -1284,7 +1296,7 @@ TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const t
                 cnt = hop1 < N ? hop1 : N;
                 first = next_in + hop1 + N - cnt;
             }
-            PipePasses<CH, 0, CH::PASSES>::run(ex, lane, sm, tb, a, have_next, next_in, first, cnt, true, out_pos, hop);
+            PipePasses<CH, 0, CH::PASSES>::run(ex, lane, sm, tb, a, have_next, next_in, first, cnt, true, out_pos, hop, ff >= lead);
             in_off = next_in;
             out_pos += hop;
         }
@@ -1305,7 +1317,7 @@ TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const t
                         const long long row = (long long)seg * a.lanes + lane;
                         ex.each([&](int tid, Regs &rg) { CH::regs_to(tid, a.st_warm_phase, row, rg.last_phase); });
                     }
-                } else {
+                } else if (ff - (warm ? 1 : 0) >= lead) {  // (lead-in frames: their increments are the previous segment's)
                     double *inc_row = a.st_inc ? a.st_inc + ((long long)lane * a.inc_frames + first_frame + ff - (warm ? 1 : 0)) * CH::M
                                                : nullptr;
                     ex.each([&](int tid, Regs &rg) { CH::phase_pv_accumulate(tid, sm, rg, tb, inc_row); });
@@ -1318,7 +1330,7 @@ TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const t
         } else {
             ex.each([&](int tid, Regs &) { CH::phase_gain(tid, sm, tb); });
         }
-        InvPasses<CH, 0, CH::PASSES>::run(ex, lane, sm, tb, a, out_pos, hop);
+        InvPasses<CH, 0, CH::PASSES>::run(ex, lane, sm, tb, a, out_pos, hop, ff >= lead);
         in_off += hop;
         out_pos += hop;
     }

@@ -18,6 +18,10 @@
 
 namespace tsb {
 
+// columns of a time-segment row (ChainArgs::seg_tab, see SegInfo in tsb_chain.cuh)
+constexpr int SEG_COLS = 8;
+
+
 template <typename T>
 struct alignas(2 * sizeof(T)) cpx {
     T x, y;

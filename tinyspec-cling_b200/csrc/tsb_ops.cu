@@ -566,7 +566,7 @@ timepar_scan_kernel(const double *inc, long long inc_frames, const long long *se
     const bool bin_ok = bin0 + b < m;
     const double *src = inc + lane * inc_frames * m + bin0 + b;
     // frames covered: the segments are consecutive, [first_0, first_last + cnt_last)
-    const long long f_begin = seg_tab[0], f_end = seg_tab[6 * (n_seg - 1)] + seg_tab[6 * (n_seg - 1) + 1];
+    const long long f_begin = seg_tab[0], f_end = seg_tab[SEG_COLS * (n_seg - 1)] + seg_tab[SEG_COLS * (n_seg - 1) + 1];
     auto fetch = [&](int buf, long long f0) {
         for (int r = r0; r < SCAN_TILE; r += SCAN_THREADS / SCAN_BINS) {
             const long long f = f0 + r;
@@ -594,7 +594,7 @@ timepar_scan_kernel(const double *inc, long long inc_frames, const long long *se
                 if (f0 + r == next_start) {  // a segment starts here: it starts from the sum so far
                     if (sum_rows) sum_rows[(long long)s * lanes * m + idx] = c;
                     s++;
-                    next_start = s < n_seg ? seg_tab[6 * s] : -1;
+                    next_start = s < n_seg ? seg_tab[SEG_COLS * s] : -1;
                 }
                 // up to the next segment start (or the end of the tile) nothing but the additions: the loads do
                 // not depend on the sum, so the compiler batches them ahead of the dependent chain

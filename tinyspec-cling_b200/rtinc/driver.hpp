@@ -278,15 +278,12 @@ struct Renderer {
         a.load_state = 1;  // arrays were zeroed above when the state does not carry over
         a.lanes = (int32_t)lanes;
         // A few lanes cannot fill the GPU frame after frame (a lane is one CTA walking its frames in order): cut the
-        // run into concurrent time segments instead.  PV state comes out bit-identical to the sequential launch, the
-        // samples differ by the order of the four overlap-add addends right after a segment start.
+        // run into concurrent time segments instead — samples and PV state bit-identical to the sequential launch.
         const int64_t frames_run = (int64_t)p.hops.size();
         const size_t inc_bytes = lanes * (size_t)frames_run * (n / 2) * 8;
         int32_t nseg = (int32_t)((148 * 4 + lanes - 1) / lanes);
         if (nseg > frames_run / 16) nseg = (int32_t)(frames_run / 16);
-        // (not for the float32-stream mode: there the tail added after the fact would round differently from the
-        // reference's float tail, one float32 step in the samples right after a segment start)
-        if (opt.timepar && chain_precision() != TSB_F64_OUT32 && nseg >= 2 && inc_bytes <= ((size_t)4 << 30)) {
+        if (opt.timepar && nseg >= 2 && inc_bytes <= ((size_t)4 << 30)) {
             check(tsb_chain_render_timepar(rt.context(), plan, &a, constant ? nullptr : p.hops.data(), nseg),
                   "tsb_chain_render_timepar");
             timepar_launches++;
