@@ -351,7 +351,7 @@ def main():
             torch.cuda.synchronize()
             line["single_stream"] = {"value": F / (e0.elapsed_time(e1) / 3 * 1e-3), "unit": "frames/s",
                                      "note": f"BASELINE configs[0] as is: ONE stereo 60 s stream (2 lanes), rendered as {nseg} "
-                                             "concurrent time segments (tsb_chain_render_timepar: pre-pass + scan + main + tail fix-up)"}
+                                             "concurrent time segments (tsb_chain_render_timepar: pre-pass + scan + main; bit-identical to the sequential render)"}
     # ---- CPU baseline: rank 0, N=1 only, bounded sample ----
     if rank == 0 and world == 1:
         frames, wall, kind, what, used = run_reference(1, min(args.seconds, 60.0))

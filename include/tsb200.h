@@ -141,15 +141,19 @@ int tsb_chain_render_host(tsb_ctx *ctx, tsb_plan *plan, const tsb_chain_args *ar
  *   scan      per bin, the stored increments are added one frame at a time in frame order, from the carry-in:
  *             exactly the additions of the sequential render, so every segment starts from the very phase_sum the
  *             sequential render has there (summing per-segment totals first would regroup them and drift);
- *   main      the full chain per segment from that state, each segment starting with an empty overlap tail;
- *   fix-up    segment s-1's overlap tail is added onto the head of segment s's output, in a fixed order.
- * phase_sum / last_phase are bit-identical to tsb_chain_render's at every frame; the samples differ only where a
- * tail was added afterwards (the same four addends in another order, ~1 ulp of the sample).
+ *   main      the full chain per segment from that state.  A segment first replays, without emitting anything, the
+ *             frames whose output overlaps its first own frame (n/hop - 1 of them for a constant hop; the pre-pass
+ *             and the scan are shifted by as many frames): that rebuilds the overlap tail it starts with, with the
+ *             sequential render's own arithmetic.
+ * Samples, phase_sum / last_phase and the final overlap tail are bit-identical to tsb_chain_render's, in every
+ * precision (the float32 tail arithmetic of TSB_F64_OUT32 included).  Cost: the lead-in frames are rendered twice.
  * This is what lets ONE long stream fill a GPU, and what a multi-GPU time split is built from: rank g renders a
  * block of frames (its input must start one warm-up frame earlier: `warmup` = 1 and args->in_off0 - warm_hop >= 0),
  * pre-passes it, takes the running phase_sum from rank g-1 (tsb_timepar_scan: carry in, carry out — a chain of
  * short steps over the ranks), renders, and hands its final overlap tail (state_ola) to rank g+1, which adds it at
- * the head of its output with tsb_add_tail.  Scratch: lanes * n_frames * n/2 doubles for the stored increments. */
+ * the head of its output with tsb_add_tail (the first segment of a block has no lead-in frames: across blocks the
+ * samples after the boundary meet their addends in another order, ~1 ulp).  Scratch: lanes * n_frames * n/2 doubles
+ * for the stored increments. */
 typedef struct tsb_timepar tsb_timepar;
 /* args is copied (device pointers must stay valid); host_hop_tab = host copy of args->hop_tab (NULL iff hop_tab is NULL) */
 int tsb_timepar_create(tsb_ctx *ctx, tsb_plan *plan, const tsb_chain_args *args, const int32_t *host_hop_tab,

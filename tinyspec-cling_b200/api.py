@@ -343,9 +343,8 @@ class Plan:
 
     def render_timepar(self, x, n_frames, hop, n_segments, out=None, in_off0=2048, out_off0=0, hop_tab=None,
                        state=None, load_state=False, out_len=None):
-        """Same PV state as render() bit for bit, samples equal except the order of the overlap-add addends right after
-        a segment start, with the frames of every lane cut into
-        `n_segments` concurrent time segments (tsb_chain_render_timepar)."""
+        """render() bit for bit (samples and PV state), with the frames of every lane cut into `n_segments`
+        concurrent time segments (tsb_chain_render_timepar)."""
         a, out, ht, ht_host = self._device_args(x, n_frames, hop, out, in_off0, out_off0, hop_tab, state, load_state,
                                                 out_len)
         _check(_load().tsb_chain_render_timepar(self.ctx.h, self.h, C.byref(a),
