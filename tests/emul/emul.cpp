@@ -31,7 +31,8 @@ static int run(const PlanDesc &d, const ChainArgs &a) {
     for (int lane = 0; lane < a.lanes; lane++) {
         std::memset(sm.get(), 0, sizeof(typename CH::Smem));
         HostExec<CH> ex;
-        run_lane<CH>(ex, lane, 0, *sm, tb, a);
+        if (a.mode == 1) run_lane<CH, true>(ex, lane, 0, *sm, tb, a);
+        else run_lane<CH, false>(ex, lane, 0, *sm, tb, a);
     }
     return 0;
 }

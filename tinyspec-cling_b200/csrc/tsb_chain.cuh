@@ -1059,9 +1059,9 @@ struct Chain {
     // The last pass hands its outputs F[m] straight to the synthesis window and the overlap-add:
     // x[2m] = Re F[m], x[2m+1] = -Im F[m]; out = x*ws; accumulate into the ring; the first `hop`
     // positions are complete (tinyspec.cpp:173-182) and leave the chip, the rest is the tail (194-200).
-    template <int P, int NT = T>
+    template <int P, int NT = T, bool EMIT = true>
     static TSB_HD void inv_pass(int tid, int lane, Smem &sm, const Tables &tb, const ChainArgs &a, long long out_pos,
-                                int hop, bool emit) {
+                                int hop) {
         const C *src = inv_buffer(sm, P);
         auto in = [&](int x, int c) { return ld_sw(src, x, c); };
         if (P < PASSES - 1) {
@@ -1075,7 +1075,7 @@ struct Chain {
             // samples of this frame that may be written: n < lim (everything when the row has room)
             const long long room = a.out_len - out_pos;
             // (a lead-in frame of a time segment writes nothing: it only rebuilds the overlap tail)
-            const int lim = !emit ? 0 : (room >= (long long)N + hop ? 0x7fffffff : (room < 0 ? 0 : (int)room));
+            const int lim = !EMIT ? 0 : (room >= (long long)N + hop ? 0x7fffffff : (room < 0 ? 0 : (int)room));
             // one output sample: `done` positions leave the chip, the others stay in the tail.  OUT32 follows the
             // reference's types: the finished sample is the float of (float tail + double value) (:180), the tail
             // accumulates the value narrowed first, in float (:195-197).
@@ -1150,21 +1150,20 @@ struct FwdPasses<CH, END, END> {
 };
 template <class CH, int P, int END>
 struct InvPasses {
-    template <class Exec>
+    template <bool EMIT, class Exec>
     static TSB_HD void run(Exec &ex, int lane, typename CH::Smem &sm, const typename CH::Tables &tb, const ChainArgs &a,
-                           long long out_pos, int hop, bool emit) {
+                           long long out_pos, int hop) {
         ex.each([&](int tid, typename CH::Regs &) {
-            CH::template inv_pass<P>(tid, lane, sm, tb, a, out_pos, hop, emit);
+            CH::template inv_pass<P, CH::T, EMIT>(tid, lane, sm, tb, a, out_pos, hop);
             if (P == END - 1) CH::ring_wait();
         });
-        InvPasses<CH, P + 1, END>::run(ex, lane, sm, tb, a, out_pos, hop, emit);
+        InvPasses<CH, P + 1, END>::template run<EMIT>(ex, lane, sm, tb, a, out_pos, hop);
     }
 };
 template <class CH, int END>
 struct InvPasses<CH, END, END> {
-    template <class Exec>
-    static TSB_HD void run(Exec &, int, typename CH::Smem &, const typename CH::Tables &, const ChainArgs &, long long, int,
-                           bool) {}
+    template <bool EMIT, class Exec>
+    static TSB_HD void run(Exec &, int, typename CH::Smem &, const typename CH::Tables &, const ChainArgs &, long long, int) {}
 };
 
 // Software-pipelined pass pairs (CH::PIPE): in one barrier interval the first T0 threads run forward pass P of
@@ -1172,10 +1171,10 @@ struct InvPasses<CH, END, END> {
 // split is at warp granularity).  Both transforms have the same pass structure, so they stay in step.
 template <class CH, int P, int END>
 struct PipePasses {
-    template <class Exec>
+    template <bool EMIT, class Exec>
     static TSB_HD void run(Exec &ex, int lane, typename CH::Smem &sm, const typename CH::Tables &tb, const ChainArgs &a,
                            bool have_next, long long next_in_off, long long fetch_first, int fetch_cnt, bool have_cur,
-                           long long out_pos, int hop, bool emit) {
+                           long long out_pos, int hop) {
         ex.each([&](int tid, typename CH::Regs &) {
             if (tid < CH::T0) {
                 if (have_next) {
@@ -1188,18 +1187,18 @@ struct PipePasses {
                     if (P == END - 1 && fetch_cnt > 0) CH::template ring_fill<CH::T0>(tid, lane, sm, a, fetch_first, fetch_cnt);
                 }
             } else if (have_cur) {
-                CH::template inv_pass<P, CH::T0>(tid - CH::T0, lane, sm, tb, a, out_pos, hop, emit);
+                CH::template inv_pass<P, CH::T0, EMIT>(tid - CH::T0, lane, sm, tb, a, out_pos, hop);
             }
         });
-        PipePasses<CH, P + 1, END>::run(ex, lane, sm, tb, a, have_next, next_in_off, fetch_first, fetch_cnt, have_cur,
-                                        out_pos, hop, emit);
+        PipePasses<CH, P + 1, END>::template run<EMIT>(ex, lane, sm, tb, a, have_next, next_in_off, fetch_first, fetch_cnt,
+                                                       have_cur, out_pos, hop);
     }
 };
 template <class CH, int END>
 struct PipePasses<CH, END, END> {
-    template <class Exec>
+    template <bool EMIT, class Exec>
     static TSB_HD void run(Exec &, int, typename CH::Smem &, const typename CH::Tables &, const ChainArgs &, bool, long long,
-                           long long, int, bool, long long, int, bool) {}
+                           long long, int, bool, long long, int) {}
 };
 
 // The whole launch for one (segment, lane).  `Exec::each(f)` runs f(tid, regs) for every thread of the lane and
@@ -1230,32 +1229,35 @@ TSB_HD SegInfo seg_info(const ChainArgs &a, int lane, int seg) {
     return sg;
 }
 
-template <class CH, class Exec>
+// PREPASS (ChainArgs::mode == 1) is a compile-time choice: the pre-pass lives in its own kernel, so that its loop
+// does not weigh on the register allocation of the render loop.
+template <class CH, bool PREPASS, class Exec>
 TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const typename CH::Tables &tb, const ChainArgs &a) {
     using Regs = typename CH::Regs;
     constexpr int N = CH::N;
     static_assert(CH::PASSES >= 2, "frame sizes below 64 are not instantiated");
     // Only what the frame loop needs stays live across it (registers are what limits residency): the segment
     // description is re-read from the argument block / table at the end.
+    // Frames are numbered from the segment's first OWN frame: ff < 0 are its lead-in frames (and, in the pre-pass,
+    // the warm-up frame before them), so that nothing but the counter tells them apart inside the loop.
     long long in_off, out_pos;
-    int total;
+    int own, ff_first;
     const int *hop_tab;
-    bool prepass, warm;
+    constexpr bool prepass = PREPASS && CH::IS_PV;
+    bool warm;
     int warm_hop;
-    long long first_frame;
-    int lead;
+    long long first_own;
     {
         SegInfo sg = seg_info<CH>(a, lane, seg);
-        first_frame = sg.first_frame;
-        lead = sg.lead;
-        prepass = CH::IS_PV && a.mode == 1;
+        first_own = sg.first_frame + sg.lead;
         warm = prepass && sg.warm;
         warm_hop = sg.warm_hop;
         // a warm-up frame is the frame before the segment: it only primes last_phase
         in_off = warm ? sg.in_off0 - sg.warm_hop : sg.in_off0;
         out_pos = sg.out_off0;
-        total = (int)sg.n_frames + (warm ? 1 : 0);
-        hop_tab = a.hop_tab ? a.hop_tab + sg.first_frame - (warm ? 1 : 0) : nullptr;  // indexed by ff below
+        own = (int)sg.n_frames - sg.lead;
+        ff_first = -sg.lead - (warm ? 1 : 0);
+        hop_tab = a.hop_tab ? a.hop_tab + first_own : nullptr;  // indexed by ff below (the warm-up frame has warm_hop)
         ex.each([&](int tid, Regs &rg) {
             CH::load_state(tid, sm, rg, tb, a, sg);
             CH::ring_fill(tid, lane, sm, a, in_off, N);
@@ -1266,16 +1268,18 @@ TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const t
         // frame f: [analyse f][synthesise f][inverse passes of f  ||  forward passes of f+1]; the forward passes of
         // the first frame run alone as a prologue.  `hop_of(f)` = samples emitted after frame f.
         auto hop_of = [&](int f) { return hop_tab ? TSB_LDG(&hop_tab[f]) : a.hop; };
-        if (total > 0) {
-            int hop0 = hop_of(0);
-            int cnt = total > 1 ? (hop0 < N ? hop0 : N) : 0;
-            PipePasses<CH, 0, CH::PASSES>::run(ex, lane, sm, tb, a, true, in_off, in_off + hop0 + N - cnt, cnt, false, out_pos, 0,
-                                               false);
+        if (ff_first < own) {
+            int hop0 = hop_of(ff_first);
+            int cnt = ff_first + 1 < own ? (hop0 < N ? hop0 : N) : 0;
+            PipePasses<CH, 0, CH::PASSES>::template run<false>(ex, lane, sm, tb, a, true, in_off, in_off + hop0 + N - cnt, cnt,
+                                                               false, out_pos, 0);
         }
-        for (int ff = 0; ff < total; ff++) {
+        // one frame; EMIT is a type so that the lead-in frames get their own (cold) copy of the passes and the
+        // steady-state loop carries nothing extra
+        auto frame = [&](int ff, auto EMIT) {
             const int hop = hop_of(ff);
             if (CH::IS_PV) {
-                const bool all = ff + 1 == total;  // last_phase is state: the last frame of a launch analyses every bin
+                const bool all = ff + 1 == own;  // last_phase is state: the last frame of a launch analyses every bin
                 ex.each([&](int tid, Regs &rg) { CH::phase_pv_analyze(tid, sm, rg, tb, all); });
                 ex.each([&](int tid, Regs &rg) {
                     CH::phase_pv_synth(tid, sm, rg, tb);
@@ -1287,29 +1291,35 @@ TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const t
                     CH::ring_wait();
                 });
             }
-            const bool have_next = ff + 1 < total;
+            const bool have_next = ff + 1 < own;
             const long long next_in = in_off + hop;
             int cnt = 0;
             long long first = 0;
-            if (have_next && ff + 2 < total) {  // while frame ff+1 is transformed, fetch what frame ff+2 adds
+            if (have_next && ff + 2 < own) {  // while frame ff+1 is transformed, fetch what frame ff+2 adds
                 int hop1 = hop_of(ff + 1);
                 cnt = hop1 < N ? hop1 : N;
                 first = next_in + hop1 + N - cnt;
             }
-            PipePasses<CH, 0, CH::PASSES>::run(ex, lane, sm, tb, a, have_next, next_in, first, cnt, true, out_pos, hop, ff >= lead);
+            PipePasses<CH, 0, CH::PASSES>::template run<decltype(EMIT)::value>(ex, lane, sm, tb, a, have_next, next_in, first, cnt,
+                                                                              true, out_pos, hop);
             in_off = next_in;
             out_pos += hop;
-        }
-    } else
-    for (int ff = 0; ff < total; ff++) {
-        const bool is_warm = warm && ff == 0;
+        };
+        int ff = ff_first;
+        for (; ff < 0 && ff < own; ff++) frame(ff, std::false_type{});
+        for (; ff < own; ff++) frame(ff, std::true_type{});
+    } else {
+    bool warm_pending = warm;
+    for (int ff = ff_first; ff < own; ff++) {
+        const bool is_warm = warm_pending;
+        warm_pending = false;
         int hop = is_warm ? warm_hop : (hop_tab ? TSB_LDG(&hop_tab[ff]) : a.hop);
         // slots [in_off, in_off+hop) are dead once pass 0 has read the frame
-        int cnt = ff + 1 < total ? (hop < N ? hop : N) : 0;
+        int cnt = ff + 1 < own ? (hop < N ? hop : N) : 0;
         long long first = in_off + hop + N - cnt;
         FwdPasses<CH, 0, CH::PASSES>::run(ex, lane, sm, tb, a, in_off, first, cnt);
         if (CH::IS_PV) {
-            const bool all = is_warm || ff + 1 == total;
+            const bool all = is_warm || ff + 1 == own;
             ex.each([&](int tid, Regs &rg) { CH::phase_pv_analyze(tid, sm, rg, tb, all); });
             if (prepass) {
                 if (is_warm) {
@@ -1317,9 +1327,8 @@ TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const t
                         const long long row = (long long)seg * a.lanes + lane;
                         ex.each([&](int tid, Regs &rg) { CH::regs_to(tid, a.st_warm_phase, row, rg.last_phase); });
                     }
-                } else if (ff - (warm ? 1 : 0) >= lead) {  // (lead-in frames: their increments are the previous segment's)
-                    double *inc_row = a.st_inc ? a.st_inc + ((long long)lane * a.inc_frames + first_frame + ff - (warm ? 1 : 0)) * CH::M
-                                               : nullptr;
+                } else if (ff >= 0) {  // (lead-in frames: their increments are the previous segment's)
+                    double *inc_row = a.st_inc ? a.st_inc + ((long long)lane * a.inc_frames + first_own + ff) * CH::M : nullptr;
                     ex.each([&](int tid, Regs &rg) { CH::phase_pv_accumulate(tid, sm, rg, tb, inc_row); });
                 }
                 ex.each([&](int, Regs &) { CH::ring_wait(); });
@@ -1330,9 +1339,11 @@ TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const t
         } else {
             ex.each([&](int tid, Regs &) { CH::phase_gain(tid, sm, tb); });
         }
-        InvPasses<CH, 0, CH::PASSES>::run(ex, lane, sm, tb, a, out_pos, hop, ff >= lead);
+        if (ff >= 0) InvPasses<CH, 0, CH::PASSES>::template run<true>(ex, lane, sm, tb, a, out_pos, hop);
+        else InvPasses<CH, 0, CH::PASSES>::template run<false>(ex, lane, sm, tb, a, out_pos, hop);
         in_off += hop;
         out_pos += hop;
+    }
     }
     {
         SegInfo sg = seg_info<CH>(a, lane, seg);

@@ -42,7 +42,8 @@ constexpr int min_blocks() {
 template <class CH>
 constexpr int default_carveout_kb() { return 228; }
 
-template <typename real, int LOG2N, int PROG, bool OUT32>
+// PREPASS: the time-parallel pre-pass (ChainArgs::mode == 1: analysis and per-frame increments only)
+template <typename real, int LOG2N, int PROG, bool OUT32, bool PREPASS>
 __global__ void __launch_bounds__(Chain<real, LOG2N, PROG, OUT32>::T, min_blocks<Chain<real, LOG2N, PROG, OUT32>>())
 chain_kernel(const ChainTables<real> tb, const ChainArgs a) {
     using CH = Chain<real, LOG2N, PROG, OUT32>;
@@ -51,13 +52,15 @@ chain_kernel(const ChainTables<real> tb, const ChainArgs a) {
     DevExec<CH> ex;
     const int nseg = a.n_seg > 1 ? a.n_seg : 1;
     for (long long b = blockIdx.x; b < (long long)a.lanes * nseg; b += gridDim.x)
-        run_lane<CH>(ex, (int)(b % a.lanes), (int)(b / a.lanes), sm, tb, a);
+        run_lane<CH, PREPASS>(ex, (int)(b % a.lanes), (int)(b / a.lanes), sm, tb, a);
 }
 
 template <typename real, int LOG2N, int PROG, bool OUT32 = false>
 static cudaError_t launch(const void *tables, const ChainArgs &a, cudaStream_t stream) {
     using CH = Chain<real, LOG2N, PROG, OUT32>;
-    auto kern = chain_kernel<real, LOG2N, PROG, OUT32>;
+    // the pre-pass writes no samples: one instantiation (OUT32 = false) serves both output types
+    auto kern = (a.mode == 1 && PROG == PROG_PV_SHIFT) ? chain_kernel<real, LOG2N, PROG, OUT32, true>
+                                                         : chain_kernel<real, LOG2N, PROG, OUT32, false>;
     size_t smem = sizeof(typename CH::Smem);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
