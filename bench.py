@@ -122,9 +122,24 @@ def ref_binary():
     return None, None
 
 
+def host_cpus():
+    """the CPUs this process may run on (cgroup/affinity aware), in order"""
+    try:
+        return sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        return list(range(os.cpu_count() or 1))
+
+
+# One MKL/OpenMP thread per reference process: the reference is single-threaded (one worker, tinyspec.cpp:284);
+# without this every copy's MKL pool spawns a thread per core and P copies oversubscribe the host (round-1 flaw).
+ONE_THREAD = {"OMP_NUM_THREADS": "1", "MKL_NUM_THREADS": "1", "OPENBLAS_NUM_THREADS": "1", "MKL_DYNAMIC": "FALSE"}
+
+
 def run_reference(procs, seconds):
     """`procs` concurrent copies of the compiled, unmodified reference (oracle/_ref), one stereo stream each
-    (its own README's way to scale, README.md:85-86).  Returns (frames per process, wall seconds)."""
+    (its own README's way to scale, README.md:85-86), each pinned to its own host core with one FFT thread
+    (BASELINE.md §3.3).  Time = the binary's own first->last process-callback wall (oracle/ref/fake_jack.cpp,
+    TSREF_TIMING), the slowest copy counting for all.  Returns (frames per process, seconds, kind, what, procs)."""
     binary, fft = ref_binary()
     samples = int(seconds * RATE)
     if binary is None:
@@ -136,19 +151,53 @@ def run_reference(procs, seconds):
         return r["frames"], time.perf_counter() - t0, "port", "C oracle (oracle/oracle.c), radix-2 FFT", 1
     import tempfile
     env = dict(os.environ, TSREF_SAMPLES=str(samples), TSREF_N=str(N_FRAME), TSREF_HOP_RATIO=str(HOP / N_FRAME),
-               TSREF_SHIFT=str(SHIFT), TSREF_CH=str(CH), TSREF_TIMING="1", TSREF_DUMP_FIRST="0")
+               TSREF_SHIFT=str(SHIFT), TSREF_CH=str(CH), TSREF_TIMING="1", TSREF_DUMP_FIRST="0", **ONE_THREAD)
+    cpus = host_cpus()
     dirs = [tempfile.mkdtemp(prefix="tsref") for _ in range(procs)]
-    t0 = time.perf_counter()
+
+    def pin(cpu):
+        return lambda: os.sched_setaffinity(0, {cpu})
+
     ps = [subprocess.Popen([binary], env=dict(env, TSREF_STREAM=str(i)), cwd=d, stdout=subprocess.PIPE,
-                           stderr=subprocess.DEVNULL, text=True) for i, d in enumerate(dirs)]
-    outs = [p.communicate()[0] for p in ps]
-    wall = time.perf_counter() - t0
-    frames = 0
+                           stderr=subprocess.DEVNULL, text=True, preexec_fn=pin(cpus[i % len(cpus)]))
+          for i, d in enumerate(dirs)]
+    outs = []
+    for p in ps:
+        try:
+            outs.append(p.communicate(timeout=600)[0])
+        except subprocess.TimeoutExpired:
+            p.kill()
+            outs.append("")
+    frames, walls = 0, []
     for o in outs:
         for line in o.splitlines():
             if line.startswith("{"):
-                frames = json.loads(line)["frames"]
-    return frames, wall, "reference", f"unmodified reference (oracle/_ref), {fft}", procs
+                j = json.loads(line)
+                frames = j["frames"]
+                walls.append(j["wall_s"])
+    for d in dirs:
+        try:
+            os.rmdir(d)
+        except OSError:
+            pass
+    if len(walls) != procs:
+        raise SystemExit(f"reference arm: {procs - len(walls)} of {procs} reference processes did not finish")
+    return frames, max(walls), "reference", f"unmodified reference (oracle/_ref), {fft}", procs
+
+
+def frames_per_stream(length):
+    """frames the scheduler runs over `length` input samples (tinyspec.cpp:142-149: the first advance is 2048)"""
+    return (length - 2048 - N_FRAME) // HOP + 1
+
+
+def workload_config(seconds, streams, precision):
+    """`config` of the JSON line — the same dict for both arms (the reference arm runs a bounded sample of it)"""
+    L = int(seconds * RATE)
+    return {"workload": "cfg1x", "what": "hacks/pitchshift-pv.cpp chain (BASELINE configs[0]) x S streams",
+            "frame": N_FRAME, "hop": HOP, "channels": CH, "rate": RATE, "shift": SHIFT,
+            "seconds_per_stream": seconds, "frames_per_stream": frames_per_stream(L), "streams_per_gpu": streams,
+            "lanes_per_gpu": streams * CH, "sharding": "streams across GPUs, no collective",
+            "l2": f"inputs larger than L2 ({streams * CH * L * 4 / 1e9:.1f} GB in per GPU)"}
 
 
 def main():
@@ -177,11 +226,11 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cores = os.cpu_count() or 1
-        secs = min(args.seconds, 20.0)
+        cores = len(host_cpus())
+        S = args.streams or STREAMS[args.precision]
         times, frames = [], 0
         for i in range(args.warmup + args.steps):
-            frames, wall, kind, what, used = run_reference(cores, secs)
+            frames, wall, kind, what, used = run_reference(cores, args.seconds)
             if i >= args.warmup:
                 times.append(wall)
         tot = sum(times)
@@ -190,11 +239,13 @@ def main():
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "frame_channels_per_s": fps * CH, "out_samples_per_s": fps * CH * HOP,
-                "config": {"workload": "cfg1x", "frame": N_FRAME, "hop": HOP, "channels": CH, "rate": RATE,
-                           "shift": SHIFT, "streams_per_step": used, "seconds_per_stream": secs},
+                "frames_per_s_per_core": fps / used,
+                "config": workload_config(args.seconds, S, args.precision),
                 "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": used, "kind": kind,
-                                 "sample": f"{used} concurrent processes x 1 stereo stream x {secs:g} s "
-                                           f"({frames} frames each) per step; {what}"},
+                                 "sample": f"bounded sample of the workload: {used} of its streams per step, one "
+                                           f"reference process per host core (pinned, 1 FFT thread each), 1 stereo "
+                                           f"stream x {args.seconds:g} s = {frames} frames each; time = the slowest "
+                                           f"process's own first->last callback wall; {what}"},
                 "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -289,11 +340,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "frame_channels_per_s": fcs, "out_samples_per_s": fcs * HOP,
-            "config": {"workload": "cfg1x", "what": "hacks/pitchshift-pv.cpp chain (BASELINE configs[0]) x S streams",
-                       "frame": N_FRAME, "hop": HOP, "channels": CH, "rate": RATE, "shift": SHIFT,
-                       "seconds_per_stream": args.seconds, "frames_per_stream": F, "streams_per_gpu": S,
-                       "lanes_per_gpu": lanes, "sharding": "streams across GPUs, no collective",
-                       "l2": f"inputs larger than L2 ({lanes * L * 4 / 1e9:.1f} GB in per GPU)"},
+            "config": workload_config(args.seconds, S, args.precision),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_frame_channel": balg,
                          "kernel": "tsb::chain_kernel<" + ("double" if args.precision == "f64" else "float") + ",10,PV>",
@@ -356,7 +403,9 @@ def main():
     if rank == 0 and world == 1:
         frames, wall, kind, what, used = run_reference(1, min(args.seconds, 60.0))
         line["cpu_baseline"] = {"value": frames / wall, "unit": "frames/s", "cores": used, "kind": kind,
-                                "sample": f"1 process, 1 stereo stream x {min(args.seconds, 60.0):g} s = {frames} frames; {what}"}
+                                "sample": f"1 process pinned to 1 core (1 FFT thread), 1 stereo stream x "
+                                          f"{min(args.seconds, 60.0):g} s = {frames} frames, its own first->last "
+                                          f"callback wall; {what}"}
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:
