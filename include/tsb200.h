@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TSB_ABI_VERSION 1
+#define TSB_ABI_VERSION 2
 
 enum { TSB_OK = 0, TSB_EINVAL = -1, TSB_ECUDA = -2, TSB_EUNSUPPORTED = -3, TSB_ENOMEM = -4 };
 /* arithmetic of the chain (phase accumulators are fp64 in all three).  TSB_F64_OUT32 computes like TSB_F64 and
@@ -109,7 +109,12 @@ int tsb_plan_destroy(tsb_plan *plan);
  *             (live bins 0..n/2-1) and the overlap tail relative to the next output position.
  *             load_state = 0 starts from PhaseVocoder::reset() and an empty tail; the arrays (may be
  *             NULL) receive the state after the last frame, so a render can be continued, split into
- *             time segments, or teacher-forced. */
+ *             time segments, or teacher-forced.
+ *   prev_hop  load_state = 1 only: computed_hop of the frame before the first one of this call (its samples
+ *             start at in_off0 - prev_hop of the same rows), 0 = not known.  Only TSB_F32 reads it: a wrap of
+ *             phase_to_frequency (rtlib/pv.hpp:41-43) that the float32 transform cannot decide safely is
+ *             re-evaluated in double precision from the samples of the frame and of the one before it; with
+ *             prev_hop = 0 the first frame of a continued render keeps the float32 decision. */
 typedef struct tsb_chain_args {
     const float *in;
     int64_t in_stride, in_len;
@@ -122,6 +127,7 @@ typedef struct tsb_chain_args {
     double *state_last_phase, *state_phase_sum, *state_ola;
     int32_t load_state;
     int32_t lanes;
+    int32_t prev_hop;
 } tsb_chain_args;
 int tsb_chain_render(tsb_ctx *ctx, tsb_plan *plan, const tsb_chain_args *args);
 

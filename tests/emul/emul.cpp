@@ -20,6 +20,12 @@ struct HostExec {
     void each(F f) {
         for (int tid = 0; tid < CH::T; tid++) f(tid, regs[tid]);
     }
+    template <class F>
+    bool each_or(F f) {
+        bool any = false;
+        for (int tid = 0; tid < CH::T; tid++) any = f(tid, regs[tid]) || any;
+        return any;
+    }
 };
 
 template <typename real, int LOG2N, int PROG, bool OUT32>
@@ -57,7 +63,7 @@ extern "C" int emul_chain_render(int precision, int log2n, int program, int win_
                                  const float *in, long long in_stride, long long in_len, void *out,
                                  long long out_stride, long long out_len, long long n_frames, long long in_off0,
                                  long long out_off0, int hop, const int *hop_tab, double *st_last_phase,
-                                 double *st_phase_sum, double *st_ola, int load_state, int lanes) {
+                                 double *st_phase_sum, double *st_ola, int load_state, int lanes, int prev_hop) {
     PlanDesc d;
     d.n = 1 << log2n;
     d.program = program;
@@ -77,6 +83,7 @@ extern "C" int emul_chain_render(int precision, int log2n, int program, int win_
     a.load_state = load_state; a.lanes = lanes;
     a.n_seg = 0; a.seg_tab = nullptr; a.mode = 0; a.st_warm_phase = nullptr;
     a.st_inc = nullptr; a.inc_frames = 0;
+    a.prev_hop = prev_hop;
     if (precision == 0)
         return program == PROG_PV_SHIFT ? by_size<float, PROG_PV_SHIFT>(log2n, d, a) : by_size<float, PROG_GAIN>(log2n, d, a);
     if (precision == 2)
@@ -113,6 +120,7 @@ extern "C" int emul_chain_render_ex(int precision, int log2n, int program, int w
     a.load_state = load_state; a.lanes = lanes;
     a.n_seg = 1; a.seg_tab = seg; a.mode = mode; a.st_warm_phase = st_warm_phase;
     a.st_inc = st_inc; a.inc_frames = n_frames;
+    a.prev_hop = 0;
     if (precision == 0)
         return program == PROG_PV_SHIFT ? by_size<float, PROG_PV_SHIFT>(log2n, d, a) : by_size<float, PROG_GAIN>(log2n, d, a);
     if (precision == 2)
@@ -167,4 +175,12 @@ extern "C" void emul_pv_math(long long n, const double *y, const double *x, doub
         wrap_out[i] = wrap_quotient(x[i]);
         fast_sincos(y[i], sin_out[i], cos_out[i]);
     }
+}
+
+// fp32 PV: doubtful wraps re-evaluated in double precision since the last call / of them decided the other way
+extern "C" void emul_wrap_counters(long long *fixed, long long *changed) {
+    long long *c = host_wrap_counters();
+    *fixed = c[0];
+    *changed = c[1];
+    c[0] = c[1] = 0;
 }

@@ -6,7 +6,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB = os.path.join(HERE, "_build", "libtsb_emul.so")
+LIB = os.environ.get("TSB_EMUL_LIB") or os.path.join(HERE, "_build", "libtsb_emul.so")
 _lib = None
 
 
@@ -20,16 +20,23 @@ def lib():
                                                                              C.c_longlong, C.c_longlong,
                                                                              C.c_longlong, C.c_longlong,
                                                                              C.c_longlong, C.c_int, P, P, P, P,
-                                                                             C.c_int, C.c_int]
+                                                                             C.c_int, C.c_int, C.c_int]
         _lib.emul_fft.argtypes = [C.c_int, C.c_int, P, P]
         _lib.emul_pv_math.argtypes = [C.c_longlong, P, P, P, P, P, P, P]
         _lib.emul_pv_math.restype = None
-        _lib.emul_chain_render_ex.argtypes = _lib.emul_chain_render.argtypes + [C.c_int, C.c_int, C.c_int, P, P, C.c_int]
+        _lib.emul_chain_render_ex.argtypes = _lib.emul_chain_render.argtypes[:-1] + [C.c_int, C.c_int, C.c_int, P, P, C.c_int]
     return _lib
 
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def wrap_counters():
+    """(doubtful wraps the fp32 PV re-evaluated in double precision, of them decided the other way) since the last call"""
+    a, b = C.c_longlong(), C.c_longlong()
+    lib().emul_wrap_counters(C.byref(a), C.byref(b))
+    return a.value, b.value
 
 
 def pv_math(y, x):
@@ -48,7 +55,7 @@ WIN = {"none": 0, None: 0, "hann": 1, "sqrt_hann": 2}
 
 def chain_render(x, n, hop, n_frames, precision="f64", program="pv", ratio=2.0, gain=None, fn_bins=None,
                  win_in="sqrt_hann", win_out="sqrt_hann", rate=48000.0, hop_d=None, hop_tab=None, in_off0=2048,
-                 out_off0=0, state=None, out_len=None):
+                 out_off0=0, state=None, out_len=None, prev_hop=0):
     """x: planar float32 [lanes, L].  Returns (out [lanes, out_len], state dict)."""
     x = np.ascontiguousarray(x, np.float32)
     lanes, L = x.shape
@@ -68,7 +75,7 @@ def chain_render(x, n, hop, n_frames, precision="f64", program="pv", ratio=2.0, 
                                 WIN[win_in], WIN[win_out], float(hop if hop_d is None else hop_d), rate, ratio,
                                 _p(fb), _p(g), _p(x), L, L, _p(out), out_len, out_len, n_frames, in_off0, out_off0,
                                 int(hop), _p(ht), _p(state["last_phase"]), _p(state["phase_sum"]), _p(state["ola"]),
-                                int(load), lanes)
+                                int(load), lanes, int(prev_hop))
     assert r == 0
     return out, state
 

@@ -418,6 +418,38 @@ def test_two_minute_render_does_not_diverge(env):
 
 
 @pytest.mark.gpu
+def test_fp32_two_minutes_at_x1p5_never_flips(env):
+    """BASELINE.json: "PV phase state must never diverge" — fp32 mode at a NON-integer ratio (cfg3's x1.5), where a wrap
+    decided on the other side than the reference's double arithmetic is a permanent sign flip of the bin
+    (rtlib/pv.hpp:39-45).  120 s of cfg1 at x1.5 flipped several bins before doubtful wraps were re-evaluated in
+    double precision (Chain::phase_wrap_fix); now: zero flips against the oracle, 1e-5 RMS held to the end, and the
+    time-parallel fp32 render is the sequential one bit for bit."""
+    torch, tsb, orc = env["torch"], env["tsb"], env["orc"]
+    n, hop, ch, samples, ratio = 1024, 256, 2, 120 * 48000, 1.5
+    x = orc.gen_signal(0, ch, samples)
+    ref = orc.render_pv(x, n, 0.25, ratio)
+    F = ref["frames"]
+    want = ref["ola64"][:F * hop].T
+    xd = torch.from_numpy(np.ascontiguousarray(x.T)).cuda()
+    plan = tsb.Plan(env["ctx"], n, precision="f32", program="pv", hop=hop, ratio=ratio)
+    outs = []
+    for nseg in (0, 148):
+        st = {k: torch.zeros((ch, w), dtype=torch.float64, device="cuda") for k, w in
+              (("last_phase", n // 2), ("phase_sum", n // 2), ("ola", n))}
+        out = plan.render_timepar(xd, F, hop, nseg, state=st) if nseg else plan.render(xd, F, hop, state=st)
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        dps = np.abs(st["phase_sum"].cpu().numpy() - ref["phase_sum"][:, :n // 2])
+        assert (dps > 1).sum() == 0, f"{int((dps > 1).sum())} wrap flips"
+        assert dps.max() < 1e-3
+        tail = slice(-5 * 48000, None)
+        assert rmsrel(got, want) <= F32_RMSREL
+        assert rmsrel(got[:, tail], want[:, tail]) <= F32_RMSREL
+        outs.append((got, st["phase_sum"].cpu().numpy()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("n,hr,shift,ch,samples", [(1024, 0.25, 2.0, 2, 96000), (4096, 0.25, 1.5, 8, 60000),
                                                    (256, 0.3, 1.5, 2, 9000), (64, 1.6, 1.5, 1, 9000),
                                                    (512, 0.2003, 0.75, 1, 16000), (8192, 0.25, 1.5, 1, 60000)])

@@ -53,6 +53,32 @@ def test_pv_chain(n, hr, shift, ch, samples, stream):
     assert (np.abs(st32["phase_sum"] - ref["phase_sum"][:, :n // 2]) > 1).sum() == 0
 
 
+def test_fp32_doubtful_wraps_are_decided_in_double():
+    """fp32 mode, non-integer ratio: a wrap of phase_to_frequency (rtlib/pv.hpp:41-43) that the float32 transform puts
+    within its own phase error of the +-pi boundary is re-evaluated in double precision from the input samples
+    (Chain::phase_wrap_fix).  Over 60 s of cfg1 at x1.5 the float decision is wrong a few times — each one used to be
+    a permanent sign flip of that bin — and every one is caught: the phase sums follow the fp64 render."""
+    n, hop, ratio = 1024, 256, 1.5
+    x = orc.gen_signal(0, 2, 60 * 48000).T
+    F = (x.shape[1] - 2048 - n) // hop + 1
+    out64, st64 = emul.chain_render(x, n, hop, F, precision="f64", ratio=ratio)
+    emul.wrap_counters()
+    out32, st32 = emul.chain_render(x, n, hop, F, precision="f32", ratio=ratio)
+    fixed, changed = emul.wrap_counters()
+    assert fixed > 50 and changed >= 1                      # the slow path ran, and it mattered
+    assert fixed < 0.05 * F * 2                             # ... rarely: a few per hundred frames
+    dps = np.abs(st32["phase_sum"] - st64["phase_sum"])
+    assert (dps > 1).sum() == 0 and dps.max() < 1e-3         # no flips: the sums differ by float phase noise only
+    assert rmsrel(out32, out64) < 1e-5
+    # a continued render decides the same way when it is told where the previous frame lies (ChainArgs::prev_hop)
+    a = F // 3
+    o1, st = emul.chain_render(x, n, hop, a, precision="f32", ratio=ratio)
+    o2, st = emul.chain_render(x, n, hop, F - a, precision="f32", ratio=ratio, in_off0=2048 + a * hop, state=st,
+                               prev_hop=hop)
+    assert np.array_equal(np.concatenate([o1, o2], axis=1), out32)
+    assert np.array_equal(st["phase_sum"], st32["phase_sum"])
+
+
 def test_pv_chain_fractional_hop_and_segments():
     x = orc.gen_signal(3, 1, 12000)
     n, hop_d, shift = 512, 512 * 0.2003, 0.75

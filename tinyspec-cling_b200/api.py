@@ -35,7 +35,7 @@ class _ChainArgs(C.Structure):
                 ("out_stride", C.c_int64), ("out_len", C.c_int64), ("n_frames", C.c_int64), ("in_off0", C.c_int64),
                 ("out_off0", C.c_int64), ("hop", C.c_int32), ("hop_tab", C.c_void_p),
                 ("state_last_phase", C.c_void_p), ("state_phase_sum", C.c_void_p), ("state_ola", C.c_void_p),
-                ("load_state", C.c_int32), ("lanes", C.c_int32)]
+                ("load_state", C.c_int32), ("lanes", C.c_int32), ("prev_hop", C.c_int32)]
 
 
 _lib = None

@@ -231,6 +231,7 @@ static int upload_tables(tsb_plan *p, const PlanDesc &d, ChainTables<real> &t) {
     if ((r = upload_vec(p, h.src_used, &t.src_used))) return r;
     if (!h.dst_order.empty() && (r = upload_vec(p, h.dst_order, &t.dst_order))) return r;
     if ((r = upload_vec(p, h.gain, &t.gain))) return r;
+    if (!h.win64.empty() && (r = upload_vec(p, h.win64, &t.win64))) return r;
     return TSB_OK;
 }
 
@@ -313,6 +314,7 @@ static ChainArgs to_args(const tsb_chain_args *a) {
     k.load_state = a->load_state; k.lanes = a->lanes;
     k.n_seg = 0; k.seg_tab = nullptr; k.mode = 0; k.st_warm_phase = nullptr;
     k.st_inc = nullptr; k.inc_frames = 0;
+    k.prev_hop = a->prev_hop;
     return k;
 }
 TSB_API int tsb_chain_render(tsb_ctx *c, tsb_plan *p, const tsb_chain_args *a) {
@@ -750,7 +752,11 @@ TSB_API int tsb_timepar_create(tsb_ctx *c, tsb_plan *p, const tsb_chain_args *a,
     // a single stream).  Reuse is safe in stream order; a second live tsb_timepar gets its own block.
     if (!c->tp_pool_busy) {
         if (c->tp_pool_bytes < total) {
-            CU(cudaStreamSynchronize(c->stream));
+            cudaError_t es = cudaStreamSynchronize(c->stream);
+            if (es != cudaSuccess) {
+                delete tp;
+                return fail(TSB_ECUDA, "cudaStreamSynchronize: %s", cudaGetErrorString(es));
+            }
             if (c->tp_pool) cudaFree(c->tp_pool);
             c->tp_pool = nullptr;
             c->tp_pool_bytes = 0;
@@ -774,9 +780,13 @@ TSB_API int tsb_timepar_create(tsb_ctx *c, tsb_plan *p, const tsb_chain_args *a,
     tp->d_warm = (double *)q; q += b_m;
     tp->d_ola = (double *)q; q += b_n;
     tp->d_inc = pv ? (double *)q : nullptr;
-    CU(cudaMemcpyAsync(tp->d_seg, tp->seg.data(), tp->seg.size() * 8, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(tp->d_pos, pos.data(), (size_t)nseg * 8, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));  // seg / pos are host temporaries
+    cudaError_t e = cudaMemcpyAsync(tp->d_seg, tp->seg.data(), tp->seg.size() * 8, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(tp->d_pos, pos.data(), (size_t)nseg * 8, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);  // seg / pos are host temporaries
+    if (e != cudaSuccess) {
+        tsb_timepar_destroy(tp);  // gives the pool block back / frees the private one
+        return fail(TSB_ECUDA, "time-parallel tables: %s", cudaGetErrorString(e));
+    }
     *out = tp;
     return TSB_OK;
 }
@@ -933,6 +943,7 @@ struct tsb_stream {
     int64_t hops_cap = 0;
     double *d_last = nullptr, *d_sum = nullptr, *d_ola = nullptr;
     bool started = false;
+    int32_t last_hop = 0;  // computed_hop of the last frame rendered (tsb_chain_args::prev_hop of the next call)
 };
 TSB_API int tsb_stream_destroy(tsb_stream *s) {
     if (!s) return TSB_OK;
@@ -1000,10 +1011,13 @@ TSB_API int tsb_stream_process(tsb_stream *s, const float *host_in, int64_t in_s
                              cudaMemcpyHostToDevice, c->stream));
     s->pushed += len;
     // frames that can run now (tinyspec.cpp:142-149 on the concatenated input)
+    // (on a copy of the scheduler: it is committed only once the frames are on their way, so that an error below
+    // leaves the stream where it was and the frames are scheduled again by the next call)
     int64_t out0 = s->st.out_pos;
-    std::vector<FrameRec> fr = schedule_const(s->st, s->pushed, (uint32_t)n, s->hop, -1);
+    SchedState st_next = s->st;
+    std::vector<FrameRec> fr = schedule_const(st_next, s->pushed, (uint32_t)n, s->hop, -1);
     if (!fr.empty()) {
-        int64_t total = s->st.out_pos - out0;
+        int64_t total = st_next.out_pos - out0;
         if (total > out_cap) return fail(TSB_EINVAL, "out_cap %lld too small for %lld finished samples", (long long)out_cap, (long long)total);
         if (total > s->out_cap) {
             cudaFree(s->d_out);
@@ -1041,9 +1055,14 @@ TSB_API int tsb_stream_process(tsb_stream *s, const float *host_in, int64_t in_s
         a.state_ola = s->d_ola;
         a.load_state = s->started ? 1 : 0;
         a.lanes = (int32_t)lanes;
+        a.prev_hop = s->started ? s->last_hop : 0;  // the kept input starts with the previous frame (see below)
+        // positions no frame reaches (hop > frame: the reference emits zeros there, tinyspec.cpp:184-191)
+        if (total > 0) CU(cudaMemset2DAsync(s->d_out, (size_t)s->out_cap * osz, 0, (size_t)total * osz, (size_t)lanes, c->stream));
         int r = tsb_chain_render(c, s->plan, &a);
         if (r) return r;
+        s->st = st_next;
         s->started = true;
+        s->last_hop = hops.back();
         s->frames += (int64_t)fr.size();
         if (total > 0)
             CU(cudaMemcpy2DAsync(host_out, (size_t)out_stride * osz, s->d_out, (size_t)s->out_cap * osz, (size_t)total * osz,

@@ -113,6 +113,8 @@ struct ChainTables {
     double dc_pos, dc_neg;   // arg() the reference obtains for a positive / negative DC bin (see dc_phase())
     // PROG_GAIN
     const real *gain;        // [M+1]    real gain applied to bins k and (N-k)%N
+    // fp32 PV only: the analysis window in double (unscaled), for the exact re-evaluation of doubtful wraps
+    const double *win64;     // [N] or nullptr
 };
 
 // Launch arguments (one lane per CTA).
@@ -144,6 +146,8 @@ struct ChainArgs {
     double *st_warm_phase;     // pre-pass out / main in: [rows][M] last_phase after the warm-up frame (segments with warm-up)
     double *st_inc;            // pre-pass out (or nullptr): [lanes][inc_frames][M] the increment every frame adds to the
     long long inc_frames;      //   phase_sum of every destination bin, frames numbered as in hop_tab / seg_tab
+    int prev_hop;              // load_state launches: hop of the frame before the first one (its samples sit at
+                               // in_off0 - prev_hop of the same rows), 0 = unknown.  Only the fp32 PV reads it (WrapFix).
 };
 
 // What one CTA works on.  A segment that does not start the render begins with the frames whose output overlaps
@@ -159,6 +163,14 @@ struct SegInfo {
 
 template <typename real>
 struct PvMath;
+
+#if !defined(__CUDA_ARCH__)
+// host replay only (tests/emul): [0] doubtful wraps re-evaluated, [1] of them decided the other way than float32
+inline long long *host_wrap_counters() {
+    static long long c[2] = {0, 0};
+    return c;
+}
+#endif
 
 // single-instruction (MUFU) reciprocal / reciprocal square root, ~1 ulp, flush-to-zero
 TSB_HD float fast_rcpf(float x) {
@@ -505,10 +517,26 @@ struct PvMath<double> {
 // accumulates (difference, wrap, increment, running sum, range reduction) stays fp64
 // (SURVEY.md §7 "Twiddles").  inc = ratio*(expect_j + wrapped_delta), which is what
 // pv.hpp:39-48 + the linear shift reduce to algebraically.
+#ifndef TSB_WRAPFIX_INLINE
+#define TSB_WRAPFIX_INLINE __forceinline__
+#endif
+#ifndef TSB_WRAP_K
+#define TSB_WRAP_K 4e-6f   // doubt threshold, in units of sqrt(frame energy)/|X| radians (calibration: DESIGN.md §4.1)
+#endif
+#ifndef TSB_WRAP_C0
+#define TSB_WRAP_C0 4e-6f  // ... plus this many radians (float rounding of the two phases, atan2f error)
+#endif
 template <>
 struct PvMath<float> {
+    // `doubt` (out): the wrapped phase deviation lies so close to +-pi — the boundary where (int)(delta/M_PI) changes
+    // the even multiple of pi it removes (rtlib/pv.hpp:41-43) — that the fp32 transform's phase error (~1e-7 *
+    // sqrt(frame energy) / |X|, plus the float rounding of the two phases) could put it on the other side than
+    // the reference's double arithmetic.  A wrong side adds ratio*2*pi to phase_sum for good: harmless for an
+    // integer ratio, a permanent sign flip of the bin at x1.5.  Doubtful bins are re-evaluated exactly (wrap_fix).
+    // thr = WRAP_K * sqrt(frame energy), see Chain::wrap_threshold.
+    static constexpr float WRAP_K = TSB_WRAP_K, WRAP_C0 = TSB_WRAP_C0;
     static TSB_HD void analyze(int j, cpx<float> X, float &last_phase, const ChainTables<float> &tb, int n,
-                               float &amp, double &inc, bool dc) {
+                               float &amp, double &inc, bool dc, float thr, bool &doubt) {
         (void)n;
         float re = X.x, im = -X.y;
         float pw = fmaf(re, re, im * im);
@@ -530,6 +558,27 @@ struct PvMath<float> {
         else qpd -= qpd & 1;
         double wrapped = fma(-TSB_PI, (double)qpd, delta);
         inc = tb.ratio * (expect + wrapped);
+        const float margin = 3.14159274f - fabsf((float)wrapped);
+        doubt = !dc && margin * amp < fmaf(WRAP_C0, amp, thr);
+    }
+    // The exact side of the wrap from double-precision phases of this frame and the one before (both recomputed
+    // from the input samples by Chain::wrap_fix, expressions of PvMath<double>::analyze), applied to the float32
+    // increment: the value stays the one the float phases give (so that the increments of a bin keep telescoping —
+    // their sum follows phase_f - phase_0 instead of random-walking), only the multiple of 2*pi*ratio is the exact one.
+    static TSB_HD double exact_inc(double expect, double ratio, double inc32, double phase, double last_phase) {
+        double delta = sub_rn(sub_rn(phase, last_phase), expect);
+        int qpd = wrap_quotient(delta);
+        qpd += qpd >= 0 ? (qpd & 1) : -(qpd & 1);
+        double wrapped = fma(-TSB_PI, (double)qpd, delta);
+        const double inc64 = ratio * (expect + wrapped);
+        const double turn = ratio * (2.0 * TSB_PI);
+        if (turn == 0.0) return inc32;
+        const double k = rint((inc32 - inc64) / turn);  // 0 when the float decision was right, else +-1
+#if !defined(__CUDA_ARCH__)
+        host_wrap_counters()[0]++;
+        host_wrap_counters()[1] += k != 0.0;
+#endif
+        return k == 0.0 ? inc32 : inc32 - turn * k;
     }
     static TSB_HD double accumulate(double phase_sum, double inc) { return phase_sum + inc; }
     template <bool FAST = true>
@@ -588,6 +637,8 @@ struct Chain {
     static constexpr int S = (HALF + T - 1) / T;             // pair slots per thread
     static constexpr int PASSES = RadixPlan<LOG2M>::passes;
     static constexpr bool IS_PV = PROG == PROG_PV_SHIFT;
+    // fp32 PV: doubtful principal-argument wraps are re-evaluated in double precision (PvMath<float>::analyze)
+    static constexpr bool WRAP_FIX = IS_PV && sizeof(real) == 4;
     // fp64 synthesis: the table-based branch-free sincos lets the compiler overlap the bins of a thread, which
     // costs registers; with 8 or more bins of state per thread (N >= 4096) that tips the FFT passes into spilling
     // (measured slower than CUDA's sincos there)
@@ -617,6 +668,8 @@ struct Chain {
         // PV amplitude exchange array: fp32 needs its own (the spare FFT buffer is filled by the M fp64
         // increments); in fp64 the spare buffer (16*M bytes) holds both, so nothing extra is reserved.
         real amp_own[(PROG == PROG_PV_SHIFT && sizeof(real) == 4 && !PIPE) ? M : 1];
+        // fp32 PV: energy of the windowed frame (sum of squares), one partial per warp of the forward pass 0
+        float energy[WRAP_FIX ? T / 32 : 1];
     };
     // Per-thread state that lives in registers for the whole launch.
     struct Regs {
@@ -631,6 +684,7 @@ struct Chain {
         // (last_phase is state), a destination without sources stays silent and keeps its phase_sum.
         uint32_t used;
         uint32_t dpair[(S + 1) / 2];  // destination pair of slot i (16 bits each): k of the synthesis side
+        uint32_t doubts;              // WRAP_FIX: doubt bits of the frame just analysed (bit 2 * slot + side)
     };
 
     // Forward pass p writes buf[p & 1] (pass 0 reads the ring), so the packed spectrum ends up in RB.
@@ -834,13 +888,16 @@ struct Chain {
         if (P == 0) {
             const int rb = (int)(in_off & (N - 1));
             const C *wa = reinterpret_cast<const C *>(tb.win_a);
+            real e_acc = 0;  // WRAP_FIX: this thread's share of the windowed frame's energy
             if ((rb & 1) == 0) {
                 const cpx<float> *ring2 = reinterpret_cast<const cpx<float> *>(sm.ring);
                 const int rb2 = rb >> 1;
                 auto in = [&](int a, int c) {
                     cpx<float> q = ring2[(rb2 + a + c) & (M - 1)];
                     C w = TSB_LDG(wa + a + c);
-                    return mk<real>((real)q.x * w.x, (real)q.y * w.y);
+                    C z = mk<real>((real)q.x * w.x, (real)q.y * w.y);
+                    if (WRAP_FIX) e_acc = fmaf(z.x, z.x, fmaf(z.y, z.y, e_acc));
+                    return z;
                 };
                 stockham_pass_io<real, LOG2M, NT, P, decltype(in), decltype(out), TW_DERIVE>(tid, tb.tw, in, out);
             } else {
@@ -849,15 +906,39 @@ struct Chain {
                     float x0 = sm.ring[(rb + 2 * m) & (N - 1)];
                     float x1 = sm.ring[(rb + 2 * m + 1) & (N - 1)];
                     C w = TSB_LDG(wa + m);
-                    return mk<real>((real)x0 * w.x, (real)x1 * w.y);
+                    C z = mk<real>((real)x0 * w.x, (real)x1 * w.y);
+                    if (WRAP_FIX) e_acc = fmaf(z.x, z.x, fmaf(z.y, z.y, e_acc));
+                    return z;
                 };
                 stockham_pass_io<real, LOG2M, NT, P, decltype(in), decltype(out), TW_DERIVE>(tid, tb.tw, in, out);
             }
+            if (WRAP_FIX) energy_store(tid, sm, (float)e_acc);
         } else {
             const C *src = sm.buf[(P - 1) & 1];
             auto in = [&](int a, int c) { return ld_sw(src, a, c); };
             stockham_pass_io<real, LOG2M, NT, P, decltype(in), decltype(out), TW_DERIVE>(tid, tb.tw, in, out);
         }
+    }
+    // Warp-shuffle reduction of the per-thread energy shares; lane 0 of every warp of the pass keeps the warp's sum.
+    // (Host replay: threads run one after the other, the first lane of a warp starts the sum.)
+    static TSB_HD void energy_store(int tid, Smem &sm, float e) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+        if ((tid & 31) == 0) sm.energy[tid >> 5] = e;
+#else
+        if ((tid & 31) == 0) sm.energy[tid >> 5] = e;
+        else sm.energy[tid >> 5] += e;
+#endif
+    }
+    // WRAP_K * sqrt(energy of the windowed frame): the doubt threshold of PvMath<float>::analyze.  NW = warps that ran
+    // forward pass 0 (their partial sums; the window table carries 1/sqrt(N), so sqrt(energy) is the RMS bin magnitude).
+    template <int NT>
+    static TSB_HD float wrap_threshold(const Smem &sm) {
+        float e = 0;
+#pragma unroll
+        for (int w = 0; w < (NT + 31) / 32; w++) e += sm.energy[w];
+        return PvMath<float>::WRAP_K * (e * fast_rsqrtf(fmaxf(e, 1e-37f)));  // sqrt(e), one MUFU, no slow-path call
     }
 
     // spectrum of the real frame at bins k and M-k (k != 0) from the packed transform Zc (see file header)
@@ -892,16 +973,134 @@ struct Chain {
     // slot (half of a thread's transcendental work when it owns two slots).
     static TSB_HD bool is_special(int i, int k) { return i == 0 && k == 0; }
 
+    // ------------------------------------------------------------------ fp32 PV: exact wraps for doubtful bins
+    // What the frame being analysed follows (WRAP_FIX): hop of the frame before it (>= 0: its samples start that many
+    // before this frame's), PH_ZERO: none — last_phase is the exact zero of a reset PhaseVocoder, PH_UNKNOWN: not known
+    // (a continued render without ChainArgs::prev_hop; a warm-up frame, whose increments nobody uses): no fix.
+    static constexpr int PH_ZERO = -1, PH_UNKNOWN = -2;
+    // Partial sums over n = l, l + NL, ... of the frft(+1) bin j (kernel e^{+2 pi i j n / N}) of the windowed frames
+    // starting at input offsets off_c and off_p, in double precision straight from the float32 input rows.
+    static TSB_HD void dft_bin_partial(const float *src, long long in_len, const double *win64, long long off_c,
+                                       long long off_p, int j, int l, int NL, double &rc, double &ic, double &rp, double &ip) {
+        auto unit = [](int q, double &c, double &sn) {  // e^{2 pi i q / N}, q reduced mod N (table-based, no slow-path call)
+            fast_sincos((double)(q & (N - 1)) * (2.0 * TSB_PI / (double)N), sn, c);
+        };
+        double wx, wy, sx, sy;
+        unit(j * l, wx, wy);
+        unit(j * NL, sx, sy);
+        rc = ic = rp = ip = 0.0;
+        for (int n = l; n < N; n += NL) {
+            const double wv = TSB_LDG(&win64[n]);
+            const long long sc = off_c + n, sp = off_p + n;
+            const double xc = (sc >= 0 && sc < in_len) ? (double)src[sc] * wv : 0.0;
+            const double xp = (sp >= 0 && sp < in_len) ? (double)src[sp] * wv : 0.0;
+            rc = fma(xc, wx, rc);
+            ic = fma(xc, wy, ic);
+            rp = fma(xp, wx, rp);
+            ip = fma(xp, wy, ip);
+            const double nx = wx * sx - wy * sy;
+            wy = fma(wx, sy, wy * sx);
+            wx = nx;
+        }
+    }
+    // bin index of doubt bit b of the thread `stid`: slot b >> 1, side b & 1 (k or M - k; thread 0 slot 0: 0 / M/2)
+    static TSB_HD int doubt_bin(int stid, int b) {
+        const int i = b >> 1, k = stid + T * i;
+        return (b & 1) ? (is_special(i, k) ? HALF : M - k) : k;
+    }
+    // Every thread of the warp calls wrap_fix at the end of the analysis phase with the doubt bits of its own bins.
+    // When the warp has any, it takes them one by one: all lanes sum a share of the two direct DFTs, a shuffle
+    // reduction brings them together, and the owning lane replaces the bin's increment by the exact one.  The slow
+    // path is a real function call (not inlined, scalars by value) so that it costs the frame loop no registers.
+    struct WrapFixArgs {
+        const float *src;      // this lane's input row
+        long long in_len, cur_off, prev_off;
+        const double *win64;
+        double *inc_x;
+        double hop, inv_n, ratio;
+        int ph;
+    };
+#if defined(__CUDA_ARCH__)
+    static __device__ TSB_WRAPFIX_INLINE void wrap_fix_slow(int tid, uint32_t doubts, WrapFixArgs w) {
+        unsigned any = __ballot_sync(0xffffffffu, doubts != 0);
+        while (any) {
+            const int sl = __ffs(any) - 1;
+            any &= any - 1;
+            uint32_t fm = __shfl_sync(0xffffffffu, doubts, sl);
+            const int stid = (tid & ~31) | sl;
+            while (fm) {
+                const int b = __ffs(fm) - 1;
+                fm &= fm - 1;
+                const int j = doubt_bin(stid, b);
+                double v[4];
+                dft_bin_partial(w.src, w.in_len, w.win64, w.cur_off, w.prev_off, j, tid & 31, 32, v[0], v[1], v[2], v[3]);
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+                if ((tid & 31) == sl) {
+                    const double expect = mul_rn(mul_rn((double)(2 * j), TSB_PI), w.hop) * w.inv_n;  // expected_advance
+                    w.inc_x[j] = PvMath<float>::exact_inc(expect, w.ratio, w.inc_x[j], fast_atan2(v[1], v[0]),
+                                                          w.ph >= 0 ? fast_atan2(v[3], v[2]) : 0.0);
+                }
+            }
+        }
+    }
+#endif
+    static TSB_HD void phase_wrap_fix(int tid, int lane, Smem &sm, Regs &rg, const Tables &tb, const ChainArgs &a,
+                                      long long cur_off, int ph) {
+        uint32_t doubts = rg.doubts;
+#if defined(__CUDA_ARCH__)
+        if (!__any_sync(0xffffffffu, doubts != 0)) return;
+#else
+        if (!doubts) return;
+#endif
+        WrapFixArgs w;
+        w.src = a.in + (long long)lane * a.in_stride;
+        w.in_len = a.in_len;
+        w.cur_off = cur_off;
+        w.prev_off = ph >= 0 ? cur_off - ph : cur_off;
+        w.win64 = tb.win64;
+        w.inc_x = xch_inc(sm);
+        w.hop = tb.hop;
+        w.inv_n = tb.inv_n;
+        w.ratio = tb.ratio;
+        w.ph = ph;
+#if defined(__CUDA_ARCH__)
+        wrap_fix_slow(tid, doubts, w);
+#else
+        while (doubts) {
+            int b = 0;
+            while (!((doubts >> b) & 1)) b++;
+            doubts &= doubts - 1;
+            const int j = doubt_bin(tid, b);
+            double v[4] = {0, 0, 0, 0};
+            for (int l = 0; l < 32; l++) {
+                double q[4];
+                dft_bin_partial(w.src, w.in_len, w.win64, w.cur_off, w.prev_off, j, l, 32, q[0], q[1], q[2], q[3]);
+                for (int u = 0; u < 4; u++) v[u] += q[u];
+            }
+            w.inc_x[j] = PvMath<float>::exact_inc(expected_advance(j, tb), w.ratio, w.inc_x[j], fast_atan2(v[1], v[0]),
+                                                  w.ph >= 0 ? fast_atan2(v[3], v[2]) : 0.0);
+        }
+#endif
+    }
+
     // ------------------------------------------------------------------ PV phase C: split + analysis
     // (rtlib/pv.hpp:17-28 over the live bins 0..N/2-1; results go to the exchange arrays)
     // `all`: analyse every bin (last frame of a launch, warm-up frame); otherwise only the sources the shift uses.
     // Slots are taken two at a time and their k-side bins analysed together, then their (M-k)-side bins: an upward
     // shift drops the upper sources, i.e. the (M-k) side of most pairs, and this grouping lets a thread skip them
     // while the two bins it does analyse still overlap.
-    static TSB_HD void phase_pv_analyze(int tid, Smem &sm, Regs &rg, const Tables &tb, bool all) {
+    // lane / a / cur_off / ph: what wrap_fix needs (fp32 only); NT0 = threads that ran forward pass 0.
+    // Returns true when this thread found a doubtful wrap (fp32 only): the caller then runs phase_wrap_fix.
+    static TSB_HD bool phase_pv_analyze(int tid, Smem &sm, Regs &rg, const Tables &tb, bool all, bool fix) {
         const C *Zc = fwd_result(sm);
         double *inc_x = xch_inc(sm);
         real *amp_x = xch_amp(sm);
+        float thr = 0.f;
+        uint32_t doubts = 0;
+        if constexpr (WRAP_FIX) thr = wrap_threshold<PIPE ? T0 : T>(sm);
         auto split_slot = [&](int i, int k, C &Xa, C &Xb) {
             if (i == 0) {
                 const bool sp = is_special(i, k);
@@ -913,28 +1112,37 @@ struct Chain {
                 split_pair(Zc, tb, k, Xa, Xb);
             }
         };
-        auto analyze_bin = [&](int j, C X, real &last_phase, bool dc) {
+        // dbit: this bin's bit in `doubts` (2 * slot + side)
+        auto analyze_bin = [&](int j, C X, real &last_phase, bool dc, int dbit) {
             real amp;
             double inc;
-            PvMath<real>::analyze(j, X, last_phase, tb, N, amp, inc, dc);
+            if constexpr (sizeof(real) == 4) {
+                bool doubt;
+                PvMath<real>::analyze(j, X, last_phase, tb, N, amp, inc, dc, thr, doubt);
+                if (WRAP_FIX) doubts |= (uint32_t)doubt << dbit;
+            } else {
+                (void)dbit;
+                PvMath<real>::analyze(j, X, last_phase, tb, N, amp, inc, dc);
+            }
             amp_x[j] = (real)0.5 * amp;  // Y[k >= N/2] = 0 after shift, so Z = conj(Y)/2: exact scaling, done here
             inc_x[j] = inc;
         };
         if constexpr (S == 1) {
             int k = tid;
-            if (HALF % T != 0 && k >= HALF) return;
             const bool sp = is_special(0, k);
-            const bool need_a = all || (rg.used & 1u), need_b = all || (rg.used & 2u);
-            if (!need_a && !need_b) return;
-            C Xa, Xb;
-            split_slot(0, k, Xa, Xb);
-            if (need_a && need_b) {  // (one pair per thread: the two bins overlap only when both are wanted)
-                analyze_bin(k, Xa, rg.last_phase[0], sp);
-                analyze_bin(sp ? HALF : M - k, Xb, rg.last_phase[1], false);
-            } else if (need_a) {
-                analyze_bin(k, Xa, rg.last_phase[0], sp);
-            } else {
-                analyze_bin(sp ? HALF : M - k, Xb, rg.last_phase[1], false);
+            const bool in_range = !(HALF % T != 0 && k >= HALF);
+            const bool need_a = in_range && (all || (rg.used & 1u)), need_b = in_range && (all || (rg.used & 2u));
+            if (need_a || need_b) {
+                C Xa, Xb;
+                split_slot(0, k, Xa, Xb);
+                if (need_a && need_b) {  // (one pair per thread: the two bins overlap only when both are wanted)
+                    analyze_bin(k, Xa, rg.last_phase[0], sp, 0);
+                    analyze_bin(sp ? HALF : M - k, Xb, rg.last_phase[1], false, 1);
+                } else if (need_a) {
+                    analyze_bin(k, Xa, rg.last_phase[0], sp, 0);
+                } else {
+                    analyze_bin(sp ? HALF : M - k, Xb, rg.last_phase[1], false, 1);
+                }
             }
         } else {
 #pragma unroll
@@ -949,17 +1157,23 @@ struct Chain {
                 split_slot(i, k0, Xa0, Xb0);
                 if (two) split_slot(i + 1, k1, Xa1, Xb1);
                 if (need_a) {
-                    analyze_bin(k0, Xa0, rg.last_phase[2 * i], sp);
-                    if (two) analyze_bin(k1, Xa1, rg.last_phase[2 * i + 2], false);
+                    analyze_bin(k0, Xa0, rg.last_phase[2 * i], sp, 2 * i);
+                    if (two) analyze_bin(k1, Xa1, rg.last_phase[2 * i + 2], false, 2 * i + 2);
                 }
                 if (need_b) {
-                    analyze_bin(sp ? HALF : M - k0, Xb0, rg.last_phase[2 * i + 1], false);
-                    if (two) analyze_bin(M - k1, Xb1, rg.last_phase[2 * i + 3], false);
+                    analyze_bin(sp ? HALF : M - k0, Xb0, rg.last_phase[2 * i + 1], false, 2 * i + 1);
+                    if (two) analyze_bin(M - k1, Xb1, rg.last_phase[2 * i + 3], false, 2 * i + 3);
                 }
             }
             sched_fence();
         }
         }
+        if constexpr (WRAP_FIX) {
+            if (!fix) doubts = 0;
+            rg.doubts = doubts;
+            return doubts != 0;
+        }
+        return false;
     }
     // shift gather for destination bin k (rtlib/pv.hpp:70-78: amplitudes add in ascending source
     // order, the frequency of the last source wins; bins with no source are silent with freq 0).
@@ -1246,6 +1460,7 @@ TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const t
     constexpr bool prepass = PREPASS && CH::IS_PV;
     bool warm;
     int warm_hop;
+    int ph = 0;  // hop of the frame before the one being analysed (or a PH_* code)
     long long first_own;
     {
         SegInfo sg = seg_info<CH>(a, lane, seg);
@@ -1258,12 +1473,30 @@ TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const t
         own = (int)sg.n_frames - sg.lead;
         ff_first = -sg.lead - (warm ? 1 : 0);
         hop_tab = a.hop_tab ? a.hop_tab + first_own : nullptr;  // indexed by ff below (the warm-up frame has warm_hop)
+        // what the first analysed frame follows (CH::WRAP_FIX, see Chain::PH_ZERO): the warm-up frame of a segment,
+        // nothing (a fresh PhaseVocoder), or the caller's previous frame
+        if (warm) ph = CH::PH_UNKNOWN;  // the warm-up frame itself: its increments are not used
+        else if (sg.warm) ph = sg.warm_hop;
+        else if (!a.load_state) ph = CH::PH_ZERO;
+        else ph = a.prev_hop > 0 ? a.prev_hop : CH::PH_UNKNOWN;
         ex.each([&](int tid, Regs &rg) {
             CH::load_state(tid, sm, rg, tb, a, sg);
             CH::ring_fill(tid, lane, sm, a, in_off, N);
             CH::ring_wait();
         });
     }
+    // PV analysis of the frame at input offset `off`.  fp32: the barrier that ends the phase also tells whether any
+    // thread met a doubtful wrap; if so (about one frame in 50 for noisy input) an extra phase re-evaluates those bins
+    // exactly before the synthesis reads the increments.
+    auto analyze_frame = [&](bool all, long long off, int prev) {
+        if constexpr (CH::WRAP_FIX) {
+            const bool fix = tb.win64 != nullptr && prev != CH::PH_UNKNOWN;
+            if (ex.each_or([&](int tid, Regs &rg) { return CH::phase_pv_analyze(tid, sm, rg, tb, all, fix); }))
+                ex.each([&](int tid, Regs &rg) { CH::phase_wrap_fix(tid, lane, sm, rg, tb, a, off, prev); });
+        } else {
+            ex.each([&](int tid, Regs &rg) { CH::phase_pv_analyze(tid, sm, rg, tb, all, false); });
+        }
+    };
     if (CH::PIPE && !prepass) {
         // frame f: [analyse f][synthesise f][inverse passes of f  ||  forward passes of f+1]; the forward passes of
         // the first frame run alone as a prologue.  `hop_of(f)` = samples emitted after frame f.
@@ -1280,7 +1513,8 @@ TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const t
             const int hop = hop_of(ff);
             if (CH::IS_PV) {
                 const bool all = ff + 1 == own;  // last_phase is state: the last frame of a launch analyses every bin
-                ex.each([&](int tid, Regs &rg) { CH::phase_pv_analyze(tid, sm, rg, tb, all); });
+                analyze_frame(all, in_off, ph);
+                if (CH::WRAP_FIX) ph = hop;
                 ex.each([&](int tid, Regs &rg) {
                     CH::phase_pv_synth(tid, sm, rg, tb);
                     CH::ring_wait();  // next frame's samples (requested a frame ago) are in the ring after this barrier
@@ -1320,7 +1554,8 @@ TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const t
         FwdPasses<CH, 0, CH::PASSES>::run(ex, lane, sm, tb, a, in_off, first, cnt);
         if (CH::IS_PV) {
             const bool all = is_warm || ff + 1 == own;
-            ex.each([&](int tid, Regs &rg) { CH::phase_pv_analyze(tid, sm, rg, tb, all); });
+            analyze_frame(all, in_off, ph);
+            if (CH::WRAP_FIX) ph = hop;
             if (prepass) {
                 if (is_warm) {
                     if (a.st_warm_phase) {

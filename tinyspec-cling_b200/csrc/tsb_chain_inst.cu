@@ -24,6 +24,11 @@ struct DevExec {
         f((int)threadIdx.x, rg);
         __syncthreads();
     }
+    // same, and tells every thread whether f returned true for any of them
+    template <class F>
+    __device__ __forceinline__ bool each_or(F f) {
+        return __syncthreads_or(f((int)threadIdx.x, rg) ? 1 : 0) != 0;
+    }
 };
 
 // Resident CTAs per SM the kernel is compiled for: what shared memory allows (227 KB, 1 KB reserved per
@@ -43,8 +48,14 @@ template <class CH>
 constexpr int default_carveout_kb() { return 228; }
 
 // PREPASS: the time-parallel pre-pass (ChainArgs::mode == 1: analysis and per-frame increments only)
+// The fp32 pre-pass carries the exact-wrap phase (Chain::phase_wrap_fix) in its plain frame loop; one CTA less per
+// SM gives it the registers to do so without spilling (the pre-pass is latency-bound on its barriers either way).
+template <class CH, bool PREPASS>
+constexpr int kernel_blocks() {
+    return (PREPASS && CH::WRAP_FIX && min_blocks<CH>() > 2) ? min_blocks<CH>() - 1 : min_blocks<CH>();
+}
 template <typename real, int LOG2N, int PROG, bool OUT32, bool PREPASS>
-__global__ void __launch_bounds__(Chain<real, LOG2N, PROG, OUT32>::T, min_blocks<Chain<real, LOG2N, PROG, OUT32>>())
+__global__ void __launch_bounds__(Chain<real, LOG2N, PROG, OUT32>::T, kernel_blocks<Chain<real, LOG2N, PROG, OUT32>, PREPASS>())
 chain_kernel(const ChainTables<real> tb, const ChainArgs a) {
     using CH = Chain<real, LOG2N, PROG, OUT32>;
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -44,6 +44,7 @@ template <typename real>
 struct HostTables {
     std::vector<cpx<real>> tw, twn;
     std::vector<real> win_a, win_s, gain;
+    std::vector<double> win64;  // fp32 PV: the analysis window in double (ChainTables::win64)
     std::vector<uint32_t> map;
     std::vector<uint16_t> map_src;
     std::vector<int16_t> map1;  // empty unless every destination has at most one source
@@ -70,6 +71,7 @@ struct HostTables {
         t.dc_pos = dc_pos;
         t.dc_neg = dc_neg;
         t.gain = gain.data();
+        t.win64 = win64.empty() ? nullptr : win64.data();
         return t;
     }
 };
@@ -93,6 +95,7 @@ HostTables<real> build_tables(const PlanDesc &d) {
         h.win_s.resize(n);
         for (int i = 0; i < n; i++) h.win_s[i] = (real)(ws[i] / sqrtn);
     }
+    if (sizeof(real) == 4 && d.program == PROG_PV_SHIFT) h.win64 = wa;
     h.hop = d.hop;
     h.rate = d.rate;
     h.ratio = d.ratio;

@@ -168,6 +168,7 @@ struct Renderer {
     DevBuf d_in, d_out, d_hops, d_last, d_sum, d_ola;
     std::map<std::string, tsb_plan *> plans;
     bool state_valid = false;
+    int32_t last_hop = 0;  // computed_hop of the last frame rendered so far
     const void *state_pv = nullptr;
     int state_epoch = -1;
     uint32_t state_n = 0;
@@ -246,12 +247,20 @@ struct Renderer {
             check(tsb_plan_create(rt.context(), &d, &plan), "tsb_plan_create");
         }
         // state: PhaseVocoder::resize / reset zero it (rtinc/pv.hpp:23-35); a size change also drops it
-        bool keep_pv = state_valid && state_pv == k.pv && state_epoch == k.pv_epoch && state_n == n;
+        // (reset(last, sum) zeroes only what it names, rtinc/pv.hpp:32-35; a resize zeroes both)
+        const bool same_pv = state_valid && state_pv == k.pv && state_n == n;
+        bool zero_last = !same_pv, zero_sum = !same_pv;
+        PhaseVocoder *pvp = (PhaseVocoder *)k.pv;
+        if (same_pv && state_epoch != k.pv_epoch) {
+            zero_last = pvp->_reset_last;
+            zero_sum = pvp->_reset_sum;
+        }
+        if (pvp) pvp->_reset_last = pvp->_reset_sum = false;
         bool keep_ola = state_valid && state_n == n;
         if (state_valid && state_n != n) fatal("frame size changed from " + std::to_string(state_n) + " to " + std::to_string(n) +
                                                " mid-render: fused mode needs a constant frame size, use --mode immediate");
-        d_last.ensure(lanes * (n / 2) * 8, !keep_pv);
-        d_sum.ensure(lanes * (n / 2) * 8, !keep_pv);
+        d_last.ensure(lanes * (n / 2) * 8, zero_last);
+        d_sum.ensure(lanes * (n / 2) * 8, zero_sum);
         d_ola.ensure(lanes * n * 8, !keep_ola);
         tsb_chain_args a;
         memset(&a, 0, sizeof a);
@@ -277,6 +286,9 @@ struct Renderer {
         a.state_ola = (double *)d_ola.d;
         a.load_state = 1;  // arrays were zeroed above when the state does not carry over
         a.lanes = (int32_t)lanes;
+        // the frame before this run (its samples are in the same rows): lets the float32 chain decide doubtful wraps exactly
+        a.prev_hop = (same_pv && !zero_last) ? last_hop : 0;
+        last_hop = p.hops.back();
         // A few lanes cannot fill the GPU frame after frame (a lane is one CTA walking its frames in order): cut the
         // run into concurrent time segments instead — samples and PV state bit-identical to the sequential launch.
         const int64_t frames_run = (int64_t)p.hops.size();
@@ -324,6 +336,10 @@ struct Renderer {
             if (!classify(rt.trace, &audio_in, &audio_out, k, why)) fatal(why + ": use --mode immediate");
             k.n = (uint32_t)window_size;
             if (k.pv) k.pv_epoch = ((const PhaseVocoder *)k.pv)->_state_epoch;
+            if (queues_cleared && frames > 0)
+                fatal("set_num_channels mid-render drops the queued input (rtlib/control.hpp:56-57): how much that is depends on "
+                      "the audio period, which an offline render does not have; call it before the first frame");
+            queues_cleared = false;
             if (nch_in != nch_out) fatal("fused chains need as many output as input channels");
             if (audio_out.size != window_size || audio_out.num_channels != nch_out) fatal("fused chains need out to keep the frame's shape");
             if (!(k == pend.key)) {

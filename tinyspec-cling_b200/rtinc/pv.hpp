@@ -35,6 +35,7 @@ struct PhaseVocoder {
             last_phase.resize(num_channels, size);
             phase_sum.resize(num_channels, size);
             _state_epoch++;
+            _reset_last = _reset_sum = true;
         }
     }
     void reset(bool last = true, bool sum = true) {

@@ -37,7 +37,8 @@ want = ref["ola64"][:F * hop].T
 peak = np.abs(want).max()
 res = {"seconds": args.seconds, "ratio": args.ratio, "frames": F, "oracle_cpu_s": t_cpu,
        "max_phase_sum_rad": float(np.abs(ref["phase_sum"]).max())}
-for name, precision, nseg in (("f64", "f64", 0), ("f64_timepar_592seg", "f64", 592), ("f32", "f32", 0)):
+for name, precision, nseg in (("f64", "f64", 0), ("f64_timepar_592seg", "f64", 592), ("f32", "f32", 0),
+                              ("f32_timepar_592seg", "f32", 592)):
     plan = tsb200.Plan(ctx, n, precision=precision, program="pv", hop=hop, ratio=args.ratio)
     st = {k: torch.zeros((ch, w), dtype=torch.float64, device="cuda") for k, w in
           (("last_phase", n // 2), ("phase_sum", n // 2), ("ola", n))}
