@@ -214,7 +214,10 @@ def main():
     ap.add_argument("--e2e-out", default="f32", choices=["f32", "f64"],
                     help="sample type the end-to-end leg returns to the host: the reference's float32 stream (default) "
                          "or, in fp64 mode, the unrounded float64 accumulation")
-    ap.add_argument("--no-extras", action="store_true", help="skip the secondary figures (other precision, single stream)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary figures (other precision, single stream, "
+                                                             "time-sharded cfg3, cfg5)")
+    ap.add_argument("--ts-seconds", type=float, default=600.0,
+                    help="audio seconds of the time-sharded cfg3 render (BASELINE configs[2] is 3600 s; 0 = skip)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -329,12 +332,19 @@ def main():
     state_bytes = lanes * (N_FRAME // 2) * 8 * 2 * 2 * 0  # state arrays are not passed in the bench (reset start)
     alg_bytes_launch = S * F * CH * balg + state_bytes
     achieved = alg_bytes_launch / (ms_step * 1e-3) / 1e9
-    traffic = None
+    # per-launch DRAM traffic and executed arithmetic of this kernel from the committed `ncu --set full` capture of the
+    # same launch shape (profiles/ncu_traffic.json: what was measured, how, from which report)
+    traffic, flops_fc, ncu_src = None, None, None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
         tj = json.load(open(tp)).get(args.precision)
         if tj:
             traffic = tj["dram_bytes_per_frame_channel"] * S * F * CH
+            flops_fc = tj.get("flops_per_frame_channel")
+            ncu_src = tj.get("source")
+    # compute-side roofline: the kernel is issue/arithmetic-bound, so its executed flops (ncu's per-opcode counts: FMA = 2)
+    # are reported against the device's measured FMA rate in the same type
+    fma_peak = ctx.fma_peak(args.precision)
 
     line = {"metric": "stft_pv_istft_frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -344,7 +354,13 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_frame_channel": balg,
                          "kernel": "tsb::chain_kernel<" + ("double" if args.precision == "f64" else "float") + ",10,PV>",
-                         "note": "the fused chain is issue/latency-bound, not HBM-bound (SURVEY.md §7 hard part 1); "
+                         "compute_peak_tflops": fma_peak,
+                         "compute_peak_source": "measured here: tsb_probe_fma_peak (independent " + args.precision + " FMA chains, CUDA events)",
+                         "compute_achieved_tflops": None if flops_fc is None else flops_fc * fcs / world / 1e12,
+                         "compute_frac": None if flops_fc is None else flops_fc * fcs / world / 1e12 / fma_peak,
+                         "flops_per_frame_channel": flops_fc, "ncu_source": ncu_src,
+                         "note": "the fused chain is issue/latency-bound, not HBM-bound (SURVEY.md §7 hard part 1): "
+                                 "compute_frac (executed flops / measured FMA peak) is the yardstick that applies; "
                                  "see profiles/ for the ncu SOL"},
             "clocks": clocks, "gpu_launches": launches}
 
@@ -360,10 +376,29 @@ def main():
         xh.copy_(x)
         oh = torch.empty((lanes, F * HOP), dtype=plan.out_dtype, pin_memory=True)
         torch.cuda.empty_cache()
-        plan.render_host(xh, F, HOP, out=oh)  # warm-up
+        # the floor: the bare copies of the same buffers, both directions at once, nothing else (every rank at the
+        # same time: with several ranks the host's memory and PCIe complex are shared)
+        xd2 = torch.empty((lanes, L), dtype=torch.float32, device=dev)
+        od2 = torch.empty((lanes, F * HOP), dtype=plan.out_dtype, device=dev)
+        s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+        floor = []
+        for i in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            with torch.cuda.stream(s_up):
+                xd2.copy_(xh, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                oh.copy_(od2, non_blocking=True)
+            torch.cuda.synchronize()
+            floor.append((time.perf_counter() - t0) * 1e3)
+        floor_ms = max_over_ranks(min(floor[1:]))
+        del xd2, od2
+        torch.cuda.empty_cache()
+        for _ in range(2):
+            plan.render_host(xh, F, HOP, out=oh)  # warm-up
         barrier()
         t0 = time.perf_counter()
-        esteps = max(1, min(args.steps, 2))
+        esteps = max(1, args.steps)
         for _ in range(esteps):
             plan.render_host(xh, F, HOP, out=oh)
         barrier()
@@ -372,6 +407,10 @@ def main():
                        "d2h_bytes_per_step": lanes * F * HOP * oh.element_size(), "ms_per_step": ems, "steps": esteps,
                        "out_dtype": str(oh.dtype).replace("torch.", ""), "arithmetic": args.precision,
                        "host_cpus_bound": len(bound) if bound else None,
+                       "copy_floor_ms": floor_ms,
+                       "copy_floor_gbs_per_gpu": (lanes * L * 4 + lanes * F * HOP * oh.element_size()) / floor_ms / 1e6,
+                       "copy_floor_note": "the same pinned buffers copied up and down concurrently with nothing else, all "
+                                          "ranks at once (max over ranks): what the host/PCIe side allows",
                        "api": "tsb_chain_render_host (pinned host buffers; upload + kernel + download inside the timed region)"}
         del oh, xh
         ctx.trim()  # the context keeps the staging rows between calls: release them for the legs below
@@ -399,6 +438,13 @@ def main():
             line["single_stream"] = {"value": F / (e0.elapsed_time(e1) / 3 * 1e-3), "unit": "frames/s",
                                      "note": f"BASELINE configs[0] as is: ONE stereo 60 s stream (2 lanes), rendered as {nseg} "
                                              "concurrent time segments (tsb_chain_render_timepar: pre-pass + scan + main; bit-identical to the sequential render)"}
+    # ---- BASELINE configs[2] in small: ONE long 8-channel render split by time segment across the ranks ----
+    if not args.no_extras and args.ts_seconds > 0:
+        del x, x_all
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import cfg3_timeshard
+        line["time_sharded"] = cfg3_timeshard.run(dist, rank, world, dev, ctx, seconds=args.ts_seconds, precision="f64")
     # ---- CPU baseline: rank 0, N=1 only, bounded sample ----
     if rank == 0 and world == 1:
         frames, wall, kind, what, used = run_reference(1, min(args.seconds, 60.0))

@@ -131,6 +131,10 @@ typedef struct tsb_chain_args {
 } tsb_chain_args;
 int tsb_chain_render(tsb_ctx *ctx, tsb_plan *plan, const tsb_chain_args *args);
 
+/* Measurement aid: the device's measured non-tensor FMA rate in TFLOP/s (an FMA = 2 flops), fp64 or fp32, from a
+ * kernel of independent FMA chains timed with CUDA events.  bench.py reports the chain kernel's arithmetic against it. */
+int tsb_probe_fma_peak(tsb_ctx *ctx, int32_t is_f64, double *tflops);
+
 /* Same, with HOST buffers (in, out, hop_tab, state_* are host pointers): returns when the result is in `out`.
  * Large batches are cut into lane chunks whose upload, chain kernel and download overlap (separate copy engines
  * per direction, one stream per chunk); per-lane results are bit-identical to tsb_chain_render.  Pinned host
@@ -154,16 +158,19 @@ int tsb_chain_render_host(tsb_ctx *ctx, tsb_plan *plan, const tsb_chain_args *ar
  * Samples, phase_sum / last_phase and the final overlap tail are bit-identical to tsb_chain_render's, in every
  * precision (the float32 tail arithmetic of TSB_F64_OUT32 included).  Cost: the lead-in frames are rendered twice.
  * This is what lets ONE long stream fill a GPU, and what a multi-GPU time split is built from: rank g renders a
- * block of frames (its input must start one warm-up frame earlier: `warmup` = 1 and args->in_off0 - warm_hop >= 0),
- * pre-passes it, takes the running phase_sum from rank g-1 (tsb_timepar_scan: carry in, carry out — a chain of
- * short steps over the ranks), renders, and hands its final overlap tail (state_ola) to rank g+1, which adds it at
- * the head of its output with tsb_add_tail (the first segment of a block has no lead-in frames: across blocks the
- * samples after the boundary meet their addends in another order, ~1 ulp).  Scratch: lanes * n_frames * n/2 doubles
- * for the stored increments. */
+ * block of frames that begins with its own `lead` lead-in frames — the frames of the block before whose output
+ * reaches into its first own frame — and one warm-up frame before those (`warmup` = 1, args->in_off0 - warm_hop
+ * >= 0; args->in_off0 / out_off0 / n_frames / hop_tab describe the block INCLUDING the lead-in frames, which emit
+ * nothing).  It pre-passes the block, takes the running phase_sum before its first lead-in frame from rank g-1
+ * (tsb_timepar_scan_at: carry in, carry out at a frame of its choice — a chain of short steps over the ranks) and
+ * renders: the lead-in frames rebuild the overlap tail the block starts with, so nothing but that carry crosses a
+ * block boundary and the stitched output is the one-GPU render bit for bit.  (With lead = 0 a block's first
+ * samples lack the previous block's tail: tsb_add_tail adds another block's final state_ola, ~1 ulp from the
+ * sequential order.)  Scratch: lanes * n_frames * n/2 doubles for the stored increments. */
 typedef struct tsb_timepar tsb_timepar;
 /* args is copied (device pointers must stay valid); host_hop_tab = host copy of args->hop_tab (NULL iff hop_tab is NULL) */
 int tsb_timepar_create(tsb_ctx *ctx, tsb_plan *plan, const tsb_chain_args *args, const int32_t *host_hop_tab,
-                       int32_t n_segments, int32_t warmup, int32_t warm_hop, tsb_timepar **tp);
+                       int32_t n_segments, int32_t warmup, int32_t warm_hop, int32_t lead, tsb_timepar **tp);
 int tsb_timepar_segments(tsb_timepar *tp);   /* segments actually used (each must emit at least n samples) */
 /* block_total (the block's increments summed from zero) / block_last_phase: device [lanes][n/2] float64, may be NULL */
 int tsb_timepar_prepass(tsb_timepar *tp, double *block_total, double *block_last_phase);
@@ -174,6 +181,10 @@ int tsb_timepar_scan(tsb_timepar *tp, const double *carry_in, double *carry_out)
 /* The same for lanes lane0 .. lane0+n_lanes-1 only (carry_in / carry_out: [n_lanes][n/2]): lanes are independent, so
  * a chain of ranks can hand the sums on lane by lane and overlap their scans.  The caller covers every lane. */
 int tsb_timepar_scan_lanes(tsb_timepar *tp, int32_t lane0, int32_t n_lanes, const double *carry_in, double *carry_out);
+/* The same with carry_out = the phase_sum BEFORE frame `carry_frame` of the block (0 <= carry_frame < n_frames; the
+ * first lead-in frame of the next rank's block), instead of after its last frame (carry_frame < 0). */
+int tsb_timepar_scan_at(tsb_timepar *tp, int32_t lane0, int32_t n_lanes, const double *carry_in, double *carry_out,
+                        int64_t carry_frame);
 /* initial state = args->state_* (NULL or load_state 0: reset state); they receive the final state */
 int tsb_timepar_render(tsb_timepar *tp);
 int tsb_timepar_destroy(tsb_timepar *tp);

@@ -101,58 +101,56 @@ class ReplayBackend:
     """CPU stand-in for the device side of tinyspec-cling_b200/shard.py (kernel phases replayed thread by thread),
     so the multi-rank orchestration can be tested with gloo in a container without a GPU."""
 
-    def __init__(self, n, hop, ratio, precision="f64", rate=48000.0):
-        self.n, self.hop, self.ratio, self.precision, self.rate = n, hop, ratio, precision, rate
+    def __init__(self, n, hop_d, ratio, precision="f64", rate=48000.0):
+        self.n, self.hop_d, self.ratio, self.precision, self.rate = n, hop_d, ratio, precision, rate
 
-    def _call(self, x, n_frames, in_off0, out_len, mode, warm, state, warm_phase, load, inc=None):
+    def _call(self, out_len, mode, state, inc=None):
+        b, x = self._b, self._x
         lanes, L = x.shape
+        ht = b["hop_tab"]
         dt = np.float64 if self.precision == "f64" else np.float32
         out = np.zeros((lanes, max(out_len, 1)), dt)
-        r = lib().emul_chain_render_ex(1 if self.precision == "f64" else 0, int(np.log2(self.n)), 0, 2, 2, float(self.hop),
+        r = lib().emul_chain_render_ex(1 if self.precision == "f64" else 0, int(np.log2(self.n)), 0, 2, 2, float(self.hop_d),
                                        self.rate, self.ratio, None, None, _p(x), L, L, _p(out), out.shape[1], out_len,
-                                       n_frames, in_off0, 0, int(self.hop), None, _p(state["last_phase"]),
-                                       _p(state["phase_sum"]), _p(state["ola"]), int(load), lanes, mode, int(warm),
-                                       int(self.hop), _p(warm_phase), _p(inc), 0)
+                                       int(ht.size), b["in_off0"], 0, int(ht[0]), _p(ht), _p(state["last_phase"]),
+                                       _p(state["phase_sum"]), _p(state["ola"]), 1, lanes, mode, int(b["warm"]),
+                                       int(b["warm_hop"]), _p(self._wp), _p(inc), int(b["lead"]))
         assert r == 0
         return out
 
-    def prepass(self, x, n_frames, in_off0, warm):
+    def prepass(self, x, block):
         lanes = x.shape[0]
         m = self.n // 2
-        self._x, self._nf, self._off, self._warm = np.ascontiguousarray(x, np.float32), n_frames, in_off0, warm
+        self._x, self._b = np.ascontiguousarray(x, np.float32), block
         self._wp = np.zeros((lanes, m))
         st = dict(last_phase=np.zeros((lanes, m)), phase_sum=np.zeros((lanes, m)), ola=np.zeros((lanes, self.n)))
-        self._inc = np.zeros((lanes, max(n_frames, 1), m))
-        self._call(self._x, n_frames, in_off0, 0, 1, warm, st, self._wp, True, self._inc)
-        return st["phase_sum"].copy()
+        self._inc = np.zeros((lanes, max(int(block["hop_tab"].size), 1), m))
+        self._call(0, 1, st, self._inc)
 
     def zero_carry(self):
         return np.zeros((self._x.shape[0], self.n // 2))
 
-    def scan(self, carry, lane0=0, n_lanes=None):
-        """the running sum of lanes lane0.. after this block, from the sum before it: the block's increments added
-        frame by frame, exactly the additions of the sequential render (tsb_timepar_scan_lanes)"""
+    def scan(self, carry, lane0=0, n_lanes=None, carry_frame=-1):
+        """the running sum of lanes lane0.. before frame `carry_frame` of the block (after its last frame when < 0),
+        from the sum before its first: the block's increments added frame by frame, exactly the additions of the
+        sequential render (tsb_timepar_scan_at)"""
         lanes = self._x.shape[0]
         n_lanes = lanes - lane0 if n_lanes is None else n_lanes
         ps = np.ascontiguousarray(carry, np.float64).copy()
         if not hasattr(self, "_carry"):
             self._carry = np.zeros((lanes, self.n // 2))
         self._carry[lane0:lane0 + n_lanes] = ps
-        for f in range(self._nf):
+        noted = None
+        for f in range(int(self._b["hop_tab"].size)):
+            if f == carry_frame:
+                noted = ps.copy()
             ps = ps + self._inc[lane0:lane0 + n_lanes, f, :]
-        return ps
+        return ps if noted is None else noted
 
-    def render(self, carry=None):
-        if carry is None:
-            carry = self._carry
+    def render(self):
         lanes = self._x.shape[0]
         m = self.n // 2
-        st = dict(last_phase=np.zeros((lanes, m)), phase_sum=np.ascontiguousarray(carry, np.float64).copy(),
+        st = dict(last_phase=np.zeros((lanes, m)), phase_sum=np.ascontiguousarray(self._carry, np.float64).copy(),
                   ola=np.zeros((lanes, self.n)))
-        out = self._call(self._x, self._nf, self._off, self._nf * self.hop, 0, self._warm, st, self._wp, True)
-        return out, st["ola"].copy()
-
-    def add_tail(self, out, tail):
-        w = min(self.n, out.shape[1])
-        out[:, :w] += tail[:, :w].astype(out.dtype)
-        return out
+        out = self._call(int(self._b["hop_tab"].sum()), 0, st)
+        return out[:, self._b["out_pad"]:]

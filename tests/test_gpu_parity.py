@@ -331,6 +331,41 @@ def test_timepar_two_blocks_like_two_gpus(env):
     assert (d == 0).mean() > 1 - 1.01 * n / whole.shape[1]   # only block 0's tail is added afterwards
 
 
+@pytest.mark.parametrize("n,hop_d,precision,world", [(1024, 256.0, "f64", 2), (256, 51.3, "f64", 3), (1024, 256.0, "f32", 3),
+                                                     (4096, 1024.0, "f64o32", 2)])
+def test_time_blocks_with_lead_in_are_the_whole_render(env, n, hop_d, precision, world):
+    """The multi-GPU time split as shard.render_time_sharded runs it, with the ranks' blocks rendered one after the
+    other on this device: a block starts with its lead-in frames (one warm-up frame before them), takes the running
+    phase_sum the block before noted for it, and needs nothing else — the stitched output is the whole render bit for
+    bit, in every precision and with a fractional hop (every block slices its own hop table)."""
+    torch, tsb, orc = env["torch"], env["tsb"], env["orc"]
+    from tinyspec_cling_b200 import shard
+    ch, samples = 2, 150000
+    x = orc.gen_signal(1, ch, samples)
+    sch = tsb.schedule_const(samples, n, hop_d)
+    F = sch["n_frames"]
+    xd = torch.from_numpy(np.ascontiguousarray(x.T)).cuda()
+    plan = tsb.Plan(env["ctx"], n, precision=precision, program="pv", hop=hop_d, ratio=1.5)
+    whole = plan.render(xd, F, int(sch["hop"][0]), hop_tab=sch["hop"]).clone()
+    blocks = shard.plan_time_blocks(sch, n, world)
+    backs = []
+    for b in blocks:
+        be = shard.GpuBackend(plan, 6)
+        be.prepass(xd[:, b["in_lo"]:b["in_hi"]].contiguous(), b)
+        backs.append(be)
+    carry = backs[0].zero_carry()
+    for b, be in zip(blocks, backs):       # the carry chain, lane by lane as the ranks do it
+        carry = torch.cat([be.scan(carry[c:c + 1].contiguous(), c, 1, b["carry_frame"]) for c in range(ch)])
+    got = torch.cat([be.render() for be in backs], dim=1)
+    torch.cuda.synchronize()
+    assert got.shape == whole.shape
+    assert torch.equal(got, whole)
+    st = {k: torch.zeros((ch, w), dtype=torch.float64, device="cuda") for k, w in
+          (("last_phase", n // 2), ("phase_sum", n // 2), ("ola", n))}
+    plan.render(xd, F, int(sch["hop"][0]), hop_tab=sch["hop"], state=st)
+    assert torch.equal(carry, st["phase_sum"])   # the last block's scan ends on the render's final phase_sum
+
+
 @pytest.mark.parametrize("n,hr,precision", [(1024, 0.25, "f64"), (512, 0.2003, "f32"), (64, 1.6, "f64")])
 def test_streaming_front_end_bit_identical(env, n, hr, precision):
     """Audio periods of arbitrary, varying length pushed one by one (tsb_stream_process) give exactly the samples

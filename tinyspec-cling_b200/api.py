@@ -58,6 +58,7 @@ def _load():
     L.tsb_ctx_trim.argtypes = [P]
     L.tsb_launch_count.argtypes = [P]
     L.tsb_launch_count.restype = C.c_int64
+    L.tsb_probe_fma_peak.argtypes = [P, C.c_int32, C.POINTER(C.c_double)]
     L.tsb_hop_fixed.argtypes = [C.c_double, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.tsb_schedule_const.argtypes = [C.c_int64, C.c_uint32, C.c_double, C.c_double, C.c_int64, C.c_int64,
                                      C.POINTER(C.c_int64), P, P, P, P]
@@ -75,11 +76,12 @@ def _load():
     L.tsb_pv_freqs.argtypes = [P, P, I64, I64, P]
     L.tsb_pv_shift.argtypes = [P, P, I64, I64, D, P, P]
     I32 = C.c_int32
-    L.tsb_timepar_create.argtypes = [P, P, C.POINTER(_ChainArgs), P, I32, I32, I32, C.POINTER(P)]
+    L.tsb_timepar_create.argtypes = [P, P, C.POINTER(_ChainArgs), P, I32, I32, I32, I32, C.POINTER(P)]
     L.tsb_timepar_segments.argtypes = [P]
     L.tsb_timepar_prepass.argtypes = [P, P, P]
     L.tsb_timepar_scan.argtypes = [P, P, P]
     L.tsb_timepar_scan_lanes.argtypes = [P, I32, I32, P, P]
+    L.tsb_timepar_scan_at.argtypes = [P, I32, I32, P, P, C.c_int64]
     L.tsb_timepar_render.argtypes = [P]
     L.tsb_timepar_destroy.argtypes = [P]
     L.tsb_chain_render_timepar.argtypes = [P, P, C.POINTER(_ChainArgs), P, I32]
@@ -186,6 +188,12 @@ class Context:
     @property
     def launches(self):
         return _load().tsb_launch_count(self.h)
+
+    def fma_peak(self, precision="f64"):
+        """measured non-tensor FMA rate of the device in TFLOP/s (tsb_probe_fma_peak)"""
+        v = C.c_double()
+        _check(_load().tsb_probe_fma_peak(self.h, 1 if precision == "f64" else 0, C.byref(v)))
+        return v.value
 
     # ---- the helpers one by one (tsb200.h "immediate mode"); tensors are CUDA float64 / complex128 ----
     def window(self, data, kind):
@@ -353,11 +361,12 @@ class Plan:
         return out
 
     def timepar(self, x, n_frames, hop, n_segments, out=None, in_off0=2048, out_off0=0, hop_tab=None, state=None,
-                load_state=False, out_len=None, warmup=False, warm_hop=0):
-        """Two-step form (pre-pass, then render) for renders split across GPUs: returns a TimePar."""
+                load_state=False, out_len=None, warmup=False, warm_hop=0, lead=0):
+        """Two-step form (pre-pass, then render) for renders split across GPUs: returns a TimePar.  lead: the block's
+        first `lead` frames are lead-in frames (they emit nothing and rebuild the overlap tail the block starts with)."""
         a, out, ht, ht_host = self._device_args(x, n_frames, hop, out, in_off0, out_off0, hop_tab, state, load_state,
                                                 out_len)
-        return TimePar(self, a, out, ht_host, n_segments, warmup, warm_hop, keep=(x, ht, state))
+        return TimePar(self, a, out, ht_host, n_segments, warmup, warm_hop, keep=(x, ht, state), lead=lead)
 
     def add_tail(self, out, pos, tail):
         """out[l][pos + i] += tail[l][i]: another block's final overlap tail onto the head of this block's output."""
@@ -407,11 +416,11 @@ class Plan:
 class TimePar:
     """tsb_timepar_*: pre-pass (block totals) and render of one block of frames cut into time segments."""
 
-    def __init__(self, plan, args, out, ht_host, n_segments, warmup, warm_hop, keep):
+    def __init__(self, plan, args, out, ht_host, n_segments, warmup, warm_hop, keep, lead=0):
         self.plan, self.args, self.out, self._keep, self._ht = plan, args, out, keep, ht_host
         h = C.c_void_p()
         _check(_load().tsb_timepar_create(plan.ctx.h, plan.h, C.byref(args), None if ht_host is None else ht_host.ctypes.data,
-                                          int(n_segments), int(bool(warmup)), int(warm_hop), C.byref(h)))
+                                          int(n_segments), int(bool(warmup)), int(warm_hop), int(lead), C.byref(h)))
         self.h = h
 
     @property
@@ -427,18 +436,19 @@ class TimePar:
         _check(_load().tsb_timepar_prepass(self.h, tot.data_ptr(), last.data_ptr()))
         return tot, last
 
-    def scan(self, carry_in=None, lane0=0, n_lanes=None):
-        """phase_sum after the block's last frame, from the phase_sum before its first (CUDA float64 [n_lanes, n/2];
-        None: the state given at creation, or zeros): the block's stored increments added frame by frame.
-        lane0 / n_lanes restrict it to some lanes (a chain of ranks hands the sums on lane by lane)."""
+    def scan(self, carry_in=None, lane0=0, n_lanes=None, carry_frame=-1):
+        """phase_sum after the block's last frame — or before its frame `carry_frame` — from the phase_sum before its
+        first (CUDA float64 [n_lanes, n/2]; None: the state given at creation, or zeros): the block's stored
+        increments added frame by frame.  lane0 / n_lanes restrict it to some lanes (a chain of ranks hands the sums
+        on lane by lane)."""
         import torch
         lanes, m = self.out.shape[0], self.plan.n // 2
         n_lanes = lanes - lane0 if n_lanes is None else n_lanes
         if carry_in is not None:
             assert carry_in.is_cuda and carry_in.dtype == torch.float64 and carry_in.shape == (n_lanes, m) and carry_in.is_contiguous()
         out = torch.empty((n_lanes, m), dtype=torch.float64, device=self.out.device)
-        _check(_load().tsb_timepar_scan_lanes(self.h, int(lane0), int(n_lanes), None if carry_in is None else carry_in.data_ptr(),
-                                              out.data_ptr()))
+        _check(_load().tsb_timepar_scan_at(self.h, int(lane0), int(n_lanes), None if carry_in is None else carry_in.data_ptr(),
+                                           out.data_ptr(), int(carry_frame)))
         self._keep_carry = carry_in
         return out
 

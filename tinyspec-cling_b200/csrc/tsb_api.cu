@@ -165,6 +165,20 @@ TSB_API int tsb_download(tsb_ctx *c, void *host, const void *dptr, size_t bytes)
     return TSB_OK;
 }
 
+// Measured non-tensor FMA rate of the device (TFLOP/s, an FMA counted as two): fp64 if is_f64, else fp32.
+TSB_API int tsb_probe_fma_peak(tsb_ctx *c, int32_t is_f64, double *tflops) {
+    if (!c || !tflops) return fail(TSB_EINVAL, "null argument");
+    CU(cudaSetDevice(c->device));
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    void *sink = nullptr;
+    CU(cudaMalloc(&sink, 64));
+    cudaError_t e = op_fma_peak(is_f64, sink, sms, c->stream, tflops);
+    cudaFree(sink);
+    if (e != cudaSuccess) return fail(TSB_ECUDA, "fma peak probe: %s", cudaGetErrorString(e));
+    return TSB_OK;
+}
+
 // ---- host logic ----
 TSB_API int tsb_hop_fixed(double hop, uint64_t *hop_samples, uint64_t *hop_fract) {
     if (!hop_samples || !hop_fract) return fail(TSB_EINVAL, "tsb_hop_fixed: null output");
@@ -678,13 +692,15 @@ TSB_API int tsb_timepar_destroy(tsb_timepar *tp) {
 }
 TSB_API int tsb_timepar_segments(tsb_timepar *tp) { return tp ? tp->n_seg : 0; }
 TSB_API int tsb_timepar_create(tsb_ctx *c, tsb_plan *p, const tsb_chain_args *a, const int32_t *host_hop_tab,
-                               int32_t n_segments, int32_t warmup, int32_t warm_hop, tsb_timepar **out) {
+                               int32_t n_segments, int32_t warmup, int32_t warm_hop, int32_t block_lead, tsb_timepar **out) {
     if (!c || !p || !out) return fail(TSB_EINVAL, "null argument");
     int r = check_args(a);
     if (r) return r;
     if ((a->hop_tab == nullptr) != (host_hop_tab == nullptr)) return fail(TSB_EINVAL, "host_hop_tab must mirror args->hop_tab");
     if (p->desc.program != TSB_PROG_PV_SHIFT && warmup) return fail(TSB_EINVAL, "warm-up frames only exist for the phase vocoder");
     if (warmup && (warm_hop < 0 || a->in_off0 - warm_hop < 0)) return fail(TSB_EINVAL, "warm-up frame would start before the input");
+    if (block_lead < 0 || (block_lead > 0 && block_lead >= a->n_frames)) return fail(TSB_EINVAL, "lead-in frames (%d) must leave the block a frame of its own", block_lead);
+    if (block_lead > 0 && !warmup) return fail(TSB_EINVAL, "a block with lead-in frames needs the warm-up frame before them");
     CU(cudaSetDevice(c->device));
     tsb_timepar *tp = new tsb_timepar();
     tp->ctx = c;
@@ -705,7 +721,8 @@ TSB_API int tsb_timepar_create(tsb_ctx *c, tsb_plan *p, const tsb_chain_args *a,
     int64_t min_frames = hop_min > 0 ? ((int64_t)tp->n + hop_min - 1) / hop_min : F;
     if (min_frames < 1) min_frames = 1;
     int64_t nseg = n_segments < 1 ? 1 : n_segments;
-    if (F > 0 && nseg > F / min_frames) nseg = F / min_frames;
+    const int64_t F_own = F - block_lead;  // the block's first `block_lead` frames are its lead-in (segment 0's)
+    if (F > 0 && nseg > F_own / min_frames) nseg = F_own / min_frames;
     if (nseg < 1) nseg = 1;
     tp->n_seg = (int)nseg;
     tp->seg.assign((size_t)SEG_COLS * nseg, 0);
@@ -719,9 +736,9 @@ TSB_API int tsb_timepar_create(tsb_ctx *c, tsb_plan *p, const tsb_chain_args *a,
         in_at[fr + 1] = in_at[fr] + hop_of(fr);
         out_at[fr + 1] = out_at[fr] + hop_of(fr);
     }
-    int64_t f = 0;
+    int64_t f = block_lead;
     for (int64_t s = 0; s < nseg; s++) {
-        int64_t cnt = F / nseg + (s < F % nseg ? 1 : 0);
+        int64_t cnt = F_own / nseg + (s < F_own % nseg ? 1 : 0);
         // lead-in: the earlier frames whose output reaches into this segment's first frame (N/hop - 1 of them for a
         // constant hop).  The segment replays them silently, so it starts with the overlap tail the sequential
         // render has there; segment 0 of the block has none (it starts the render, or takes its tail from the
@@ -730,6 +747,7 @@ TSB_API int tsb_timepar_create(tsb_ctx *c, tsb_plan *p, const tsb_chain_args *a,
         while (s > 0 && lead < f && out_at[f - lead - 1] + (int64_t)tp->n > out_at[f]) lead++;
         if (lead > f - 1) lead = f > 0 ? f - 1 : 0;  // keep one frame before it for the warm-up analysis (segments hold
                                                     // at least n/hop_min frames, so this never bites)
+        if (s == 0) lead = block_lead;              // the block's own lead-in; its warm-up frame lies before the block
         const int64_t f0 = f - lead;
         long long *t = &tp->seg[(size_t)SEG_COLS * s];
         t[0] = f0;
@@ -849,7 +867,12 @@ TSB_API int tsb_timepar_prepass(tsb_timepar *tp, double *block_total, double *bl
     return TSB_OK;
 }
 TSB_API int tsb_timepar_scan_lanes(tsb_timepar *tp, int32_t lane0, int32_t n_lanes, const double *carry_in, double *carry_out) {
+    return tsb_timepar_scan_at(tp, lane0, n_lanes, carry_in, carry_out, -1);
+}
+TSB_API int tsb_timepar_scan_at(tsb_timepar *tp, int32_t lane0, int32_t n_lanes, const double *carry_in, double *carry_out,
+                                int64_t carry_frame) {
     if (!tp) return fail(TSB_EINVAL, "null argument");
+    if (carry_frame >= tp->args.n_frames) return fail(TSB_EINVAL, "carry_frame %lld beyond the block's %lld frames", (long long)carry_frame, (long long)tp->args.n_frames);
     if (!tp->prepassed) return fail(TSB_EINVAL, "tsb_timepar_scan before tsb_timepar_prepass");
     if (lane0 < 0 || n_lanes < 0 || (size_t)lane0 + (size_t)n_lanes > tp->lanes)
         return fail(TSB_EINVAL, "lanes %d..%d out of range (0..%zu)", lane0, lane0 + n_lanes, tp->lanes);
@@ -868,7 +891,7 @@ TSB_API int tsb_timepar_scan_lanes(tsb_timepar *tp, int32_t lane0, int32_t n_lan
     const double *base = carry_in;
     if (!base && a.state_phase_sum && a.load_state) base = a.state_phase_sum + (size_t)lane0 * tp->m;
     CU(op_timepar_scan(tp->d_inc, a.n_frames, tp->d_seg, tp->n_seg, base, tp->d_sum, carry_out, (long long)tp->lanes,
-                       (long long)tp->m, lane0, n_lanes, c->stream));
+                       (long long)tp->m, lane0, n_lanes, c->stream, carry_frame));
     c->launches++;
     tp->scanned = true;
     return TSB_OK;
@@ -903,7 +926,7 @@ TSB_API int tsb_timepar_render(tsb_timepar *tp) {
 TSB_API int tsb_chain_render_timepar(tsb_ctx *c, tsb_plan *p, const tsb_chain_args *a, const int32_t *host_hop_tab,
                                      int32_t n_segments) {
     tsb_timepar *tp = nullptr;
-    int r = tsb_timepar_create(c, p, a, host_hop_tab, n_segments, 0, 0, &tp);
+    int r = tsb_timepar_create(c, p, a, host_hop_tab, n_segments, 0, 0, 0, &tp);
     if (r) return r;
     r = tsb_timepar_prepass(tp, nullptr, nullptr);
     if (!r) r = tsb_timepar_render(tp);

@@ -521,10 +521,10 @@ struct PvMath<double> {
 #define TSB_WRAPFIX_INLINE __forceinline__
 #endif
 #ifndef TSB_WRAP_K
-#define TSB_WRAP_K 4e-6f   // doubt threshold, in units of sqrt(frame energy)/|X| radians (calibration: DESIGN.md §4.1)
+#define TSB_WRAP_K 2e-6f   // doubt threshold, in units of sqrt(frame energy)/|X| radians (calibration: DESIGN.md §4.1)
 #endif
 #ifndef TSB_WRAP_C0
-#define TSB_WRAP_C0 4e-6f  // ... plus this many radians (float rounding of the two phases, atan2f error)
+#define TSB_WRAP_C0 2e-6f  // ... plus this many radians (float rounding of the two phases, atan2f error)
 #endif
 template <>
 struct PvMath<float> {
@@ -558,8 +558,20 @@ struct PvMath<float> {
         else qpd -= qpd & 1;
         double wrapped = fma(-TSB_PI, (double)qpd, delta);
         inc = tb.ratio * (expect + wrapped);
-        const float margin = 3.14159274f - fabsf((float)wrapped);
-        doubt = !dc && margin * amp < fmaf(WRAP_C0, amp, thr);
+        // |wrapped| within 2^-6 of pi?  (an integer compare on the high word of the double; only then — one bin in
+        // 200 — the float test: the threshold cannot exceed 2^-6 rad, which only caps it for bins 100 dB down)
+#if defined(__CUDA_ARCH__)
+        const int hi = __double2hiint(wrapped) & 0x7fffffff;
+#else
+        uint64_t wb;
+        memcpy(&wb, &wrapped, 8);
+        const int hi = (int)(wb >> 32) & 0x7fffffff;
+#endif
+        doubt = false;
+        if (hi >= 0x400901FB && !dc) {  // high word of pi - 2^-6
+            const float margin = 3.14159274f - fabsf((float)wrapped);
+            doubt = margin * amp < fmaf(WRAP_C0, amp, thr);
+        }
     }
     // The exact side of the wrap from double-precision phases of this frame and the one before (both recomputed
     // from the input samples by Chain::wrap_fix, expressions of PvMath<double>::analyze), applied to the float32
@@ -989,8 +1001,14 @@ struct Chain {
         unit(j * l, wx, wy);
         unit(j * NL, sx, sy);
         rc = ic = rp = ip = 0.0;
+        // (plain loads, unrolled: the samples come from L2 / HBM and several iterations' requests must be in flight)
+#pragma unroll 8
         for (int n = l; n < N; n += NL) {
-            const double wv = TSB_LDG(&win64[n]);
+#if defined(__CUDA_ARCH__)
+            const double wv = __ldg(&win64[n]);
+#else
+            const double wv = win64[n];
+#endif
             const long long sc = off_c + n, sp = off_p + n;
             const double xc = (sc >= 0 && sc < in_len) ? (double)src[sc] * wv : 0.0;
             const double xp = (sp >= 0 && sp < in_len) ? (double)src[sp] * wv : 0.0;
@@ -1459,12 +1477,14 @@ TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const t
     const int *hop_tab;
     constexpr bool prepass = PREPASS && CH::IS_PV;
     bool warm;
+    bool store_lead;
     int warm_hop;
     int ph = 0;  // hop of the frame before the one being analysed (or a PH_* code)
     long long first_own;
     {
         SegInfo sg = seg_info<CH>(a, lane, seg);
         first_own = sg.first_frame + sg.lead;
+        store_lead = sg.first_frame == 0 && sg.lead > 0;
         warm = prepass && sg.warm;
         warm_hop = sg.warm_hop;
         // a warm-up frame is the frame before the segment: it only primes last_phase
@@ -1562,7 +1582,8 @@ TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const t
                         const long long row = (long long)seg * a.lanes + lane;
                         ex.each([&](int tid, Regs &rg) { CH::regs_to(tid, a.st_warm_phase, row, rg.last_phase); });
                     }
-                } else if (ff >= 0) {  // (lead-in frames: their increments are the previous segment's)
+                } else if (ff >= 0 || store_lead) {  // (lead-in frames: their increments are the previous segment's,
+                                                     // unless the segment starts its block: the block's own lead-in)
                     double *inc_row = a.st_inc ? a.st_inc + ((long long)lane * a.inc_frames + first_own + ff) * CH::M : nullptr;
                     ex.each([&](int tid, Regs &rg) { CH::phase_pv_accumulate(tid, sm, rg, tb, inc_row); });
                 }

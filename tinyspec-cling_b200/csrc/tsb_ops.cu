@@ -557,7 +557,7 @@ cudaError_t op_pv_shift(const double *tmp, double *pvdata, const double *fn_freq
 constexpr int SCAN_BINS = 16, SCAN_TILE = 128, SCAN_THREADS = 256;
 __global__ void __launch_bounds__(SCAN_THREADS)
 timepar_scan_kernel(const double *inc, long long inc_frames, const long long *seg_tab, int n_seg, const double *base,
-                    double *sum_rows, double *carry_out, long long lanes, long long m, long long lane0) {
+                    double *sum_rows, double *carry_out, long long lanes, long long m, long long lane0, long long carry_at) {
     __shared__ __align__(16) double tile[2][SCAN_TILE][SCAN_BINS];
     const long long bin_blocks = (m + SCAN_BINS - 1) / SCAN_BINS;
     // lanes lane0 .. lane0 + gridDim.x / bin_blocks - 1; base / carry_out are indexed from lane0
@@ -581,6 +581,8 @@ timepar_scan_kernel(const double *inc, long long inc_frames, const long long *se
     double c = (tid < SCAN_BINS && bin_ok && base) ? base[sidx] : 0.0;
     int s = 0;
     long long next_start = f_begin;
+    // carry_out = the running sum before frame carry_at (the next block's first lead-in frame), or after the last frame
+    const bool carry_inside = carry_at >= f_begin && carry_at < f_end;
     fetch(0, f_begin);
     int buf = 0;
     for (long long f0 = f_begin; f0 < f_end; f0 += SCAN_TILE, buf ^= 1) {
@@ -596,9 +598,11 @@ timepar_scan_kernel(const double *inc, long long inc_frames, const long long *se
                     s++;
                     next_start = s < n_seg ? seg_tab[SEG_COLS * s] : -1;
                 }
+                if (carry_inside && f0 + r == carry_at && carry_out) carry_out[sidx] = c;
                 // up to the next segment start (or the end of the tile) nothing but the additions: the loads do
                 // not depend on the sum, so the compiler batches them ahead of the dependent chain
-                const int stop = (next_start > f0 + r && next_start < f0 + cnt) ? (int)(next_start - f0) : cnt;
+                int stop = (next_start > f0 + r && next_start < f0 + cnt) ? (int)(next_start - f0) : cnt;
+                if (carry_inside && carry_at > f0 + r && carry_at < f0 + stop) stop = (int)(carry_at - f0);
 #pragma unroll 8
                 for (; r < stop; r++) c = __dadd_rn(c, tile[buf][r][b]);
             }
@@ -608,16 +612,16 @@ timepar_scan_kernel(const double *inc, long long inc_frames, const long long *se
     if (tid < SCAN_BINS && bin_ok) {
         for (; s < n_seg; s++)  // (segments without frames)
             if (sum_rows) sum_rows[(long long)s * lanes * m + idx] = c;
-        if (carry_out) carry_out[sidx] = c;
+        if (carry_out && !carry_inside) carry_out[sidx] = c;
     }
 }
 cudaError_t op_timepar_scan(const double *inc, long long inc_frames, const long long *seg_tab, int n_seg, const double *base,
                             double *sum_rows, double *carry_out, long long lanes, long long m, long long lane0,
-                            long long n_lanes, cudaStream_t st) {
+                            long long n_lanes, cudaStream_t st, long long carry_at) {
     if (n_lanes * m == 0 || n_seg <= 0) return cudaSuccess;
     const long long grid = ((m + SCAN_BINS - 1) / SCAN_BINS) * n_lanes;
     timepar_scan_kernel<<<(unsigned)grid, SCAN_THREADS, 0, st>>>(inc, inc_frames, seg_tab, n_seg, base, sum_rows, carry_out, lanes, m,
-                                                                 lane0);
+                                                                 lane0, carry_at);
     return cudaGetLastError();
 }
 // out[lane][pos + i] += tail[lane][i] (i < n): a segment's overlap tail lands on the head of the next segment's
@@ -712,6 +716,51 @@ cudaError_t op_overlap_add(const double *frame, long long osize, long long hop, 
                                                                          tail_in, tail_out, tail_cap, tail_len, new_tail_len,
                                                                          lanes);
     return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ arithmetic peak probe (measurement aid)
+// Independent FMA chains, enough of them per thread to cover the pipe latency, enough CTAs to fill every SM: the
+// device's non-tensor FMA rate in the given type.  bench.py reports the chain kernel's arithmetic against it.
+template <typename T>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T *sink, T a, T b, int iters) {
+    T v[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) v[q] = (T)(threadIdx.x + q);
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int q = 0; q < 8; q++) v[q] = v[q] * a + b;
+    }
+    T acc = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) acc += v[q];
+    if (acc == (T)123456789) sink[0] = acc;  // never true: keeps the chains alive
+}
+cudaError_t op_fma_peak(int is_f64, void *sink, int sms, cudaStream_t st, double *tflops) {
+    const int ctas = sms * 8, iters = is_f64 ? 4096 : 16384;
+    cudaEvent_t e0, e1;
+    cudaError_t e = cudaEventCreate(&e0);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaEventCreate(&e1)) != cudaSuccess) return e;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0, st);
+        if (is_f64) fma_peak_kernel<double><<<ctas, 256, 0, st>>>((double *)sink, 1.0000001, 1e-9, iters);
+        else fma_peak_kernel<float><<<ctas, 256, 0, st>>>((float *)sink, 1.0000001f, 1e-9f, iters);
+        cudaEventRecord(e1, st);
+        if ((e = cudaEventSynchronize(e1)) != cudaSuccess) break;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    const double fmas = (double)ctas * 256 * (double)iters * 32;
+    *tflops = 2.0 * fmas / (best * 1e-3) / 1e12;
+    return cudaSuccess;
 }
 
 }  // namespace tsb
