@@ -445,6 +445,33 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import cfg3_timeshard
         line["time_sharded"] = cfg3_timeshard.run(dist, rank, world, dev, ctx, seconds=args.ts_seconds, precision="f64")
+    # ---- BASELINE configs[4]: spectral bytebeat, frame 65536 (inverse FFT of 131072 points), 64 channels, fp64 ----
+    if not args.no_extras:
+        n5, ch5, f5 = 65536, 64, 24
+        hop5 = n5 // 4
+        out5 = torch.zeros((ch5, (f5 - 1) * hop5 + n5), dtype=torch.float64, device=dev)
+        l0 = ctx.launches
+        for _ in range(2):
+            ctx.spectral_render(n5, ch5, f5, hop5, out=out5)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        reps5 = 3
+        for _ in range(reps5):
+            ctx.spectral_render(n5, ch5, f5, hop5, out=out5)
+        e1.record()
+        barrier()
+        ms5 = max_over_ranks(e0.elapsed_time(e1)) / reps5
+        fc5 = world * ch5 * f5 / (ms5 * 1e-3)
+        balg5 = (n5 + 1) * 16 + hop5 * 8   # the Hermitian half spectrum + hop output samples
+        line["cfg5"] = {"what": "spectral bytebeat pattern (hacks/spectral_bytebeat/*.cpp): seeded integer spectrum generated on the "
+                                "device -> inverse real FFT of 131072 points -> triangular window -> overlap-add, fp64; every rank "
+                                "renders its own 64 channels", "frame": n5, "fft_points": 2 * n5, "hop": hop5,
+                        "channels_per_gpu": ch5, "frames": f5, "ms_per_render": ms5, "frames_per_s": fc5 / ch5,
+                        "frame_channels_per_s": fc5, "out_samples_per_s": fc5 * hop5, "gpu_launches_per_render": (ctx.launches - l0) // (2 + reps5),
+                        "roofline": {"bound": "hbm", "alg_bytes_per_frame_channel": balg5, "achieved": fc5 / world * balg5 / 1e9,
+                                     "peak": peak, "unit": "GB/s", "frac": fc5 / world * balg5 / 1e9 / peak}}
+        del out5
     # ---- CPU baseline: rank 0, N=1 only, bounded sample ----
     if rank == 0 and world == 1:
         frames, wall, kind, what, used = run_reference(1, min(args.seconds, 60.0))

@@ -131,6 +131,35 @@ typedef struct tsb_chain_args {
 } tsb_chain_args;
 int tsb_chain_render(tsb_ctx *ctx, tsb_plan *plan, const tsb_chain_args *args);
 
+/* ---- fused spectral synthesis (BASELINE cfg5; the reference's hacks/spectral_bytebeat/*.cpp, e.g. voidbubbles.cpp:4-19):
+ * per frame and channel a Hermitian spectrum of 2*frame points -> frft(., -1) (rtlib/fft.hpp:3-42) -> the first
+ * `frame` real samples times the hack's triangular window 1 - |1 - i/(frame/2)| -> overlap-add at `hop`
+ * (tinyspec.cpp:170-200), in double precision, as two kernels per frame (four-step inverse real FFT, the
+ * intermediate staying in L2).  The spectrum comes from the device:
+ *   TSB_GEN_HASH    the seeded integer formula of SURVEY.md §8d / examples/bytebeat.cpp, evaluated in the kernel:
+ *                   h = frame*2654435761 ^ (c*40503 + i*2246822519); h ^= h>>15; h *= 2246822519; h ^= h>>13;
+ *                   X[i] = (((h & 0xffff) - 32768) + i*((h >> 16) - 32768)) / 32768.0 / (1 + (i >> 4)),  0 < i < frame
+ *   TSB_GEN_BUFFER  values the caller computed: device complex128 [n_frames][channels][frame], bins 1..frame-1 read
+ * and X[2*frame - i] = conj(X[i]).  Bins 0 and `frame`, which such a hack never writes, hold what its static buffer
+ * holds there: the previous frame's output samples y[0] and y[frame] (frft runs in place) — zero before the first
+ * frame; state_edge [channels][2] carries them between calls.  Frame f is ADDED to out[c][out_off0 + f*hop ...]
+ * (the caller zeroes `out`; after the call positions below out_off0 + n_frames*hop are final, the rest is the tail). */
+enum { TSB_GEN_HASH = 0, TSB_GEN_BUFFER = 1 };
+typedef struct tsb_spectral_args {
+    uint32_t frame;          /* power of two, 256 .. 262144; the inverse FFT has 2*frame points */
+    int32_t channels;
+    int64_t n_frames;
+    int64_t first_frame;     /* frame counter of the first frame (TSB_GEN_HASH) */
+    int32_t hop;             /* computed_hop, constant */
+    int32_t generator;
+    const double *spectrum;  /* TSB_GEN_BUFFER */
+    double *out;             /* device float64 [channels][out_stride] */
+    int64_t out_stride, out_len, out_off0;
+    double *state_edge;      /* device float64 [channels][2] or NULL, in (load_state) / out */
+    int32_t load_state;
+} tsb_spectral_args;
+int tsb_spectral_render(tsb_ctx *ctx, const tsb_spectral_args *args);
+
 /* Measurement aid: the device's measured non-tensor FMA rate in TFLOP/s (an FMA = 2 flops), fp64 or fp32, from a
  * kernel of independent FMA chains timed with CUDA events.  bench.py reports the chain kernel's arithmetic against it. */
 int tsb_probe_fma_peak(tsb_ctx *ctx, int32_t is_f64, double *tflops);

@@ -91,13 +91,19 @@ def granular_case(name, samples, vary, n_first=0, stream=0):
     print(name, "frames", len(r["t"]), "stream", r["stream"].shape)
 
 
-def bytebeat_case(name, n, ch, frames):
+def bytebeat_case(name, n, ch, frames, every=1):
+    """every > 1 (the full cfg5 size): keep every `every`-th sample of each frame's double `out` and of the stream —
+    each sample depends on every bin of the spectrum, so a subset pins the transform as well as all of them"""
     r = run_ref("ref_bytebeat_tap", dict(TSREF_N=n, TSREF_CH=ch, TSREF_MAX_FRAMES=frames, TSREF_DUMP_FIRST=frames),
                 [("t", np.float64), ("out", np.float64)])
     k = len(r["t"])
+    out = r["out"].reshape(k, ch, n)
+    stream = r["stream"].reshape(-1, ch)
     np.savez_compressed(os.path.join(GOLD, name + ".npz"), meta=np.array([n, ch, frames], np.int64), t=r["t"],
-                        out=r["out"].reshape(k, ch, n), stream=r["stream"].reshape(-1, ch))
-    print(name, "frames dumped", k, "stream", r["stream"].shape)
+                        out=out[:, :, ::every], stream=stream[::every], every=np.array([every], np.int64),
+                        stream_len=np.array([stream.shape[0]], np.int64),
+                        frame_sum=out.sum(axis=2), frame_sumsq=(out ** 2).sum(axis=2))
+    print(name, "frames dumped", k, "stream", stream.shape)
 
 
 if __name__ == "__main__":
@@ -117,3 +123,5 @@ if __name__ == "__main__":
     granular_case("granular_1800", 60000, 0)
     granular_case("granular_vary", 60000, 1, n_first=64, stream=2)
     bytebeat_case("bytebeat_n2048", 2048, 2, 12)
+    # BASELINE cfg5 at its real size: frame 65536 -> frft of 131072 points (two channels, six frames, every 32nd sample)
+    bytebeat_case("bytebeat_n65536", 65536, 2, 6, every=32)

@@ -276,3 +276,44 @@ def render_granular(x, n_first=0, n_base=1800, vary=False, stream_idx=0, rate=48
     F = r.frames
     return dict(frames=F, stream=stream[:r.out_len].reshape(-1, nch), ola64=ola64.reshape(-1, nch),
                 tables=dict(in_off=tabs[0][:F], out_off=tabs[1][:F], hop=tabs[2][:F], win=tabs[3][:F], t=tabs[4][:F]))
+
+
+# ---- the spectral-bytebeat pattern (BASELINE cfg5), numpy restatement ----
+def bytebeat_spectrum(frame_idx, ch, n):
+    """Bins 1..n-1 of the seeded integer generator of oracle/ref/taps/bytebeat_tap.cpp:17-24 (the hack's per-bin
+    loop, hacks/spectral_bytebeat/voidbubbles.cpp:9-15 with an integer-only formula): complex128 [ch, n], bin 0 = 0."""
+    i = np.arange(n, dtype=np.uint32)[None, :]
+    c = np.arange(ch, dtype=np.uint32)[:, None]
+    with np.errstate(over="ignore"):
+        h = (np.uint32(frame_idx) * np.uint32(2654435761)) ^ (c * np.uint32(40503) + i * np.uint32(2246822519))
+        h ^= h >> np.uint32(15)
+        h *= np.uint32(2246822519)
+        h ^= h >> np.uint32(13)
+    d = (1 + (np.arange(n) >> 4)).astype(np.float64)[None, :]
+    re = ((h & np.uint32(0xffff)).astype(np.int64) - 32768) / 32768.0 / d
+    im = ((h >> np.uint32(16)).astype(np.int64) - 32768) / 32768.0 / d
+    x = re + 1j * im
+    x[:, 0] = 0
+    return x
+
+
+def render_bytebeat(n, ch, frames, hop=None, spectrum=None):
+    """The pattern of hacks/spectral_bytebeat/*.cpp (voidbubbles.cpp:4-19) frame by frame: a STATIC buffer of 2n points,
+    bins i and 2n-i (0 < i < n) rewritten every frame, frft(buf, buf, -1) IN PLACE (rtlib/fft.hpp:3-42: forward DFT
+    over sqrt(2n)) — so bins 0 and n hold the previous frame's output samples — out = Re(buf[:n]) * (1 - |1 - i/(n/2)|),
+    overlap-added at `hop` in double (the scheduler's own stream is float32, tinyspec.cpp:170-200).
+    spectrum(f) -> complex [ch, n] overrides the seeded generator.  Returns dict(out [frames, ch, n], ola64 [ch, L])."""
+    hop = n // 4 if hop is None else hop
+    buf = np.zeros((ch, 2 * n), np.complex128)
+    i = np.arange(n)
+    tri = 1.0 - np.abs(1.0 - i / (n / 2.0))
+    outs = np.zeros((frames, ch, n))
+    ola = np.zeros((ch, (frames - 1) * hop + n if frames else 0))
+    for f in range(frames):
+        x = bytebeat_spectrum(f, ch, n) if spectrum is None else spectrum(f)
+        buf[:, 1:n] = x[:, 1:n]
+        buf[:, 2 * n - 1:n:-1] = np.conj(x[:, 1:n])
+        buf = np.fft.fft(buf, axis=1) / np.sqrt(2.0 * n)
+        outs[f] = buf[:, :n].real * tri
+        ola[:, f * hop:f * hop + n] += outs[f]
+    return dict(out=outs, ola64=ola)

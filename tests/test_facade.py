@@ -171,10 +171,16 @@ def test_immediate_bytebeat_cfg5_pattern(golden):
 
 
 @pytest.mark.gpu
-def test_immediate_bytebeat_full_size_runs():
-    """The real cfg5 size: frame 65536 -> inverse FFT of 131072 points (four-step), 4 channels, 3 frames."""
+def test_immediate_bytebeat_full_size(golden):
+    """The real cfg5 size through the facade: frame 65536 -> frft of 131072 points on the device (four-step), the
+    hack's own per-bin loops on the host; against the compiled reference's stream (every 32nd sample kept)."""
+    g = golden("bytebeat_n65536")
+    n, ch, frames = (int(v) for v in g["meta"])
+    every = int(g["every"][0])
     b = build(os.path.join(EX, "bytebeat.cpp"))
-    r, info, y = render(b, "--mode", "immediate", "--max-frames", 3, "--seconds", 100, lanes=4,
-                        env={"BYTEBEAT_N": "65536", "BYTEBEAT_CH": "4"})
+    r, info, y = render(b, "--mode", "immediate", "--max-frames", frames, "--seconds", 100, lanes=ch,
+                        env={"BYTEBEAT_N": str(n), "BYTEBEAT_CH": str(ch)})
     assert r.returncode == 0, r.stderr
-    assert info["frames"] == 3 and y.shape[1] == 3 * 16384 and np.isfinite(y).all() and np.abs(y).max() > 0
+    assert info["frames"] == frames and y.shape[1] == int(g["stream_len"][0])
+    d = np.abs(y.T[::every] - g["stream"])
+    assert d.max() <= 1.2e-7 * np.abs(g["stream"]).max() and (d == 0).mean() > 0.99

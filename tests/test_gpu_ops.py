@@ -122,3 +122,73 @@ def test_pv_steps_vs_golden(env, golden):
                 assert np.abs(psum.cpu().numpy() - g["pv_phase_sum"][sl].reshape(2, n)).max() < 1e-8
                 assert np.abs(last.cpu().numpy() - g["pv_last_phase"][sl].reshape(2, n)).max() < 1e-12
                 off += 2 * n
+
+
+# ---- fused spectral synthesis (BASELINE cfg5): tsb_spectral_render ----
+@pytest.mark.parametrize("name", ["bytebeat_n2048", "bytebeat_n65536"])
+def test_spectral_render_matches_the_compiled_reference(env, golden, name):
+    """Generator on the device -> inverse real FFT of 2*frame points (four-step) -> triangular window -> overlap-add,
+    against the per-frame double `out` buffers and the stream of the UNMODIFIED reference running
+    oracle/ref/taps/bytebeat_tap.cpp — at cfg5's real frame size 65536 (FFT of 131072 points) too."""
+    torch = env["torch"]
+    g = golden(name)
+    n, ch, frames = (int(v) for v in g["meta"])
+    every, hop = int(g["every"][0]), n // 4
+    peak = np.abs(g["out"]).max()
+    # frame by frame (each into its own zeroed row) = the hack's `out` buffer of that frame; the carried bins 0 / n
+    # travel through state_edge
+    edge = torch.zeros((ch, 2), dtype=torch.float64, device="cuda")
+    for f in range(frames):
+        o = env["ctx"].spectral_render(n, ch, 1, hop, first_frame=f, state_edge=edge, load_state=f > 0)
+        got = o.cpu().numpy()[:, :n]
+        assert np.abs(got[:, ::every] - g["out"][f]).max() <= 1e-9 * peak, f
+    # all frames in one call: the overlap-added stream (the reference's is its float32 narrowing)
+    out = env["ctx"].spectral_render(n, ch, frames, hop)
+    L = int(g["stream_len"][0])
+    s = out.cpu().numpy()[:, :L].T[::every]
+    assert np.abs(s - g["stream"]).max() <= 2e-7 * np.abs(g["stream"]).max()
+
+
+@pytest.mark.parametrize("n,ch,frames", [(256, 3, 5), (512, 1, 4), (4096, 2, 5), (8192, 2, 3), (16384, 5, 3), (32768, 1, 3),
+                                         (65536, 64, 2), (131072, 2, 3), (262144, 1, 2)])
+def test_spectral_render_vs_oracle_all_sizes(env, n, ch, frames):
+    """every supported frame size (both splits of the four-step transform, odd and even log2) against the numpy
+    restatement, cfg5's 64 channels included; 1e-9 of peak (BASELINE.json fp64 bound), measured ~1e-13"""
+    orc = env["orc"]
+    hop = n // 4
+    ref = orc.render_bytebeat(n, ch, frames, hop)
+    got = env["ctx"].spectral_render(n, ch, frames, hop).cpu().numpy()
+    assert got.shape == ref["ola64"].shape
+    assert np.abs(got - ref["ola64"]).max() <= 1e-9 * np.abs(ref["ola64"]).max()
+    assert np.abs(got - ref["ola64"]).max() <= 1e-11 * np.abs(ref["ola64"]).max()   # (what it actually achieves)
+
+
+def test_spectral_render_caller_spectrum_and_continuation(env):
+    """TSB_GEN_BUFFER with the generator's own values is the TSB_GEN_HASH render bit for bit; a render continued
+    through state_edge and the tail in `out` is the whole render bit for bit; an arbitrary (non-generator) spectrum
+    matches the oracle fed the same values; odd hop / odd offset take the unaligned store path."""
+    torch, orc = env["torch"], env["orc"]
+    n, ch, frames, hop = 4096, 2, 6, 1024
+    whole = env["ctx"].spectral_render(n, ch, frames, hop)
+    spec = np.stack([orc.bytebeat_spectrum(f, ch, n) for f in range(frames)])
+    via_buf = env["ctx"].spectral_render(n, ch, frames, hop, spectrum=dev(env, spec))
+    assert torch.equal(whole, via_buf)
+    out = torch.zeros_like(whole)
+    edge = torch.zeros((ch, 2), dtype=torch.float64, device="cuda")
+    env["ctx"].spectral_render(n, ch, 2, hop, out=out, state_edge=edge)
+    env["ctx"].spectral_render(n, ch, frames - 2, hop, out=out, first_frame=2, out_off0=2 * hop, state_edge=edge, load_state=True)
+    assert torch.equal(out, whole)
+    rng = np.random.default_rng(5)
+    arb = rng.standard_normal((frames, ch, n)) + 1j * rng.standard_normal((frames, ch, n))
+    hop2 = 1001
+    ref = orc.render_bytebeat(n, ch, frames, hop2, spectrum=lambda f: arb[f])
+    got = env["ctx"].spectral_render(n, ch, frames, hop2, spectrum=dev(env, arb)).cpu().numpy()
+    assert np.abs(got - ref["ola64"]).max() <= 1e-11 * np.abs(ref["ola64"]).max()
+
+
+def test_spectral_render_rejects_bad_arguments(env):
+    tsb = env["tsb"]
+    with pytest.raises(tsb.TsbError, match="powers of two"):
+        env["ctx"].spectral_render(3000, 1, 1, 750)
+    with pytest.raises(tsb.TsbError, match="powers of two"):
+        env["ctx"].spectral_render(128, 1, 1, 32)

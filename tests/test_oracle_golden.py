@@ -145,3 +145,30 @@ def test_granular(golden, name, vary):
     assert np.array_equal(r["tables"]["win"], g["win"])
     assert np.array_equal(r["tables"]["t"], g["t"])
     assert np.array_equal(r["stream"], g["stream"])
+
+
+@pytest.mark.parametrize("name", ["bytebeat_n2048", "bytebeat_n65536"])
+def test_bytebeat_restatement(golden, name):
+    """The numpy restatement of the spectral-bytebeat pattern (BASELINE cfg5: static 2n-point buffer, frft(-1) in
+    place, triangular window) against what the compiled reference produced — at the small size and at cfg5's own
+    frame 65536 (every 32nd sample of each frame; any sample depends on every bin)."""
+    g = golden(name)
+    n, ch, frames = (int(v) for v in g["meta"])
+    every = int(g["every"][0])
+    r = orc.render_bytebeat(n, ch, frames)
+    peak = np.abs(g["out"]).max()
+    assert np.abs(r["out"][:, :, ::every] - g["out"]).max() <= 1e-12 * peak
+    assert np.abs(r["out"].sum(axis=2) - g["frame_sum"]).max() <= 1e-9 * np.abs(g["frame_sum"]).max()
+    assert np.abs((r["out"] ** 2).sum(axis=2) - g["frame_sumsq"]).max() <= 1e-12 * g["frame_sumsq"].max()
+    # the reference's own stream is the float32 narrowing of the overlap-add (tinyspec.cpp:173-200)
+    L = int(g["stream_len"][0])
+    s = r["ola64"][:, :L].T[::every]
+    assert np.abs(s - g["stream"]).max() <= 2e-7 * np.abs(g["stream"]).max()
+    # the in-place quirk matters: with bins 0 and n cleared every frame the result is measurably different
+    if name == "bytebeat_n2048":
+        buf_clean = np.zeros((ch, 2 * n), np.complex128)
+        x = orc.bytebeat_spectrum(1, ch, n)
+        buf_clean[:, 1:n] = x[:, 1:n]
+        buf_clean[:, 2 * n - 1:n:-1] = np.conj(x[:, 1:n])
+        clean = (np.fft.fft(buf_clean, axis=1) / np.sqrt(2.0 * n))[:, :n].real * (1.0 - np.abs(1.0 - np.arange(n) / (n / 2.0)))
+        assert np.abs(clean - g["out"][1]).max() > 1e-6 * peak

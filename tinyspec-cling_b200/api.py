@@ -30,6 +30,13 @@ class _PlanDesc(C.Structure):
                 ("fn_bins", C.c_void_p), ("gain", C.c_void_p)]
 
 
+class _SpectralArgs(C.Structure):
+    _fields_ = [("frame", C.c_uint32), ("channels", C.c_int32), ("n_frames", C.c_int64), ("first_frame", C.c_int64),
+                ("hop", C.c_int32), ("generator", C.c_int32), ("spectrum", C.c_void_p), ("out", C.c_void_p),
+                ("out_stride", C.c_int64), ("out_len", C.c_int64), ("out_off0", C.c_int64), ("state_edge", C.c_void_p),
+                ("load_state", C.c_int32)]
+
+
 class _ChainArgs(C.Structure):
     _fields_ = [("in_", C.c_void_p), ("in_stride", C.c_int64), ("in_len", C.c_int64), ("out", C.c_void_p),
                 ("out_stride", C.c_int64), ("out_len", C.c_int64), ("n_frames", C.c_int64), ("in_off0", C.c_int64),
@@ -67,6 +74,7 @@ def _load():
     L.tsb_plan_destroy.argtypes = [P]
     L.tsb_chain_render.argtypes = [P, P, C.POINTER(_ChainArgs)]
     L.tsb_chain_render_host.argtypes = [P, P, C.POINTER(_ChainArgs)]
+    L.tsb_spectral_render.argtypes = [P, C.POINTER(_SpectralArgs)]
     I64, D = C.c_int64, C.c_double
     L.tsb_window.argtypes = [P, P, I64, I64, C.c_int32]
     L.tsb_fft_forward.argtypes = [P, P, P, I64, I64]
@@ -188,6 +196,32 @@ class Context:
     @property
     def launches(self):
         return _load().tsb_launch_count(self.h)
+
+    def spectral_render(self, frame, channels, n_frames, hop, out=None, spectrum=None, first_frame=0, out_off0=0,
+                        state_edge=None, load_state=False):
+        """tsb_spectral_render: the spectral-bytebeat pattern (BASELINE cfg5) fused on the device.  spectrum=None: the
+        seeded integer generator; else CUDA complex128 [n_frames, channels, frame].  Frames are ADDED into `out`
+        (CUDA float64 [channels, >= out_off0 + (n_frames-1)*hop + frame], zeros by default); returns it."""
+        import torch
+        if out is None:
+            out = torch.zeros((channels, out_off0 + max(n_frames - 1, 0) * hop + frame), dtype=torch.float64,
+                              device=torch.device("cuda", self.device))
+        assert out.is_cuda and out.dtype == torch.float64 and out.is_contiguous() and out.shape[0] == channels
+        a = _SpectralArgs()
+        a.frame, a.channels, a.n_frames, a.first_frame, a.hop = frame, channels, n_frames, first_frame, int(hop)
+        a.generator = 0 if spectrum is None else 1
+        if spectrum is not None:
+            assert spectrum.is_cuda and spectrum.dtype == torch.complex128 and spectrum.is_contiguous()
+            assert tuple(spectrum.shape) == (n_frames, channels, frame)
+            a.spectrum = spectrum.data_ptr()
+        a.out, a.out_stride, a.out_len, a.out_off0 = out.data_ptr(), out.stride(0) if channels > 1 else out.shape[1], out.shape[1], out_off0
+        if state_edge is not None:
+            assert state_edge.is_cuda and state_edge.dtype == torch.float64 and tuple(state_edge.shape) == (channels, 2)
+            a.state_edge = state_edge.data_ptr()
+        a.load_state = int(load_state)
+        _check(_load().tsb_spectral_render(self.h, C.byref(a)))
+        self._keep_spec = (out, spectrum, state_edge)
+        return out
 
     def fma_peak(self, precision="f64"):
         """measured non-tensor FMA rate of the device in TFLOP/s (tsb_probe_fma_peak)"""

@@ -12,6 +12,7 @@
 #include "tsb_launch.hpp"
 #include "tsb_ops.hpp"
 #include "tsb_plan.hpp"
+#include "tsb_spectral.hpp"
 #include <map>
 
 using namespace tsb;
@@ -127,6 +128,7 @@ TSB_API int tsb_ctx_trim(tsb_ctx *c) {
     c->scratch = nullptr;
     c->scratch_bytes = 0;
     op_release_scratch(c->device);
+    op_spectral_release(c->device);
     return TSB_OK;
 }
 TSB_API int tsb_ctx_sync(tsb_ctx *c) {
@@ -660,6 +662,38 @@ TSB_API int tsb_overlap_add(tsb_ctx *c, const double *frame, int64_t lanes, int6
                       c->stream));
     *new_tail_len = keep;
     c->launches++;
+    return TSB_OK;
+}
+
+// ---- fused spectral synthesis (cfg5) ----
+TSB_API int tsb_spectral_render(tsb_ctx *c, const tsb_spectral_args *a) {
+    if (!c || !a) return fail(TSB_EINVAL, "null argument");
+    const uint32_t n = a->frame;
+    if (n < 256 || n > (1u << 18) || (n & (n - 1))) return fail(TSB_EUNSUPPORTED, "frame size %u: fused spectral synthesis supports powers of two in 256..262144", n);
+    if (a->channels < 0 || a->n_frames < 0 || a->hop < 0) return fail(TSB_EINVAL, "negative channels / n_frames / hop");
+    if (a->generator != TSB_GEN_HASH && a->generator != TSB_GEN_BUFFER) return fail(TSB_EINVAL, "bad generator %d", a->generator);
+    if (a->generator == TSB_GEN_BUFFER && !a->spectrum && a->n_frames * a->channels) return fail(TSB_EINVAL, "TSB_GEN_BUFFER needs a spectrum");
+    if (a->channels == 0 || a->n_frames == 0) return TSB_OK;
+    if (!a->out || a->out_off0 < 0 || a->out_len < 0 || (a->channels > 1 && a->out_stride < a->out_len)) return fail(TSB_EINVAL, "bad output rows");
+    CU(cudaSetDevice(c->device));
+    SpectralJob jb;
+    jb.log2n = ilog2(n);
+    jb.channels = a->channels;
+    jb.n_frames = a->n_frames;
+    jb.first_frame = a->first_frame;
+    jb.hop = a->hop;
+    jb.generator = a->generator == TSB_GEN_HASH ? (int)SPEC_GEN_HASH : (int)SPEC_GEN_BUFFER;
+    jb.spectrum = a->spectrum;
+    jb.out = a->out;
+    jb.out_stride = a->out_stride;
+    jb.out_len = a->out_len;
+    jb.out_off0 = a->out_off0;
+    jb.state_edge = a->state_edge;
+    jb.load_state = a->load_state;
+    long long l = 0;
+    cudaError_t e = op_spectral_render(c->device, jb, c->stream, &l);
+    c->launches += l;
+    if (e != cudaSuccess) return fail(TSB_ECUDA, "spectral synthesis: %s", cudaGetErrorString(e));
     return TSB_OK;
 }
 
