@@ -131,7 +131,7 @@ typedef struct tsb_chain_args {
 } tsb_chain_args;
 int tsb_chain_render(tsb_ctx *ctx, tsb_plan *plan, const tsb_chain_args *args);
 
-/* ---- fused spectral synthesis (BASELINE cfg5; the reference's hacks/spectral_bytebeat/*.cpp, e.g. voidbubbles.cpp:4-19):
+/* ---- fused spectral synthesis (BASELINE cfg5; the reference's hacks/spectral_bytebeat hacks, e.g. voidbubbles.cpp:4-19):
  * per frame and channel a Hermitian spectrum of 2*frame points -> frft(., -1) (rtlib/fft.hpp:3-42) -> the first
  * `frame` real samples times the hack's triangular window 1 - |1 - i/(frame/2)| -> overlap-add at `hop`
  * (tinyspec.cpp:170-200), in double precision, as two kernels per frame (four-step inverse real FFT, the

@@ -106,6 +106,25 @@ def bytebeat_case(name, n, ch, frames, every=1):
     print(name, "frames dumped", k, "stream", stream.shape)
 
 
+def control_case(name, samples):
+    r = run_ref("ref_control_tap", dict(TSREF_SAMPLES=samples, TSREF_STREAM=1), [("rec", np.float64)])
+    rec = r["rec"].reshape(-1, 4)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), meta=np.array([samples, 1], np.int64), rec=rec,
+                        stream=r["stream"].reshape(-1, 2))
+    print(name, "frames", rec.shape[0], "stream", r["stream"].shape)
+
+
+def pvmore_case():
+    tags = ["noshift", "nonlin", "bufshift", "ownhop", "copy"]
+    dumps = [("in", np.float64), ("ownhop_hop", np.float64)]
+    for t in tags:
+        dumps += [(t + "_out", np.float64), (t + "_data", np.float64), (t + "_phase_sum", np.float64),
+                  (t + "_last_phase", np.float64)]
+    r = run_ref("ref_pvmore_tap", {}, dumps, want_out=False)
+    np.savez_compressed(os.path.join(GOLD, "pvmore.npz"), n=np.array([128]), frames=np.array([4, 4, 3, 6, 1]), **r)
+    print("pvmore", {k: v.shape for k, v in r.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL)
@@ -125,3 +144,5 @@ if __name__ == "__main__":
     bytebeat_case("bytebeat_n2048", 2048, 2, 12)
     # BASELINE cfg5 at its real size: frame 65536 -> frft of 131072 points (two channels, six frames, every 32nd sample)
     bytebeat_case("bytebeat_n65536", 65536, 2, 6, every=32)
+    control_case("control_times", 12000)
+    pvmore_case()

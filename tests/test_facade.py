@@ -34,7 +34,7 @@ def test_reference_hacks_compile_unchanged(hack, tmp_path):
 
 
 def test_examples_build():
-    for h in ("pitchshift_cfg1", "passthrough_cfg2", "lowpass_raw", "granular", "bytebeat"):
+    for h in ("pitchshift_cfg1", "passthrough_cfg2", "lowpass_raw", "granular", "bytebeat", "control_times"):
         assert os.path.exists(build(os.path.join(EX, h + ".cpp")))
 
 
@@ -184,3 +184,51 @@ def test_immediate_bytebeat_full_size(golden):
     assert info["frames"] == frames and y.shape[1] == int(g["stream_len"][0])
     d = np.abs(y.T[::every] - g["stream"])
     assert d.max() <= 1.2e-7 * np.abs(g["stream"]).max() and (d == 0).mean() > 0.99
+
+
+@pytest.mark.gpu
+def test_control_api_inside_the_callback(golden):
+    """set_time (and a rejected negative one), next_hop_samples with a fractional hop, next_hop_hz, a frame-size change
+    through next_hop_ratio's default ratio, a rejected set_hop — called from inside the frame callback
+    (rtlib/control.hpp:22-53).  Per frame t, base_time, the frame size and the first input sample, and the whole output
+    stream, equal what the unmodified reference produced (oracle/ref/taps/control_tap.cpp)."""
+    from oracle import orc
+    g = golden("control_times")
+    samples, stream = (int(v) for v in g["meta"])
+    b = build(os.path.join(EX, "control_times.cpp"))
+    x = orc.gen_signal(stream, 2, samples)
+    with tempfile.TemporaryDirectory() as d:
+        inp, dump = os.path.join(d, "in.f32"), os.path.join(d, "rec.bin")
+        np.ascontiguousarray(x.T).tofile(inp)
+        r, info, y = render(b, "--mode", "immediate", "--in", inp, lanes=2, env={"CONTROL_DUMP": dump})
+        assert r.returncode == 0, r.stderr
+        rec = np.fromfile(dump, np.float64).reshape(-1, 4)
+    assert "negative time is not supported" in r.stderr and "ignoring invalid hop" in r.stderr
+    assert info["frames"] == g["rec"].shape[0]
+    assert np.array_equal(rec, g["rec"])
+    want = g["stream"].reshape(-1, 2)
+    assert y.shape[1] == want.shape[0] and np.array_equal(y.T, want)
+
+
+@pytest.mark.gpu
+def test_skip_to_now_and_mid_render_channel_change():
+    """skip_to_now keeps one frame's worth of the queued input (rtlib/control.hpp:78-82): offline, where the whole input
+    is queued up front, the render ends after the frame that is already scheduled.  set_num_channels mid-render drops
+    the queued input in the reference (:56-57) — how much depends on the audio period — so the fused driver refuses it
+    loudly instead of guessing."""
+    with tempfile.TemporaryDirectory() as d:
+        h1 = os.path.join(d, "skip.cpp")
+        open(h1, "w").write("long fr = 0;\nnext_hop_ratio(256, 0.25);\nset_process_fn([&](WaveBuf &in, WaveBuf &out, double t) {\n"
+                            "  for (size_t c = 0; c < out.num_channels; c++) for (size_t i = 0; i < out.size; i++) out[c][i] = in[c][i];\n"
+                            "  if (++fr == 5) skip_to_now();\n});\n")
+        b1 = build(h1, out=os.path.join(d, "skip"))
+        r, info, y = render(b1, "--mode", "immediate", "--seconds", 0.5, lanes=2)
+        assert r.returncode == 0, r.stderr
+        assert info["frames"] == 6          # the fifth frame called it; one more frame was still queued
+        h2 = os.path.join(d, "chan.cpp")
+        open(h2, "w").write("long fr = 0;\nPhaseVocoder pv;\nnext_hop_ratio(256, 0.25);\nset_process_fn([&](WaveBuf &in, WaveBuf &out, double t) {\n"
+                            "  pv.analyze(in); pv.shift([](double x){ return x*2; }); pv.synthesize(out);\n"
+                            "  if (++fr == 3) set_num_channels(2, 2);\n});\n")
+        b2 = build(h2, out=os.path.join(d, "chan"))
+        r, info, y = render(b2, "--seconds", 0.5, lanes=2)
+        assert r.returncode != 0 and "set_num_channels mid-render" in r.stderr

@@ -164,7 +164,8 @@ def test_spectral_render_vs_oracle_all_sizes(env, n, ch, frames):
 
 
 def test_spectral_render_caller_spectrum_and_continuation(env):
-    """TSB_GEN_BUFFER with the generator's own values is the TSB_GEN_HASH render bit for bit; a render continued
+    """TSB_GEN_BUFFER with the generator's own values is the TSB_GEN_HASH render (to the last bits: the kernel divides
+    by a corrected Newton reciprocal); a render continued
     through state_edge and the tail in `out` is the whole render bit for bit; an arbitrary (non-generator) spectrum
     matches the oracle fed the same values; odd hop / odd offset take the unaligned store path."""
     torch, orc = env["torch"], env["orc"]
@@ -172,7 +173,7 @@ def test_spectral_render_caller_spectrum_and_continuation(env):
     whole = env["ctx"].spectral_render(n, ch, frames, hop)
     spec = np.stack([orc.bytebeat_spectrum(f, ch, n) for f in range(frames)])
     via_buf = env["ctx"].spectral_render(n, ch, frames, hop, spectrum=dev(env, spec))
-    assert torch.equal(whole, via_buf)
+    assert float((whole - via_buf).abs().max()) <= 1e-14 * float(whole.abs().max())
     out = torch.zeros_like(whole)
     edge = torch.zeros((ch, 2), dtype=torch.float64, device="cuda")
     env["ctx"].spectral_render(n, ch, 2, hop, out=out, state_edge=edge)
@@ -192,3 +193,82 @@ def test_spectral_render_rejects_bad_arguments(env):
         env["ctx"].spectral_render(3000, 1, 1, 750)
     with pytest.raises(tsb.TsbError, match="powers of two"):
         env["ctx"].spectral_render(128, 1, 1, 32)
+
+
+# ---- the rest of the PhaseVocoder surface against the compiled reference (oracle/ref/taps/pvmore_tap.cpp) ----
+def _pv_frame(env, wave_np, last, psum, pvd, hop, shift=None):
+    """PhaseVocoder::analyze(WaveBuf) [-> shift] -> synthesize(WaveBuf) from the device helpers (rtlib/pv.hpp:4-16)"""
+    torch, ctx = env["torch"], env["ctx"]
+    wave = dev(env, wave_np)
+    ctx.window(wave, "sqrt_hann")
+    spec = torch.complex(wave, torch.zeros_like(wave))
+    ctx.frft(spec, 1.0)
+    ctx.pv_analyze(spec, last, pvd, hop)
+    if shift is not None:
+        ctx.pv_shift(pvd, shift)
+    ctx.pv_synthesize(spec, psum, pvd, hop)
+    ctx.frft(spec, -1.0)
+    out = spec.real.contiguous()
+    ctx.window(out, "sqrt_hann")
+    return out.cpu().numpy()
+
+
+def _pv_check(g, tag, f, n, out, last, psum, pvd):
+    want = g[tag + "_out"].reshape(-1, 2, n)[f]
+    assert np.abs(out - want).max() <= 1e-9 * max(np.abs(want).max(), 1e-300), (tag, f)
+    d = g[tag + "_data"].reshape(-1, 2, n, 2)[f]
+    got = pvd.cpu().numpy()
+    assert np.abs(got[..., 0] - d[..., 0]).max() < 1e-12, (tag, f)
+    assert np.abs(got[..., 1] - d[..., 1]).max() < 1e-5, (tag, f)          # Hz
+    assert np.abs(psum.cpu().numpy() - g[tag + "_phase_sum"].reshape(-1, 2, n)[f]).max() < 1e-8, (tag, f)
+    assert np.abs(last.cpu().numpy() - g[tag + "_last_phase"].reshape(-1, 2, n)[f]).max() < 1e-11, (tag, f)
+
+
+def test_pv_without_shift_nonlinear_fn_buffer_fn_own_hop(env, golden):
+    """PV without shift (all N bins carry state), a non-linear fn (several sources per destination, gaps), the
+    shift(function<void(WaveBuf&)>) overload, a per-object hop with use_global_hop(), reset(last) and reset(sum) one at a
+    time, and fill_from — each frame against the unmodified reference's dumps of out, data, phase_sum, last_phase."""
+    torch = env["torch"]
+    g = golden("pvmore")
+    n = int(g["n"][0])
+    frames_in = g["in"].reshape(-1, 2, n)
+    zeros = lambda *s: torch.zeros(s, dtype=torch.float64, device="cuda")
+    idx = 0
+    # 1. no shift
+    last, psum, pvd = zeros(2, n), zeros(2, n), zeros(2, n, 2)
+    for f in range(4):
+        out = _pv_frame(env, frames_in[idx], last, psum, pvd, 32.0)
+        _pv_check(g, "noshift", f, n, out, last, psum, pvd)
+        idx += 1
+    # 2. non-linear fn
+    last, psum, pvd = zeros(2, n), zeros(2, n), zeros(2, n, 2)
+    for f in range(4):
+        out = _pv_frame(env, frames_in[idx], last, psum, pvd, 32.0, lambda x: 300.0 + 0.6 * x + x * x / 40000.0)
+        _pv_check(g, "nonlin", f, n, out, last, psum, pvd)
+        idx += 1
+    # 3. fn on the whole buffer of bins / frequencies
+    last, psum, pvd = zeros(2, n), zeros(2, n), zeros(2, n, 2)
+    def buf_fn(b):
+        c = np.arange(b.shape[0])[:, None]
+        j = np.arange(b.shape[1])[None, :]
+        return b * (1.25 + 0.25 * c) + 3.0 * (j % 5)
+    for f in range(3):
+        out = _pv_frame(env, frames_in[idx], last, psum, pvd, 32.0, buf_fn)
+        _pv_check(g, "bufshift", f, n, out, last, psum, pvd)
+        idx += 1
+    # 4. per-object hop 48.5, back to the global 32 at frame 2, reset(last) at 3, reset(sum) at 4
+    last, psum, pvd = zeros(2, n), zeros(2, n), zeros(2, n, 2)
+    hops = g["ownhop_hop"]
+    assert list(hops) == [48.5, 48.5, 32.0, 32.0, 32.0, 32.0]
+    for f in range(6):
+        if f == 3:
+            last.zero_()
+        if f == 4:
+            psum.zero_()
+        out = _pv_frame(env, frames_in[idx], last, psum, pvd, float(hops[f]), lambda x: x * 1.5)
+        _pv_check(g, "ownhop", f, n, out, last, psum, pvd)
+        idx += 1
+    # 5. fill_from: a copy continues from the same state (global hop), no shift
+    out = _pv_frame(env, frames_in[idx], last.clone(), psum.clone(), pvd.clone(), 32.0)
+    want = g["copy_out"].reshape(2, n)
+    assert np.abs(out - want).max() <= 1e-9 * np.abs(want).max()

@@ -41,10 +41,21 @@ struct GenHash {
         h ^= h >> 15;
         h *= 2246822519u;
         h ^= h >> 13;
-        // x / 32768.0 / (double)(1 + (i >> 4)): the first division is exact, the second correctly rounded
+        // x / 32768.0 / (double)(1 + (i >> 4)): the first division is exact; the second as a Newton reciprocal
+        // (shared by both components) and one exact-remainder correction of each quotient (Markstein)
         const double d = (double)(1 + (i >> 4));
-        return mk<double>(__ddiv_rn((double)((int)(h & 0xffff) - 32768) * (1.0 / 32768.0), d),
-                          __ddiv_rn((double)((int)(h >> 16) - 32768) * (1.0 / 32768.0), d));
+        double r;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+        double e = fma(-d, r, 1.0);
+        r = fma(r, e, r);
+        e = fma(-d, r, 1.0);
+        r = fma(r, e, r);
+        const double a = (double)((int)(h & 0xffff) - 32768) * (1.0 / 32768.0);
+        const double b = (double)((int)(h >> 16) - 32768) * (1.0 / 32768.0);
+        double qa = a * r, qb = b * r;
+        qa = fma(fma(-d, qa, a), r, qa);
+        qb = fma(fma(-d, qb, b), r, qb);
+        return mk<double>(qa, qb);
     }
 };
 // Spectrum values computed by the caller: device complex128 rows [channels][n] of this frame, bins 1..n-1 are read.
@@ -64,19 +75,23 @@ struct SubFft {
     static constexpr int C = CMAX < (1 << LO) ? CMAX : (1 << LO);
     static constexpr int NT = C * T;
 };
-template <int LOG2M, int T, int P, int END>
+// LIN: the first pass reads its input unswizzled (a tile just copied in from global memory)
+template <int LOG2M, int T, int P, int END, bool LIN = false>
 struct SpecPasses {
-    static __device__ __forceinline__ cd *run(int lt, cd *src, cd *dst, const cd *tw) {
+    static __device__ __forceinline__ cd *run(int lt, const cd *src, cd *dst, cd *other, const cd *tw) {
         stockham_pass_io<double, LOG2M, T, P>(
-            lt, tw, [&](int a, int c) { return src[Swz<double>::f(a) ^ Swz<double>::f(c)]; },
+            lt, tw,
+            [&](int a, int c) { return (LIN && P == 0) ? src[a + c] : src[Swz<double>::f(a) ^ Swz<double>::f(c)]; },
             [&](int a, int c, cd v) { dst[Swz<double>::f(a) ^ Swz<double>::f(c)] = v; });
-        __syncthreads();
-        return SpecPasses<LOG2M, T, P + 1, END>::run(lt, dst, src, tw);
+        // a sub-transform of 256 points is run by exactly one warp (T = 32): its passes need no block barrier
+        if (T == 32) __syncwarp();
+        else __syncthreads();
+        return SpecPasses<LOG2M, T, P + 1, END, LIN>::run(lt, dst, other, dst, tw);
     }
 };
-template <int LOG2M, int T, int END>
-struct SpecPasses<LOG2M, T, END, END> {
-    static __device__ __forceinline__ cd *run(int, cd *src, cd *, const cd *) { return src; }
+template <int LOG2M, int T, int END, bool LIN>
+struct SpecPasses<LOG2M, T, END, END, LIN> {
+    static __device__ __forceinline__ cd *run(int, const cd *src, cd *, cd *, const cd *) { return const_cast<cd *>(src); }
 };
 
 // e^{-i pi q / n} for 0 <= q < 2n, argument exact
@@ -87,88 +102,159 @@ __device__ __forceinline__ cd unit_w(long long q, double inv_n) {
 }
 
 // ---- kernel A: one CTA = C consecutive columns k2 of one channel ----
+// wa[k1] = e^{-i pi k1 / n1} (n1 entries), wb[k2] = e^{-i pi k2 / n} (n2 entries): W^k = wa[k1] * wb[k2] for k = n2*k1 + k2
 template <int L1, int L2, class Gen>
-__global__ void __launch_bounds__(SubFft<L1, L2>::NT) spectral_cols_kernel(Gen gen, cd *scratch, const cd *tw1, int channels) {
+__global__ void __launch_bounds__(SubFft<L1, L2>::NT, SubFft<L1, L2>::NT >= 256 ? 3 : 4)
+spectral_cols_kernel(Gen gen, cd *scratch, const cd *tw1, const cd *wa, const cd *wb, int channels) {
     using F = SubFft<L1, L2>;
     constexpr int n1 = 1 << L1, n2 = 1 << L2, C = F::C, NT = F::NT;
     constexpr long long n = (long long)n1 * n2;
+    // sub-transform c lives at c * SP of a tile: the stride is padded by one element so that the C columns a warp touches
+    // together (consecutive threads = consecutive columns) fall into different banks
+    constexpr int SP = n1 + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cd *bufA = reinterpret_cast<cd *>(smem_raw), *bufB = bufA + C * n1;
-    const double inv_n = 1.0 / (double)n;
+    cd *bufA = reinterpret_cast<cd *>(smem_raw), *bufB = bufA + C * SP;
     const int groups = n2 / C;
+    // a thread keeps one column (c) and walks k1 / j1 in steps of NT / C
+    constexpr int STEP = NT / C;
+    const int c = threadIdx.x % C, r0 = threadIdx.x / C;
     for (long long b = blockIdx.x; b < (long long)channels * groups; b += gridDim.x) {
-        const int ch = (int)(b / groups), k2_0 = (int)(b % groups) * C;
-        // G[k], k = n2*k1 + k2, for the C columns: consecutive threads take consecutive k2 (the caller's spectrum rows,
-        // when the generator reads memory, are then read in contiguous pieces)
-        for (int i = threadIdx.x; i < C * n1; i += NT) {
-            const int c = i % C, k1 = i / C;
-            const long long k = (long long)n2 * k1 + k2_0 + c;
+        const int ch = (int)(b / groups), k2 = (int)(b % groups) * C + c;
+        const cd wk2 = TSB_LDG(&wb[k2]);
+        for (int k1 = r0; k1 < n1; k1 += STEP) {  // G[k], k = n2*k1 + k2
+            const long long k = (long long)n2 * k1 + k2;
             cd g = mk<double>(0.0, 0.0);
             if (k > 0) {  // (bins 0 and n are the carried ones: kernel B adds their contribution)
                 const cd a = gen(ch, (int)k), bb = conj(gen(ch, (int)(n - k)));
-                const cd s = a + bb, d = a - bb;
-                const cd w = unit_w(k, inv_n);           // W^k
-                const cd wd = cmul(w, d);
-                g = mk<double>(s.x - wd.y, s.y + wd.x);  // s + i*W^k*d
+                const cd sm = a + bb, d = a - bb;
+                const cd wd = cmul(cmul(TSB_LDG(&wa[k1]), wk2), d);  // W^k * d
+                g = mk<double>(sm.x - wd.y, sm.y + wd.x);          // sm + i*W^k*d
             }
-            bufA[c * n1 + Swz<double>::f(k1)] = g;
+            bufA[c * SP + Swz<double>::f(k1)] = g;
         }
         __syncthreads();
         const int gi = threadIdx.x / F::T, lt = threadIdx.x % F::T;
-        cd *res = SpecPasses<L1, F::T, 0, RadixPlan<L1>::passes>::run(lt, bufA + gi * n1, bufB + gi * n1, tw1) - gi * n1;
-        // A[k2][j1] * e^{-2 pi i k2 j1 / n} -> scratch[ch][j1][k2]
-        cd *dst = scratch + (long long)ch * n;
-        for (int i = threadIdx.x; i < C * n1; i += NT) {
-            const int c = i % C, j1 = i / C;
-            const long long q = (long long)(k2_0 + c) * j1;          // < n
-            const cd w = unit_w(2 * q, inv_n);
-            dst[(long long)j1 * n2 + k2_0 + c] = cmul(res[c * n1 + Swz<double>::f(j1)], w);
+        cd *res = SpecPasses<L1, F::T, 0, RadixPlan<L1>::passes>::run(lt, bufA + gi * SP, bufB + gi * SP, bufA + gi * SP, tw1) - gi * SP;
+        __syncthreads();
+        {   // A[k2][j1] * e^{-2 pi i k2 j1 / n} -> scratch[ch][j1][k2]: the factor is base^j1 with base = wb[k2]^2; the
+            // thread starts at base^r0 (square-and-multiply) and advances by base^STEP (at most 8 steps: no drift)
+            const cd base = cmul(wk2, wk2);
+            cd w = mk<double>(1.0, 0.0), pw = base;
+#pragma unroll
+            for (int bit = 0; (1 << bit) < STEP; bit++) {
+                if ((r0 >> bit) & 1) w = cmul(w, pw);
+                pw = cmul(pw, pw);
+            }
+            const cd out_step = pw;  // base^STEP (STEP is a power of two)
+            cd *dst = scratch + (long long)ch * n + k2;
+            for (int j1 = r0; j1 < n1; j1 += STEP) {
+                dst[(long long)j1 * n2] = cmul(res[c * SP + Swz<double>::f(j1)], w);
+                w = cmul(w, out_step);
+            }
         }
         __syncthreads();
     }
 }
 
-// ---- kernel B: one CTA = C consecutive rows j1 of one channel ----
+// ---- kernel B: persistent CTAs, each walking tiles of C consecutive rows j1 of one channel ----
+// A tile (C rows of n2 points, contiguous in the scratch) arrives by ONE bulk asynchronous copy (cp.async.bulk, the
+// 1-D TMA path) that completes on an mbarrier; the copy of the next tile is issued as soon as the first pass has
+// consumed the staging buffer and runs behind the remaining passes and the overlap-add of the current one.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bar_wait(unsigned long long *bar, unsigned phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TSB_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TSB_DONE_%=;\n"
+        "bra TSB_WAIT_%=;\n"
+        "TSB_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
 template <int L1, int L2>
-__global__ void __launch_bounds__(SubFft<L2, L1>::NT)
+__global__ void __launch_bounds__(SubFft<L2, L1>::NT, 2)
 spectral_rows_kernel(const cd *scratch, const cd *tw2, int channels, double *out, long long out_stride, long long out_len,
                      long long pos0, const double *edge_in, double *edge_out, int pairs_aligned) {
     using F = SubFft<L2, L1>;
     constexpr int n1 = 1 << L1, n2 = 1 << L2, C = F::C, NT = F::NT;
     constexpr long long n = (long long)n1 * n2;
+    constexpr int SP = n2 + 1;  // padded stride of a sub-transform inside a work tile (see kernel A)
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cd *bufA = reinterpret_cast<cd *>(smem_raw), *bufB = bufA + C * n2;
+    cd *stage = reinterpret_cast<cd *>(smem_raw);           // [C][n2], as it lies in the scratch
+    cd *bufA = stage + C * n2, *bufB = bufA + C * SP;
+    __shared__ __align__(8) unsigned long long bar;
     const double inv_sqrt = 1.0 / sqrt((double)(2 * n));
     const double half_n = (double)n / 2.0;
     const int groups = n1 / C;
-    for (long long b = blockIdx.x; b < (long long)channels * groups; b += gridDim.x) {
+    const long long tiles = (long long)channels * groups;
+    constexpr unsigned TILE_BYTES = (unsigned)(C * n2 * sizeof(cd));
+    constexpr int STEP = NT / C, NOUT = (n2 / 2 + STEP - 1) / STEP;  // output pairs per thread
+    const int c = threadIdx.x % C, r0 = threadIdx.x / C;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && (long long)blockIdx.x < tiles) bulk_load(stage, scratch + (long long)blockIdx.x * C * n2, TILE_BYTES, &bar);
+    unsigned phase = 0;
+    for (long long b = blockIdx.x; b < tiles; b += gridDim.x) {
         const int ch = (int)(b / groups), j1_0 = (int)(b % groups) * C;
-        const cd *src = scratch + (long long)ch * n + (long long)j1_0 * n2;  // C rows, contiguous
-        for (int i = threadIdx.x; i < C * n2; i += NT) bufA[(i / n2) * n2 + Swz<double>::f(i % n2)] = src[i];
-        __syncthreads();
+        // the output samples this thread will add to (v[j], j = j1 + n1*j2 < n/2 -> samples 2j, 2j+1): requested now,
+        // they arrive while the rows are transformed
+        double *row = out + (long long)ch * out_stride + pos0;
+        double2 acc[NOUT];
+#pragma unroll
+        for (int u = 0; u < NOUT; u++) {
+            const int j2 = r0 + u * STEP;
+            const long long m = 2 * ((long long)(j1_0 + c) + (long long)n1 * j2);
+            acc[u] = make_double2(0.0, 0.0);
+            if (j2 < n2 / 2) {
+                if (pairs_aligned && pos0 + m + 1 < out_len) acc[u] = *reinterpret_cast<const double2 *>(row + m);
+                else {
+                    if (pos0 + m < out_len) acc[u].x = row[m];
+                    if (pos0 + m + 1 < out_len) acc[u].y = row[m + 1];
+                }
+            }
+        }
+        bar_wait(&bar, phase);  // the tile is in `stage`
+        phase ^= 1;
         const int gi = threadIdx.x / F::T, lt = threadIdx.x % F::T;
-        cd *res = SpecPasses<L2, F::T, 0, RadixPlan<L2>::passes>::run(lt, bufA + gi * n2, bufB + gi * n2, tw2) - gi * n2;
+        constexpr int PASSES = RadixPlan<L2>::passes;
+        // first pass: stage -> bufA; then the staging buffer is free for the next tile's copy
+        stockham_pass_io<double, L2, F::T, 0>(
+            lt, tw2, [&](int a, int cc) { return stage[gi * n2 + a + cc]; },
+            [&](int a, int cc, cd v) { bufA[gi * SP + (Swz<double>::f(a) ^ Swz<double>::f(cc))] = v; });
+        __syncthreads();
+        if (threadIdx.x == 0 && b + gridDim.x < tiles) bulk_load(stage, scratch + (b + gridDim.x) * C * n2, TILE_BYTES, &bar);
+        cd *res = SpecPasses<L2, F::T, 1, PASSES>::run(lt, bufA + gi * SP, bufB + gi * SP, bufA + gi * SP, tw2) - gi * SP;
+        __syncthreads();
         // the carried bins 0 and n of the spectrum: X0 + Xn*(-1)^m, i.e. (d + q) on even and (d - q) on odd samples
         const double d = edge_in ? edge_in[2 * ch] : 0.0, q = edge_in ? edge_in[2 * ch + 1] : 0.0;
         const double e_even = (d + q) * inv_sqrt, e_odd = (d - q) * inv_sqrt;
-        double *row = out + (long long)ch * out_stride + pos0;
-        // v[j], j = j1 + n1*j2, j < n/2  ->  samples m = 2j, 2j+1: consecutive threads take consecutive j1
-        for (int i = threadIdx.x; i < C * (n2 / 2); i += NT) {
-            const int c = i % C, j2 = i / C;
-            const cd v = res[c * n2 + Swz<double>::f(j2)];
+#pragma unroll
+        for (int u = 0; u < NOUT; u++) {
+            const int j2 = r0 + u * STEP;
+            if (j2 >= n2 / 2) continue;
+            const cd v = res[c * SP + Swz<double>::f(j2)];
             const long long m = 2 * ((long long)(j1_0 + c) + (long long)n1 * j2);
             const double y0 = fma(v.x, inv_sqrt, e_even), y1 = fma(v.y, inv_sqrt, e_odd);
             // the hack's window, `1.0 - abs(1.0 - i/(n/2.0))`, same expression
             const double w0 = 1.0 - fabs(1.0 - (double)m / half_n), w1 = 1.0 - fabs(1.0 - (double)(m + 1) / half_n);
+            const double2 t = make_double2(acc[u].x + y0 * w0, acc[u].y + y1 * w1);
             if (pairs_aligned && pos0 + m + 1 < out_len) {
-                double2 *p = reinterpret_cast<double2 *>(row + m);  // (pos0 and out_stride are even: 16-byte aligned)
-                double2 t = *p;
-                t.x += y0 * w0;
-                t.y += y1 * w1;
-                *p = t;
+                *reinterpret_cast<double2 *>(row + m) = t;  // (pos0 and out_stride are even: 16-byte aligned)
             } else {
-                if (pos0 + m < out_len) row[m] += y0 * w0;
-                if (pos0 + m + 1 < out_len) row[m + 1] += y1 * w1;
+                if (pos0 + m < out_len) row[m] = t.x;
+                if (pos0 + m + 1 < out_len) row[m + 1] = t.y;
             }
         }
         if (edge_out && j1_0 == 0 && threadIdx.x == 0) {
@@ -183,6 +269,7 @@ spectral_rows_kernel(const cd *scratch, const cd *tw2, int channels, double *out
 // ---- host side ----
 struct SpecCache {
     std::map<int, cd *> pass_tw;
+    std::map<int, std::pair<cd *, cd *>> unit_tabs;  // log2 n -> (wa[n1], wb[n2]) of kernel A
     cd *scratch = nullptr;
     size_t scratch_elems = 0;
     double *edge[2] = {nullptr, nullptr};
@@ -219,13 +306,42 @@ cudaError_t op_spectral_release(int device) {
     return cudaSuccess;
 }
 
+// wa[k1] = e^{-i pi k1 / n1}, wb[k2] = e^{-i pi k2 / n}, from sincospi-quality host values
+static cudaError_t spec_unit_tables(SpecCache &pc, int l1, int l2, const cd **wa, const cd **wb) {
+    auto it = pc.unit_tabs.find(l1 + l2);
+    if (it == pc.unit_tabs.end()) {
+        const long long n1 = 1LL << l1, n2 = 1LL << l2, n = n1 * n2;
+        std::vector<double> a(2 * n1), b(2 * n2);
+        const long double pi = 3.14159265358979323846264338327950288L;
+        for (long long k = 0; k < n1; k++) {
+            a[2 * k] = (double)cosl(-pi * (long double)k / (long double)n1);
+            a[2 * k + 1] = (double)sinl(-pi * (long double)k / (long double)n1);
+        }
+        for (long long k = 0; k < n2; k++) {
+            b[2 * k] = (double)cosl(-pi * (long double)k / (long double)n);
+            b[2 * k + 1] = (double)sinl(-pi * (long double)k / (long double)n);
+        }
+        cd *da = nullptr, *db = nullptr;
+        cudaError_t e = cudaMalloc(&da, a.size() * 8);
+        if (e == cudaSuccess) e = cudaMalloc(&db, b.size() * 8);
+        if (e == cudaSuccess) e = cudaMemcpy(da, a.data(), a.size() * 8, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(db, b.data(), b.size() * 8, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return e;
+        it = pc.unit_tabs.emplace(l1 + l2, std::make_pair(da, db)).first;
+    }
+    *wa = it->second.first;
+    *wb = it->second.second;
+    return cudaSuccess;
+}
+
 template <int L1, int L2>
 static cudaError_t run_frames(SpecCache &pc, const SpectralJob &jb, cudaStream_t st, long long *launches) {
     constexpr long long n = 1LL << (L1 + L2);
-    const cd *tw1, *tw2;
+    const cd *tw1, *tw2, *wa, *wb;
     cudaError_t e;
     if ((e = spec_twiddles(pc, L1, &tw1)) != cudaSuccess) return e;
     if ((e = spec_twiddles(pc, L2, &tw2)) != cudaSuccess) return e;
+    if ((e = spec_unit_tables(pc, L1, L2, &wa, &wb)) != cudaSuccess) return e;
     const size_t need = (size_t)jb.channels * n;
     if (pc.scratch_elems < need) {
         if (pc.scratch) cudaFree(pc.scratch);
@@ -250,21 +366,29 @@ static cudaError_t run_frames(SpecCache &pc, const SpectralJob &jb, cudaStream_t
     using FB = SubFft<L2, L1>;
     constexpr int n1 = 1 << L1, n2 = 1 << L2;
     constexpr int CA = FA::C, CB = FB::C;
-    const size_t smA = (size_t)2 * FA::C * n1 * sizeof(cd), smB = (size_t)2 * FB::C * n2 * sizeof(cd);
+    const size_t smA = (size_t)2 * FA::C * (n1 + 1) * sizeof(cd);
+    const size_t smB = ((size_t)FB::C * n2 + (size_t)2 * FB::C * (n2 + 1)) * sizeof(cd);  // staging tile + two work tiles
     auto kA_hash = spectral_cols_kernel<L1, L2, GenHash>;
     auto kA_buf = spectral_cols_kernel<L1, L2, GenBuffer>;
     auto kB = spectral_rows_kernel<L1, L2>;
     if ((e = cudaFuncSetAttribute(kA_hash, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(kA_buf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB)) != cudaSuccess) return e;
-    const unsigned gridA = (unsigned)((long long)jb.channels * (n2 / CA)), gridB = (unsigned)((long long)jb.channels * (n1 / CB));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const long long tilesB = (long long)jb.channels * (n1 / CB);
+    int perB = 1;  // resident CTAs of kernel B per SM: it is launched persistent, one wave
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perB, kB, FB::NT, smB)) != cudaSuccess) return e;
+    if (perB < 1) perB = 1;
+    const unsigned gridA = (unsigned)((long long)jb.channels * (n2 / CA));
+    const unsigned gridB = (unsigned)(tilesB < (long long)sms * perB ? tilesB : (long long)sms * perB);
     for (long long f = 0; f < jb.n_frames; f++) {
         if (jb.generator == SPEC_GEN_HASH) {
             GenHash g{(uint32_t)(jb.first_frame + f)};
-            kA_hash<<<gridA, FA::NT, smA, st>>>(g, pc.scratch, tw1, jb.channels);
+            kA_hash<<<gridA, FA::NT, smA, st>>>(g, pc.scratch, tw1, wa, wb, jb.channels);
         } else {
             GenBuffer g{reinterpret_cast<const cd *>(jb.spectrum) + (size_t)f * jb.channels * n, n};
-            kA_buf<<<gridA, FA::NT, smA, st>>>(g, pc.scratch, tw1, jb.channels);
+            kA_buf<<<gridA, FA::NT, smA, st>>>(g, pc.scratch, tw1, wa, wb, jb.channels);
         }
         const long long pos0 = jb.out_off0 + f * jb.hop;
         const int aligned = ((pos0 | jb.out_stride) & 1) == 0 && (reinterpret_cast<uintptr_t>(jb.out) & 15) == 0;
