@@ -160,6 +160,30 @@ typedef struct tsb_spectral_args {
 } tsb_spectral_args;
 int tsb_spectral_render(tsb_ctx *ctx, const tsb_spectral_args *args);
 
+/* ---- batched granular pitch shift with a frame size, hop and output length that change every frame (BASELINE cfg4;
+ * the reference's hacks/pitchshift-simple.cpp:1-11 on the scheduler's gather and float32 overlap-add,
+ * tinyspec.cpp:135-157,170-200): per frame window_hann(in), out.resize(in.size/shift), the hack's nearest-neighbour
+ * resample `for j: for (k = j/shift; k < (j+1)/shift; k++) out[k] = in[j]`, overlap-add at computed_hop.  One launch
+ * renders every lane (lane = stream*channels + channel) of every stream; the output is the reference's float32 stream
+ * bit for bit.  The per-frame tables are HOST arrays [streams][frames_max], filled by running the hack's control
+ * logic (it depends on t only) through the reference's clock — tinyspec-cling_b200/api.py: granular_schedule does it
+ * for a Python callback: win = frame size, in_off / out_off = I_f / P_f, hop = computed_hop after
+ * the callback, osize = out.size after the callback, shift = the hack's ratio.  Frame sizes up to 8192, osize up to
+ * 16384. */
+typedef struct tsb_granular_args {
+    const float *in;          /* device float32 [lanes][in_stride] */
+    int64_t in_stride, in_len;
+    float *out;               /* device float32 [lanes][out_stride] */
+    int64_t out_stride, out_len;
+    int32_t streams, channels;
+    int64_t frames_max;
+    const int64_t *n_frames;  /* host [streams] */
+    const int32_t *win, *hop, *osize;        /* host [streams][frames_max] */
+    const int64_t *in_off, *out_off;
+    const double *shift;
+} tsb_granular_args;
+int tsb_granular_render(tsb_ctx *ctx, const tsb_granular_args *args);
+
 /* Measurement aid: the device's measured non-tensor FMA rate in TFLOP/s (an FMA = 2 flops), fp64 or fp32, from a
  * kernel of independent FMA chains timed with CUDA events.  bench.py reports the chain kernel's arithmetic against it. */
 int tsb_probe_fma_peak(tsb_ctx *ctx, int32_t is_f64, double *tflops);

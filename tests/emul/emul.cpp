@@ -21,6 +21,10 @@ struct HostExec {
         for (int tid = 0; tid < CH::T; tid++) f(tid, regs[tid]);
     }
     template <class F>
+    void each_half(F f, int) {  // (the halves are independent between their passes: any order will do)
+        for (int tid = 0; tid < CH::T; tid++) f(tid, regs[tid]);
+    }
+    template <class F>
     bool each_or(F f) {
         bool any = false;
         for (int tid = 0; tid < CH::T; tid++) any = f(tid, regs[tid]) || any;

@@ -272,3 +272,49 @@ def test_pv_without_shift_nonlinear_fn_buffer_fn_own_hop(env, golden):
     out = _pv_frame(env, frames_in[idx], last.clone(), psum.clone(), pvd.clone(), 32.0)
     want = g["copy_out"].reshape(2, n)
     assert np.abs(out - want).max() <= 1e-9 * np.abs(want).max()
+
+
+# ---- batched granular render with per-frame sizes (BASELINE cfg4): tsb_granular_render ----
+def _granular_cb(stream, vary):
+    import math
+
+    def cb(f, t, W):
+        shift = math.sin(t) / 2 + 1
+        n = (1 << (6 + ((f + 1 + stream) % 8))) if vary else 1800
+        return int(W / shift), shift, n, n * (0.5 / shift)
+    return cb
+
+
+@pytest.mark.parametrize("name,vary", [("granular_1800", False), ("granular_vary", True)])
+def test_granular_render_is_the_reference_stream(env, golden, name, vary):
+    """one launch: gather, window_hann, the hack's nearest-neighbour resample and the float32 overlap-add with a frame
+    size (64..8192 or 1800), hop and output length that change every frame — the compiled reference's stream bit for bit"""
+    tsb, orc = env["tsb"], env["orc"]
+    g = golden(name)
+    samples, _, n_first, stream = (int(v) for v in g["meta"])
+    x = orc.gen_signal(stream, 2, samples)
+    s = tsb.granular_schedule(samples, _granular_cb(stream, vary), n_first=n_first or 4096)
+    assert s["n_frames"] == len(g["t"]) and np.array_equal(s["osize"], g["osize"])
+    y = env["ctx"].granular_render(dev(env, x.T), 2, [s]).cpu().numpy()
+    assert y.shape[1] == g["stream"].shape[0]
+    assert np.array_equal(y.T, g["stream"])
+
+
+def test_granular_render_256_streams(env):
+    """BASELINE cfg4 as specified: 256 stereo streams, each with its own frame-size schedule (64..8192, offset by the
+    stream index), in ONE launch; every stream against the oracle's render of it, bit for bit."""
+    tsb, orc = env["tsb"], env["orc"]
+    streams, samples = 256, 40000
+    xs = [orc.gen_signal(st, 2, samples) for st in range(streams)]
+    scheds = [tsb.granular_schedule(samples, _granular_cb(st, True), n_first=64) for st in range(streams)]
+    x = np.concatenate([v.T for v in xs], axis=0)
+    ctx = env["ctx"]
+    l0 = ctx.launches
+    y = ctx.granular_render(dev(env, x), 2, scheds).cpu().numpy()
+    assert ctx.launches - l0 == 1
+    for st in range(0, streams, 5):
+        r = orc.render_granular(xs[st], n_first=64, vary=True, stream_idx=st)
+        L = r["stream"].shape[0]
+        assert L == int(scheds[st]["out_off"][-1] + scheds[st]["hop"][-1])
+        assert np.array_equal(y[2 * st:2 * st + 2, :L].T, r["stream"]), st
+        assert not y[2 * st:2 * st + 2, L:].any()

@@ -453,6 +453,24 @@ def test_two_minute_render_does_not_diverge(env):
 
 
 @pytest.mark.gpu
+def test_cfg3_ten_minutes_teacher_forced(env):
+    """BASELINE configs[2] (8 channels, frame 4096, hop 1024, x1.5) over 10 minutes of audio, the way SURVEY.md §7
+    (hard part 2) prescribes for renders too long for a free-running 1e-9: every 2048 frames the oracle's PhaseVocoder
+    state (last_phase, phase_sum) is loaded into the GPU render, which must then reproduce the oracle's next 64 frames to
+    1e-9 of peak, however late in the render; the free-running render is held to the drift two correct double
+    implementations show against each other (6e-10 at 10 minutes between the reference's own FFT backends)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import cfg3_teacher_forced
+    r = cfg3_teacher_forced.run(600.0, every=2048, window=64, procs=8)
+    assert r["frames"] == 28120 and r["windows"] >= 13
+    assert r["teacher_forced_max_rel_worst"] <= F64_MAXREL
+    assert r["free_running_max_rel_worst"] <= 5e-9
+    assert max(x["max_phase_sum_rad"] for x in r["rows"]) > 5e7   # the regime the check is about
+
+
+@pytest.mark.gpu
 def test_fp32_two_minutes_at_x1p5_never_flips(env):
     """BASELINE.json: "PV phase state must never diverge" — fp32 mode at a NON-integer ratio (cfg3's x1.5), where a wrap
     decided on the other side than the reference's double arithmetic is a permanent sign flip of the bin

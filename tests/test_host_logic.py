@@ -85,3 +85,28 @@ def test_shift_map_matches_oracle(n, ratio):
             freq[dest[j]] = before[j, 1] * ratio
     assert np.array_equal(amp, after[:, 0])
     assert np.array_equal(freq, after[:, 1])
+
+
+def _granular_callback(stream, vary):
+    """the control logic of examples/granular.cpp (hacks/pitchshift-simple.cpp:3,5,10 with BASELINE cfg4's frame sizes)"""
+    import math
+
+    def cb(f, t, W):
+        shift = math.sin(t) / 2 + 1
+        n = (1 << (6 + ((f + 1 + stream) % 8))) if vary else 1800
+        return int(W / shift), shift, n, n * (0.5 / shift)
+    return cb
+
+
+@pytest.mark.parametrize("vary,n_first,stream", [(False, 4096, 0), (True, 64, 2), (True, 64, 7)])
+def test_granular_schedule_matches_the_oracle(vary, n_first, stream):
+    """tsb200.granular_schedule (the reference's scheduler and clock driven by a hack's control logic only) against the
+    frame tables of the C oracle's full render: frame sizes, input offsets, output positions, computed hops and t."""
+    from oracle import orc
+    samples = 60000
+    x = orc.gen_signal(stream, 2, samples)
+    r = orc.render_granular(x, n_first=0 if n_first == 4096 else n_first, vary=vary, stream_idx=stream)
+    s = tsb200.granular_schedule(samples, _granular_callback(stream, vary), n_first=n_first)
+    assert s["n_frames"] == r["frames"] > 0
+    for k in ("win", "in_off", "out_off", "hop", "t"):
+        assert np.array_equal(s[k], r["tables"][k]), k

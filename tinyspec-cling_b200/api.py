@@ -37,6 +37,13 @@ class _SpectralArgs(C.Structure):
                 ("load_state", C.c_int32)]
 
 
+class _GranularArgs(C.Structure):
+    _fields_ = [("in_", C.c_void_p), ("in_stride", C.c_int64), ("in_len", C.c_int64), ("out", C.c_void_p),
+                ("out_stride", C.c_int64), ("out_len", C.c_int64), ("streams", C.c_int32), ("channels", C.c_int32),
+                ("frames_max", C.c_int64), ("n_frames", C.c_void_p), ("win", C.c_void_p), ("hop", C.c_void_p),
+                ("osize", C.c_void_p), ("in_off", C.c_void_p), ("out_off", C.c_void_p), ("shift", C.c_void_p)]
+
+
 class _ChainArgs(C.Structure):
     _fields_ = [("in_", C.c_void_p), ("in_stride", C.c_int64), ("in_len", C.c_int64), ("out", C.c_void_p),
                 ("out_stride", C.c_int64), ("out_len", C.c_int64), ("n_frames", C.c_int64), ("in_off0", C.c_int64),
@@ -75,6 +82,7 @@ def _load():
     L.tsb_chain_render.argtypes = [P, P, C.POINTER(_ChainArgs)]
     L.tsb_chain_render_host.argtypes = [P, P, C.POINTER(_ChainArgs)]
     L.tsb_spectral_render.argtypes = [P, C.POINTER(_SpectralArgs)]
+    L.tsb_granular_render.argtypes = [P, C.POINTER(_GranularArgs)]
     I64, D = C.c_int64, C.c_double
     L.tsb_window.argtypes = [P, P, I64, I64, C.c_int32]
     L.tsb_fft_forward.argtypes = [P, P, P, I64, I64]
@@ -133,6 +141,41 @@ def schedule_const(in_len, n, hop, rate=48000.0, max_frames=-1):
                                     tabs["hop"].ctypes.data, tabs["t"].ctypes.data))
     tabs["n_frames"] = F
     return tabs
+
+
+def granular_schedule(in_len, callback, rate=48000.0, n_first=4096, max_frames=None):
+    """The reference's frame scheduler and clock (tinyspec.cpp:135-168) run with a hack's CONTROL logic only, for hacks
+    whose frame size / hop / output length change every frame (BASELINE cfg4): callback(f, t, W) -> (osize, shift,
+    n_next, hop_next) is what the hack decides in frame f at time t with frame size W — the size of `out` after the
+    callback, the resampling ratio, and the arguments of its next_hop_* call (the next frame size and the new hop).
+    Returns the tables tsb_granular_render takes: win, in_off, out_off, hop (computed_hop after the callback), osize,
+    shift, t."""
+    rows = dict(win=[], in_off=[], out_off=[], hop=[], osize=[], shift=[], t=[])
+    new_window, computed_hop = int(n_first), 2048          # tinyspec.cpp:38-41
+    hop_s, hop_f = hop_fixed(2048.0)
+    in_pos = out_pos = ts = tf = 0
+    f = 0
+    while max_frames is None or f < max_frames:
+        W = new_window                                      # latched for this frame, :135-139
+        if in_len - in_pos < computed_hop + W:              # starved, :142-143
+            break
+        in_pos += computed_hop                              # :147-149
+        t = (float(ts) + float(tf) / 18446744073709551616.0) / rate   # current_time_secs, :110-112
+        osize, shift, n_next, hop_next = callback(f, t, W)
+        new_window = int(n_next)
+        if hop_next >= 0:                                   # set_hop ignores a negative hop, rtlib/control.hpp:23
+            hop_s, hop_f = hop_fixed(float(hop_next))
+        computed_hop = hop_s + (1 if tf + hop_f >= 1 << 64 else 0)   # :163-168
+        ts += computed_hop
+        tf = (tf + hop_f) & ((1 << 64) - 1)
+        for k, v in (("win", W), ("in_off", in_pos), ("out_off", out_pos), ("hop", computed_hop), ("osize", int(osize)),
+                     ("shift", float(shift)), ("t", t)):
+            rows[k].append(v)
+        out_pos += computed_hop
+        f += 1
+    out = {k: np.asarray(v, np.float64 if k in ("shift", "t") else np.int64) for k, v in rows.items()}
+    out["n_frames"] = f
+    return out
 
 
 def shift_map(n, rate, fn_bins):
@@ -221,6 +264,39 @@ class Context:
         a.load_state = int(load_state)
         _check(_load().tsb_spectral_render(self.h, C.byref(a)))
         self._keep_spec = (out, spectrum, state_edge)
+        return out
+
+    def granular_render(self, x, channels, schedules, out=None):
+        """tsb_granular_render: x CUDA float32 [streams*channels, L]; schedules = one granular_schedule() result per
+        stream.  Returns the float32 output streams [streams*channels, max total hop] (the reference's stream per lane;
+        a shorter stream is zero past its end)."""
+        import torch
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous()
+        streams = len(schedules)
+        assert x.shape[0] == streams * channels
+        fm = max(1, max(int(s["n_frames"]) for s in schedules))
+        tabs = {k: np.zeros((streams, fm), np.float64 if k == "shift" else (np.int64 if k in ("in_off", "out_off") else np.int32))
+                for k in ("win", "hop", "osize", "in_off", "out_off", "shift")}
+        nf = np.zeros(streams, np.int64)
+        total = 0
+        for i, s in enumerate(schedules):
+            F = int(s["n_frames"])
+            nf[i] = F
+            for k in tabs:
+                tabs[k][i, :F] = s[k][:F]
+            if F:
+                total = max(total, int(s["out_off"][F - 1] + s["hop"][F - 1]))
+        if out is None:
+            out = torch.zeros((x.shape[0], max(total, 1)), dtype=torch.float32, device=x.device)
+        assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.shape[0] == x.shape[0]
+        a = _GranularArgs()
+        a.in_, a.in_stride, a.in_len = x.data_ptr(), x.stride(0) if x.shape[0] > 1 else x.shape[1], x.shape[1]
+        a.out, a.out_stride, a.out_len = out.data_ptr(), out.stride(0) if out.shape[0] > 1 else out.shape[1], out.shape[1]
+        a.streams, a.channels, a.frames_max = streams, channels, fm
+        a.n_frames = nf.ctypes.data
+        for k in tabs:
+            setattr(a, k, tabs[k].ctypes.data)
+        _check(_load().tsb_granular_render(self.h, C.byref(a)))
         return out
 
     def fma_peak(self, precision="f64"):

@@ -13,6 +13,7 @@
 #include "tsb_ops.hpp"
 #include "tsb_plan.hpp"
 #include "tsb_spectral.hpp"
+#include "tsb_granular.hpp"
 #include <map>
 
 using namespace tsb;
@@ -694,6 +695,90 @@ TSB_API int tsb_spectral_render(tsb_ctx *c, const tsb_spectral_args *a) {
     cudaError_t e = op_spectral_render(c->device, jb, c->stream, &l);
     c->launches += l;
     if (e != cudaSuccess) return fail(TSB_ECUDA, "spectral synthesis: %s", cudaGetErrorString(e));
+    return TSB_OK;
+}
+
+// ---- batched granular render (cfg4) ----
+static int window_table_dev(tsb_ctx *c, int64_t size, int kind, double **out) {
+    auto key = std::make_pair(size, kind);
+    auto it = c->windows.find(key);
+    if (it == c->windows.end()) {
+        std::vector<double> w = window_table(kind, (int)size);
+        double *d = nullptr;
+        cudaError_t e = cudaMalloc(&d, (w.size() ? w.size() : 1) * sizeof(double));
+        if (e != cudaSuccess) return fail(TSB_ENOMEM, "cudaMalloc: %s", cudaGetErrorString(e));
+        CU(cudaMemcpy(d, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice));
+        it = c->windows.emplace(key, d).first;
+    }
+    *out = it->second;
+    return TSB_OK;
+}
+TSB_API int tsb_granular_render(tsb_ctx *c, const tsb_granular_args *a) {
+    if (!c || !a) return fail(TSB_EINVAL, "null argument");
+    if (a->streams < 0 || a->channels <= 0 || a->frames_max < 0) return fail(TSB_EINVAL, "bad streams / channels / frames_max");
+    if (a->streams == 0 || a->frames_max == 0) return TSB_OK;
+    if (!a->in || !a->out || !a->n_frames || !a->win || !a->hop || !a->osize || !a->in_off || !a->out_off || !a->shift)
+        return fail(TSB_EINVAL, "null table or buffer");
+    CU(cudaSetDevice(c->device));
+    const size_t S = (size_t)a->streams, FM = (size_t)a->frames_max, cells = S * FM;
+    // validate, and number the distinct frame sizes (their Hann tables are cached per context)
+    std::map<int32_t, int32_t> ids;
+    std::vector<int32_t> win_id(cells, 0);
+    std::vector<const double *> wt;
+    for (size_t s = 0; s < S; s++) {
+        if (a->n_frames[s] < 0 || a->n_frames[s] > a->frames_max) return fail(TSB_EINVAL, "n_frames[%zu] out of range", s);
+        for (int64_t f = 0; f < a->n_frames[s]; f++) {
+            const size_t q = s * FM + (size_t)f;
+            const int32_t W = a->win[q];
+            if (W < 1 || W > 8192) return fail(TSB_EUNSUPPORTED, "frame size %d (stream %zu, frame %lld): 1..8192 supported", W, s, (long long)f);
+            if (a->osize[q] < 0 || a->osize[q] > 16384) return fail(TSB_EUNSUPPORTED, "output frame of %d samples: 0..16384 supported", a->osize[q]);
+            if (a->hop[q] < 0 || a->hop[q] > 16384) return fail(TSB_EUNSUPPORTED, "hop %d: 0..16384 supported", a->hop[q]);
+            if (!(a->shift[q] > 0)) return fail(TSB_EINVAL, "shift must be positive");
+            auto it = ids.find(W);
+            if (it == ids.end()) {
+                double *d = nullptr;
+                int r = window_table_dev(c, W, TSB_WIN_HANN, &d);
+                if (r) return r;
+                it = ids.emplace(W, (int32_t)wt.size()).first;
+                wt.push_back(d);
+            }
+            win_id[q] = it->second;
+        }
+    }
+    // one device block for the tables
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t b_nf = al(S * 8), b_i32 = al(cells * 4), b_i64 = al(cells * 8), b_wt = al(wt.size() * 8);
+    const size_t total = b_nf + 4 * b_i32 + 2 * b_i64 + b_i64 + b_wt;
+    char *blk = nullptr;
+    cudaError_t e = cudaMalloc(&blk, total);
+    if (e != cudaSuccess) return fail(TSB_ENOMEM, "granular tables (%zu bytes): %s", total, cudaGetErrorString(e));
+    char *q = blk;
+    auto put = [&](const void *h, size_t bytes, size_t slot) {
+        char *d = q;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream);
+        q += slot;
+        return d;
+    };
+    GranularJob jb;
+    jb.n_frames = (const long long *)put(a->n_frames, S * 8, b_nf);
+    jb.win = (const int *)put(a->win, cells * 4, b_i32);
+    jb.hop = (const int *)put(a->hop, cells * 4, b_i32);
+    jb.osize = (const int *)put(a->osize, cells * 4, b_i32);
+    jb.win_id = (const int *)put(win_id.data(), cells * 4, b_i32);
+    jb.in_off = (const long long *)put(a->in_off, cells * 8, b_i64);
+    jb.out_off = (const long long *)put(a->out_off, cells * 8, b_i64);
+    jb.shift = (const double *)put(a->shift, cells * 8, b_i64);
+    jb.wtabs = (const double *const *)put(wt.data(), wt.size() * 8, b_wt);
+    jb.in = a->in; jb.in_stride = a->in_stride; jb.in_len = a->in_len;
+    jb.out = a->out; jb.out_stride = a->out_stride; jb.out_len = a->out_len;
+    jb.lanes = a->streams * a->channels;
+    jb.channels = a->channels;
+    jb.frames_max = a->frames_max;
+    if (e == cudaSuccess) e = op_granular_render(jb, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);  // the host tables / win_id / wt are about to go away
+    cudaFree(blk);
+    if (e != cudaSuccess) return fail(TSB_ECUDA, "granular render: %s", cudaGetErrorString(e));
+    c->launches++;
     return TSB_OK;
 }
 

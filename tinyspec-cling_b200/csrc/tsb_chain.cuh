@@ -1407,7 +1407,7 @@ struct PipePasses {
     static TSB_HD void run(Exec &ex, int lane, typename CH::Smem &sm, const typename CH::Tables &tb, const ChainArgs &a,
                            bool have_next, long long next_in_off, long long fetch_first, int fetch_cnt, bool have_cur,
                            long long out_pos, int hop) {
-        ex.each([&](int tid, typename CH::Regs &) {
+        auto body = [&](int tid, typename CH::Regs &) {
             if (tid < CH::T0) {
                 if (have_next) {
                     // The samples this frame adds were requested during the previous frame's last pass (below) and
@@ -1421,7 +1421,12 @@ struct PipePasses {
             } else if (have_cur) {
                 CH::template inv_pass<P, CH::T0, EMIT>(tid - CH::T0, lane, sm, tb, a, out_pos, hop);
             }
-        });
+        };
+        // The two halves work on buffers of their own (buf / ibuf) and meet again only in the PV phases: between
+        // their passes each half synchronises with itself alone (a named barrier over its T0 threads), so a heavy
+        // pass on one side (the windowed load, the overlap-add) no longer holds up the other side pass by pass.
+        if (P < END - 1) ex.each_half(body, CH::T0);
+        else ex.each(body);
         PipePasses<CH, P + 1, END>::template run<EMIT>(ex, lane, sm, tb, a, have_next, next_in_off, fetch_first, fetch_cnt,
                                                        have_cur, out_pos, hop);
     }

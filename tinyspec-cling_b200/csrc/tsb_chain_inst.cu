@@ -24,6 +24,13 @@ struct DevExec {
         f((int)threadIdx.x, rg);
         __syncthreads();
     }
+    // f, then a barrier over this thread's half of the CTA only (threads [0, half) and [half, 2*half): named barriers 1, 2)
+    template <class F>
+    __device__ __forceinline__ void each_half(F f, int half) {
+        f((int)threadIdx.x, rg);
+        if ((int)threadIdx.x >= half) asm volatile("bar.sync 2, %0;" ::"r"(half) : "memory");
+        else asm volatile("bar.sync 1, %0;" ::"r"(half) : "memory");
+    }
     // same, and tells every thread whether f returned true for any of them
     template <class F>
     __device__ __forceinline__ bool each_or(F f) {
