@@ -238,6 +238,21 @@ int tsb_timepar_scan_lanes(tsb_timepar *tp, int32_t lane0, int32_t n_lanes, cons
  * first lead-in frame of the next rank's block), instead of after its last frame (carry_frame < 0). */
 int tsb_timepar_scan_at(tsb_timepar *tp, int32_t lane0, int32_t n_lanes, const double *carry_in, double *carry_out,
                         int64_t carry_frame);
+/* The scan FUSED with the hand-over to the next GPU of a time-sharded render (one process per GPU on an NVLink box):
+ * carry_in / flag_in (NULL on the first rank) are buffers in this GPU's memory — [lanes][n/2] float64 and one int32
+ * per 16 bins of a lane — that the previous rank's kernel fills over NVLink; carry_out_peer / flag_out_peer (NULL
+ * on the last rank) are the next rank's buffers mapped into this process (tsb_ipc_open).  Each CTA waits until its
+ * own flag equals `epoch` (acquire, system scope), adds its 16 bins' increments frame by frame, writes the sums
+ * before frame `carry_frame` to the peer and releases the peer's flag: no host involvement, no NCCL call, and the
+ * ranks' scans overlap bin block by bin block.  Use a new epoch (and, to be safe against a rank running ahead,
+ * alternate two buffer sets) for every render. */
+int tsb_timepar_scan_chain(tsb_timepar *tp, const double *carry_in, const int32_t *flag_in, double *carry_out_peer,
+                           int32_t *flag_out_peer, int32_t epoch, int64_t carry_frame);
+/* Peer memory between the processes of one box: a 64-byte handle for an allocation made with tsb_malloc
+ * (cudaIpcGetMemHandle), mapping a peer's handle into this process (peer access is enabled on demand), unmapping it. */
+int tsb_ipc_export(tsb_ctx *ctx, void *dptr, void *handle64);
+int tsb_ipc_open(tsb_ctx *ctx, const void *handle64, void **dptr);
+int tsb_ipc_close(tsb_ctx *ctx, void *dptr);
 /* initial state = args->state_* (NULL or load_state 0: reset state); they receive the final state */
 int tsb_timepar_render(tsb_timepar *tp);
 int tsb_timepar_destroy(tsb_timepar *tp);

@@ -98,6 +98,13 @@ def _load():
     L.tsb_timepar_scan.argtypes = [P, P, P]
     L.tsb_timepar_scan_lanes.argtypes = [P, I32, I32, P, P]
     L.tsb_timepar_scan_at.argtypes = [P, I32, I32, P, P, C.c_int64]
+    L.tsb_timepar_scan_chain.argtypes = [P, P, P, P, P, I32, C.c_int64]
+    L.tsb_ipc_export.argtypes = [P, P, P]
+    L.tsb_ipc_open.argtypes = [P, P, C.POINTER(P)]
+    L.tsb_ipc_close.argtypes = [P, P]
+    L.tsb_malloc.argtypes = [P, C.c_size_t, C.POINTER(P)]
+    L.tsb_free.argtypes = [P, P]
+    L.tsb_memset.argtypes = [P, P, C.c_int, C.c_size_t]
     L.tsb_timepar_render.argtypes = [P]
     L.tsb_timepar_destroy.argtypes = [P]
     L.tsb_chain_render_timepar.argtypes = [P, P, C.POINTER(_ChainArgs), P, I32]
@@ -298,6 +305,31 @@ class Context:
             setattr(a, k, tabs[k].ctypes.data)
         _check(_load().tsb_granular_render(self.h, C.byref(a)))
         return out
+
+    # ---- raw device memory and peer mapping (multi-GPU chains, shard.GpuBackend.link) ----
+    def malloc(self, nbytes):
+        p = C.c_void_p()
+        _check(_load().tsb_malloc(self.h, nbytes, C.byref(p)))
+        return p.value
+
+    def free(self, ptr):
+        _check(_load().tsb_free(self.h, ptr))
+
+    def memset(self, ptr, value, nbytes):
+        _check(_load().tsb_memset(self.h, ptr, value, nbytes))
+
+    def ipc_export(self, ptr):
+        buf = C.create_string_buffer(64)
+        _check(_load().tsb_ipc_export(self.h, ptr, buf))
+        return bytes(buf.raw)
+
+    def ipc_open(self, handle):
+        p = C.c_void_p()
+        _check(_load().tsb_ipc_open(self.h, C.create_string_buffer(handle, 64), C.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr):
+        _check(_load().tsb_ipc_close(self.h, ptr))
 
     def fma_peak(self, precision="f64"):
         """measured non-tensor FMA rate of the device in TFLOP/s (tsb_probe_fma_peak)"""
@@ -561,6 +593,11 @@ class TimePar:
                                            out.data_ptr(), int(carry_frame)))
         self._keep_carry = carry_in
         return out
+
+    def scan_chain(self, carry_in, flag_in, carry_out_peer, flag_out_peer, epoch, carry_frame=-1):
+        """tsb_timepar_scan_chain: raw device pointers (ints; None = first / last rank)"""
+        _check(_load().tsb_timepar_scan_chain(self.h, carry_in, flag_in, carry_out_peer, flag_out_peer, int(epoch),
+                                              int(carry_frame)))
 
     def render(self):
         _check(_load().tsb_timepar_render(self.h))

@@ -1015,6 +1015,54 @@ TSB_API int tsb_timepar_scan_at(tsb_timepar *tp, int32_t lane0, int32_t n_lanes,
     tp->scanned = true;
     return TSB_OK;
 }
+// The same scan as ONE kernel fused with the transfer to the next GPU (a chain of ranks, one process per GPU):
+// carry_in / flag_in are buffers in THIS GPU's memory that the previous rank's kernel writes over NVLink (peer-mapped
+// through tsb_ipc_*), carry_out_peer / flag_out_peer point into the next rank's; every CTA (16 bins of a lane) waits for
+// its own flag, adds its frames and hands its bins on, so the ranks' scans overlap bin block by bin block.
+TSB_API int tsb_timepar_scan_chain(tsb_timepar *tp, const double *carry_in, const int32_t *flag_in, double *carry_out_peer,
+                                   int32_t *flag_out_peer, int32_t epoch, int64_t carry_frame) {
+    if (!tp) return fail(TSB_EINVAL, "null argument");
+    if (!tp->prepassed) return fail(TSB_EINVAL, "tsb_timepar_scan_chain before tsb_timepar_prepass");
+    if ((carry_in == nullptr) != (flag_in == nullptr) || (carry_out_peer == nullptr) != (flag_out_peer == nullptr))
+        return fail(TSB_EINVAL, "carry and flag pointers come in pairs");
+    if (carry_frame >= tp->args.n_frames) return fail(TSB_EINVAL, "carry_frame %lld beyond the block's %lld frames", (long long)carry_frame, (long long)tp->args.n_frames);
+    tsb_ctx *c = tp->ctx;
+    CU(cudaSetDevice(c->device));
+    const tsb_chain_args &a = tp->args;
+    if (tp->plan->desc.program != TSB_PROG_PV_SHIFT || a.n_frames == 0 || tp->lanes == 0)
+        return fail(TSB_EUNSUPPORTED, "the chained scan is for phase-vocoder blocks with frames");
+    const double *base = carry_in;
+    if (!base && a.state_phase_sum && a.load_state) base = a.state_phase_sum;
+    CU(op_timepar_scan(tp->d_inc, a.n_frames, tp->d_seg, tp->n_seg, base, tp->d_sum, carry_out_peer, (long long)tp->lanes,
+                       (long long)tp->m, 0, (long long)tp->lanes, c->stream, carry_frame, flag_in, flag_out_peer, epoch));
+    c->launches++;
+    tp->scanned = true;
+    return TSB_OK;
+}
+// Peer memory between the processes of one box (cudaIpc*): export an allocation made with tsb_malloc, map a peer's.
+TSB_API int tsb_ipc_export(tsb_ctx *c, void *dptr, void *handle64) {
+    if (!c || !dptr || !handle64) return fail(TSB_EINVAL, "null argument");
+    CU(cudaSetDevice(c->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, dptr));
+    memcpy(handle64, &h, 64);
+    return TSB_OK;
+}
+TSB_API int tsb_ipc_open(tsb_ctx *c, const void *handle64, void **dptr) {
+    if (!c || !dptr || !handle64) return fail(TSB_EINVAL, "null argument");
+    CU(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CU(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return TSB_OK;
+}
+TSB_API int tsb_ipc_close(tsb_ctx *c, void *dptr) {
+    if (!c) return fail(TSB_EINVAL, "null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaIpcCloseMemHandle(dptr));
+    return TSB_OK;
+}
 TSB_API int tsb_timepar_scan(tsb_timepar *tp, const double *carry_in, double *carry_out) {
     if (!tp) return fail(TSB_EINVAL, "null argument");
     return tsb_timepar_scan_lanes(tp, 0, (int32_t)tp->lanes, carry_in, carry_out);

@@ -557,7 +557,8 @@ cudaError_t op_pv_shift(const double *tmp, double *pvdata, const double *fn_freq
 constexpr int SCAN_BINS = 16, SCAN_TILE = 128, SCAN_THREADS = 256;
 __global__ void __launch_bounds__(SCAN_THREADS)
 timepar_scan_kernel(const double *inc, long long inc_frames, const long long *seg_tab, int n_seg, const double *base,
-                    double *sum_rows, double *carry_out, long long lanes, long long m, long long lane0, long long carry_at) {
+                    double *sum_rows, double *carry_out, long long lanes, long long m, long long lane0, long long carry_at,
+                    const int *flag_in, int *flag_out, int epoch) {
     __shared__ __align__(16) double tile[2][SCAN_TILE][SCAN_BINS];
     const long long bin_blocks = (m + SCAN_BINS - 1) / SCAN_BINS;
     // lanes lane0 .. lane0 + gridDim.x / bin_blocks - 1; base / carry_out are indexed from lane0
@@ -578,12 +579,34 @@ timepar_scan_kernel(const double *inc, long long inc_frames, const long long *se
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     };
     const long long idx = lane * m + bin0 + b, sidx = sub * m + bin0 + b;
-    double c = (tid < SCAN_BINS && bin_ok && base) ? base[sidx] : 0.0;
     int s = 0;
     long long next_start = f_begin;
     // carry_out = the running sum before frame carry_at (the next block's first lead-in frame), or after the last frame
     const bool carry_inside = carry_at >= f_begin && carry_at < f_end;
     fetch(0, f_begin);
+    // Chained over GPUs (tsb_timepar_scan_chain): `base` lies in THIS GPU's memory and is written by the previous
+    // rank's kernel over NVLink, one CTA's 16 bins at a time, followed by that CTA's flag (= epoch, release at system
+    // scope); carry_out / flag_out point into the NEXT rank's memory.  The first tiles are already on their way.
+    if (flag_in && tid < SCAN_BINS) {
+        const int *fp = flag_in + blockIdx.x;
+        int v;
+        do {
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(fp) : "memory");
+        } while (v != epoch);
+    }
+    double c = 0.0;
+    if (tid < SCAN_BINS && bin_ok && base) {
+        if (flag_in) asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(c) : "l"(base + sidx) : "memory");
+        else c = base[sidx];
+    }
+    bool sent = false;
+    auto send = [&]() {  // this CTA's bins are in carry_out: tell the next rank
+        if (!flag_out || sent) return;
+        sent = true;
+        __threadfence_system();
+        __syncwarp(tid < SCAN_BINS ? 0xffffu : 0xffff0000u);
+        if (tid == 0) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag_out + blockIdx.x), "r"(epoch) : "memory");
+    };
     int buf = 0;
     for (long long f0 = f_begin; f0 < f_end; f0 += SCAN_TILE, buf ^= 1) {
         fetch(buf ^ 1, f0 + SCAN_TILE);  // (an empty group past the end)
@@ -598,7 +621,10 @@ timepar_scan_kernel(const double *inc, long long inc_frames, const long long *se
                     s++;
                     next_start = s < n_seg ? seg_tab[SEG_COLS * s] : -1;
                 }
-                if (carry_inside && f0 + r == carry_at && carry_out) carry_out[sidx] = c;
+                if (carry_inside && f0 + r == carry_at && carry_out) {
+                    carry_out[sidx] = c;
+                    send();  // (all 16 threads of the CTA reach this frame together: same loop bounds)
+                }
                 // up to the next segment start (or the end of the tile) nothing but the additions: the loads do
                 // not depend on the sum, so the compiler batches them ahead of the dependent chain
                 int stop = (next_start > f0 + r && next_start < f0 + cnt) ? (int)(next_start - f0) : cnt;
@@ -614,14 +640,16 @@ timepar_scan_kernel(const double *inc, long long inc_frames, const long long *se
             if (sum_rows) sum_rows[(long long)s * lanes * m + idx] = c;
         if (carry_out && !carry_inside) carry_out[sidx] = c;
     }
+    if (tid < SCAN_BINS && flag_out) send();  // (bins past m included: the flag is per CTA)
 }
 cudaError_t op_timepar_scan(const double *inc, long long inc_frames, const long long *seg_tab, int n_seg, const double *base,
                             double *sum_rows, double *carry_out, long long lanes, long long m, long long lane0,
-                            long long n_lanes, cudaStream_t st, long long carry_at) {
+                            long long n_lanes, cudaStream_t st, long long carry_at, const int *flag_in, int *flag_out,
+                            int epoch) {
     if (n_lanes * m == 0 || n_seg <= 0) return cudaSuccess;
     const long long grid = ((m + SCAN_BINS - 1) / SCAN_BINS) * n_lanes;
     timepar_scan_kernel<<<(unsigned)grid, SCAN_THREADS, 0, st>>>(inc, inc_frames, seg_tab, n_seg, base, sum_rows, carry_out, lanes, m,
-                                                                 lane0, carry_at);
+                                                                 lane0, carry_at, flag_in, flag_out, epoch);
     return cudaGetLastError();
 }
 // out[lane][pos + i] += tail[lane][i] (i < n): a segment's overlap tail lands on the head of the next segment's

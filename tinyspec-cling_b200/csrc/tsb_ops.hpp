@@ -25,7 +25,8 @@ cudaError_t op_overlap_add(const double *frame, long long osize, long long hop, 
                            long long tail_len, long long new_tail_len, long long lanes, cudaStream_t st);
 cudaError_t op_timepar_scan(const double *inc, long long inc_frames, const long long *seg_tab, int n_seg, const double *base,
                             double *sum_rows, double *carry_out, long long lanes, long long m, long long lane0,
-                            long long n_lanes, cudaStream_t st, long long carry_at = -1);
+                            long long n_lanes, cudaStream_t st, long long carry_at = -1, const int *flag_in = nullptr,
+                            int *flag_out = nullptr, int epoch = 0);
 cudaError_t op_add_tails(void *out, int is_f64, long long out_stride, long long out_len, const long long *pos_tab,
                          int n_tails, const double *tails, long long lanes, long long n, cudaStream_t st);
 cudaError_t op_fma_peak(int is_f64, void *sink, int sms, cudaStream_t st, double *tflops);

@@ -78,6 +78,10 @@ def render_time_sharded(backend, x_block, block, dist, device_tensor=None):
     rank, world = dist.get_rank(), dist.get_world_size()
     to_t = device_tensor or (lambda a: a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a)))
     backend.prepass(x_block, block)
+    if getattr(backend, "linked", False):
+        # peer memory: every rank launches ONE scan kernel; the carries flow from GPU to GPU, CTA to CTA
+        backend.scan_chain(block["carry_frame"])
+        return backend.render()
     # the running phase_sum travels down the ranks: receive, add this block's increments in frame order, pass on
     # ... lane by lane (lanes are independent): while this rank adds lane c, the next one already works on lane c-1
     zero = backend.zero_carry()
@@ -101,6 +105,33 @@ class GpuBackend:
 
     def __init__(self, plan, n_segments):
         self.plan, self.n_segments = plan, n_segments
+        self.linked = False
+
+    def link(self, dist, lanes):
+        """Map the next rank's carry buffers into this process (cudaIpc over NVLink) so that the phase carry travels
+        from scan kernel to scan kernel without the host or NCCL (tsb_timepar_scan_chain).  Two buffer sets, used
+        alternately, each [lanes][n/2] float64 + one int32 flag per 16 bins of a lane."""
+        ctx, m = self.plan.ctx, self.plan.n // 2
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self._carry_bytes = ((lanes * m * 8 + 255) // 256) * 256
+        self._flag_bytes = ((lanes * ((m + 15) // 16) * 4 + 255) // 256) * 256
+        self._set_bytes = self._carry_bytes + self._flag_bytes
+        self._buf = ctx.malloc(2 * self._set_bytes)
+        ctx.memset(self._buf, 0, 2 * self._set_bytes)
+        ctx.sync()
+        handles = [None] * self.world
+        dist.all_gather_object(handles, ctx.ipc_export(self._buf))
+        self._next = ctx.ipc_open(handles[self.rank + 1]) if self.rank + 1 < self.world else None
+        self._epoch = 0
+        dist.barrier()
+        self.linked = True
+
+    def scan_chain(self, carry_frame):
+        self._epoch += 1
+        off = (self._epoch & 1) * self._set_bytes
+        mine = (self._buf + off, self._buf + off + self._carry_bytes) if self.rank > 0 else (None, None)
+        peer = (self._next + off, self._next + off + self._carry_bytes) if self._next is not None else (None, None)
+        self.tp.scan_chain(mine[0], mine[1], peer[0], peer[1], self._epoch, carry_frame)
 
     def prepass(self, x, block):
         import torch

@@ -54,7 +54,7 @@ def _timed(fn, dist, dev, warmup, reps):
     return out, sum(ms) / len(ms)
 
 
-def run(dist, rank, world, dev, ctx, seconds=600.0, precision="f64", segments=74, warmup=2, reps=3, check=True):
+def run(dist, rank, world, dev, ctx, seconds=600.0, precision="f64", segments=74, warmup=2, reps=3, check=True, peer=True):
     """cfg3 (8 channels, frame 4096, hop 1024, x1.5) for `seconds` of audio as ONE render split by time over the
     `world` ranks, and the same render on rank 0 alone (time-parallel over world * segments segments): times, the
     strong-scaling efficiency and whether the stitched output is the one-GPU render bit for bit.  dist: the
@@ -72,7 +72,11 @@ def run(dist, rank, world, dev, ctx, seconds=600.0, precision="f64", segments=74
         b = shard.plan_time_blocks(sch, N, world)[rank]
         x = synth(b["in_lo"], b["in_hi"], dev)
         be = shard.GpuBackend(plan, segments)
+        if peer:
+            be.link(dist, CH)
         out, ms = _timed(lambda: shard.render_time_sharded(be, x, b, dist), dist, dev, warmup, reps)
+        res["carry_transport"] = ("scan kernels chained over NVLink peer memory (tsb_timepar_scan_chain)" if peer else
+                                  "NCCL send/recv per lane")
         res["halo_samples"] = int(b["in_off0"]) if rank else None
     # the same render on one GPU (rank 0; the others wait)
     whole, ms1 = None, 0.0
@@ -121,6 +125,7 @@ def main():
     ap.add_argument("--precision", default="f64")
     ap.add_argument("--segments", type=int, default=74, help="time segments per rank (x 8 lanes = CTAs)")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--nccl-carry", action="store_true", help="hand the phase carry on with NCCL send/recv instead of peer memory")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -130,7 +135,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         d = dist
     ctx = tsb200.Context(local)
-    res = run(d, rank, world, dev, ctx, args.seconds, args.precision, args.segments, check=not args.no_check)
+    res = run(d, rank, world, dev, ctx, args.seconds, args.precision, args.segments, check=not args.no_check,
+              peer=not args.nccl_carry)
     if rank == 0:
         print(json.dumps(res))
     if d is not None:
