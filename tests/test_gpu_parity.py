@@ -309,7 +309,7 @@ def test_timepar_two_blocks_like_two_gpus(env):
     # block 0: frames [0, F0)
     st0 = dict(last_phase=zeros(n // 2), phase_sum=zeros(n // 2), ola=zeros(n))
     tp0 = plan.timepar(xd, F0, hop, 24, out=out, state=st0)
-    tot0, _ = tp0.prepass()
+    tot0, _ = tp0.prepass(want_totals=True)
     # block 1: frames [F0, F): needs input from I_F0 - hop on (the halo)
     st1 = dict(last_phase=zeros(n // 2), phase_sum=zeros(n // 2), ola=zeros(n))
     tp1 = plan.timepar(xd, F - F0, hop, 24, out=out, in_off0=int(sch["in_off"][F0]), out_off0=int(sch["out_off"][F0]),

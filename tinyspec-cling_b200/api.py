@@ -569,9 +569,13 @@ class TimePar:
     def segments(self):
         return _load().tsb_timepar_segments(self.h)
 
-    def prepass(self):
-        """-> (block_total, block_last_phase), CUDA float64 [lanes, n/2]"""
+    def prepass(self, want_totals=False):
+        """Analyse the block and store every frame's increments.  want_totals: also return (block_total,
+        block_last_phase), CUDA float64 [lanes, n/2] — an extra pass over the stored increments."""
         import torch
+        if not want_totals:
+            _check(_load().tsb_timepar_prepass(self.h, None, None))
+            return None
         lanes, m = self.out.shape[0], self.plan.n // 2
         tot = torch.zeros((lanes, m), dtype=torch.float64, device=self.out.device)
         last = torch.zeros((lanes, m), dtype=torch.float64, device=self.out.device)

@@ -137,6 +137,9 @@ class GpuBackend:
         import torch
         lanes, n = x.shape[0], self.plan.n
         self.block = block
+        if getattr(self, "tp", None) is not None:
+            self.tp.close()  # give the context's scratch block back BEFORE the next one is asked for (else the new
+            self.tp = None   # block is a private multi-GB cudaMalloc every other render)
         self.state = dict(last_phase=torch.zeros((lanes, n // 2), dtype=torch.float64, device=x.device),
                           phase_sum=torch.zeros((lanes, n // 2), dtype=torch.float64, device=x.device),
                           ola=torch.zeros((lanes, n), dtype=torch.float64, device=x.device))

@@ -64,7 +64,7 @@ def run(dist, rank, world, dev, ctx, seconds=600.0, precision="f64", segments=74
     sch = tsb200.schedule_const(L, N, HOP, RATE)
     F = int(sch["n_frames"])
     res = {"workload": "cfg3", "what": "ONE 8-channel render split by time segment across the GPUs (halo = lead-in + warm-up "
-           "frames, exact phase carry handed down the ranks over NCCL P2P)", "frame": N, "hop": HOP, "channels": CH,
+           "frames; the exact running phase_sum is handed down the ranks)", "frame": N, "hop": HOP, "channels": CH,
            "ratio": RATIO, "seconds": seconds, "frames": F, "n_gpus": world, "precision": precision,
            "segments_per_gpu": segments}
     out = None
@@ -78,6 +78,19 @@ def run(dist, rank, world, dev, ctx, seconds=600.0, precision="f64", segments=74
         res["carry_transport"] = ("scan kernels chained over NVLink peer memory (tsb_timepar_scan_chain)" if peer else
                                   "NCCL send/recv per lane")
         res["halo_samples"] = int(b["in_off0"]) if rank else None
+    if world > 1 and os.environ.get("TSB_SHARD_TRACE"):
+        # where the time goes: the three steps one by one, each synchronised (device time, per rank)
+        import time as _t
+        def step(fn):
+            torch.cuda.synchronize(); dist.barrier(); t0 = _t.perf_counter(); fn(); torch.cuda.synchronize()
+            return (_t.perf_counter() - t0) * 1e3
+        for _ in range(2):
+            tp = step(lambda: be.prepass(x, b))
+            tc = step(lambda: be.scan_chain(b["carry_frame"])) if be.linked else -1.0
+            tr = step(lambda: be.render())
+        allv = [None] * world
+        dist.all_gather_object(allv, (rank, round(tp, 3), round(tc, 3), round(tr, 3)))
+        res["trace_prepass_chain_render_ms"] = allv
     # the same render on one GPU (rank 0; the others wait)
     whole, ms1 = None, 0.0
     if rank == 0:
