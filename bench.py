@@ -471,6 +471,39 @@ def main():
                         "frame_channels_per_s": fc5, "out_samples_per_s": fc5 * hop5, "gpu_launches_per_render": (ctx.launches - l0) // (2 + reps5),
                         "roofline": {"bound": "hbm", "alg_bytes_per_frame_channel": balg5, "achieved": fc5 / world * balg5 / 1e9,
                                      "peak": peak, "unit": "GB/s", "frac": fc5 / world * balg5 / 1e9 / peak}}
+        if world == 1:
+            # the reference's own voidbubbles.cpp formula (libm sin / pow, integer bytebeat) as a spectrum expression
+            # evaluated in the kernel (TSB_GEN_EXPR), same shape
+            import tsb200
+            prog = tsb200.expr.voidbubbles()["program"]
+            for _ in range(2):
+                ctx.spectral_render(n5, ch5, f5, hop5, out=out5, expr=prog)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps5):
+                ctx.spectral_render(n5, ch5, f5, hop5, out=out5, expr=prog)
+            e1.record()
+            torch.cuda.synchronize()
+            msx = e0.elapsed_time(e1) / reps5
+            line["cfg5"]["voidbubbles_expr"] = {"what": "hacks/spectral_bytebeat/voidbubbles.cpp:9-13 as a TSB_GEN_EXPR program "
+                                                        "(36 words, interpreted per bin in kernel A), same shape",
+                                                "ms_per_render": msx, "frame_channels_per_s": ch5 * f5 / (msx * 1e-3)}
+            bb = os.path.join(ROOT, "oracle", "_ref", "ref_bytebeat_tap_mkl")
+            if os.path.exists(bb):
+                try:
+                    import tempfile
+                    d = tempfile.mkdtemp(prefix="tsref")
+                    env = dict(os.environ, TSREF_N=str(n5), TSREF_CH="2", TSREF_MAX_FRAMES="12", TSREF_DUMP_FIRST="0",
+                               TSREF_TIMING="1", **ONE_THREAD)
+                    o = subprocess.run([bb], env=env, cwd=d, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+                                       timeout=120, preexec_fn=lambda: os.sched_setaffinity(0, {host_cpus()[0]})).stdout
+                    j = [json.loads(ln) for ln in o.splitlines() if ln.startswith("{")][-1]
+                    line["cfg5"]["cpu_reference"] = {"frame_channels_per_s": 2 * j["frames"] / j["wall_s"], "cores": 1,
+                                                     "sample": f"unmodified reference (oracle/_ref/ref_bytebeat_tap_mkl: the same "
+                                                               f"seeded formula in the hack's host loop, MKL DFTI for FFTW), frame {n5}, "
+                                                               f"2 channels, {j['frames']} frames, first->last callback wall"}
+                except Exception as ex:  # the baseline is informative; the GPU figures stand without it
+                    line["cfg5"]["cpu_reference"] = {"unavailable": str(ex)[:200]}
         del out5
     # ---- CPU baseline: rank 0, N=1 only, bounded sample ----
     if rank == 0 and world == 1:

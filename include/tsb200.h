@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TSB_ABI_VERSION 2
+#define TSB_ABI_VERSION 3
 
 enum { TSB_OK = 0, TSB_EINVAL = -1, TSB_ECUDA = -2, TSB_EUNSUPPORTED = -3, TSB_ENOMEM = -4 };
 /* arithmetic of the chain (phase accumulators are fp64 in all three).  TSB_F64_OUT32 computes like TSB_F64 and
@@ -140,11 +140,62 @@ int tsb_chain_render(tsb_ctx *ctx, tsb_plan *plan, const tsb_chain_args *args);
  *                   h = frame*2654435761 ^ (c*40503 + i*2246822519); h ^= h>>15; h *= 2246822519; h ^= h>>13;
  *                   X[i] = (((h & 0xffff) - 32768) + i*((h >> 16) - 32768)) / 32768.0 / (1 + (i >> 4)),  0 < i < frame
  *   TSB_GEN_BUFFER  values the caller computed: device complex128 [n_frames][channels][frame], bins 1..frame-1 read
- * and X[2*frame - i] = conj(X[i]).  Bins 0 and `frame`, which such a hack never writes, hold what its static buffer
+ *   TSB_GEN_EXPR    a spectrum EXPRESSION evaluated per (frame, channel, bin) in the kernel (the
+ *                   per-bin host loop of a spectral_bytebeat hack — e.g. voidbubbles.cpp:9-13,
+ *                   `r = (int)(t*32)*n+i; buf[c][i] = sin(2.0*M_PI/64.*(c+((int)pow(i,1.1))&r/3|r/250|r/136|r>>16))
+ *                   /pow(i+1, 0.7)*32` — as a postfix program).  The program works on a stack of 64-bit slots (int64
+ *                   or double, statically typed: tsb_spectral_render checks the program before launching) and must
+ *                   leave exactly two doubles: re and im of X[i].  What depends on the bin only (pow(i+1, 0.7),
+ *                   (int)pow(i,1.1)) or on the frame only ((int)(t*32)*n) is evaluated by the CALLER on the host with
+ *                   the reference's own libm and handed over as per-bin tables / per-frame parameters, so that only the
+ *                   integer arithmetic (exact) and sin / cos / exp / fmod / pow of the coupled part run on the device.
+ *                   Integers are int64 (C's 32-bit `int` wrap-around: TSB_X_I_WRAP32); x/0 and x%0 give 0.
+ * In all three X[2*frame - i] = conj(X[i]).  Bins 0 and `frame`, which such a hack never writes, hold what its static buffer
  * holds there: the previous frame's output samples y[0] and y[frame] (frft runs in place) — zero before the first
  * frame; state_edge [channels][2] carries them between calls.  Frame f is ADDED to out[c][out_off0 + f*hop ...]
  * (the caller zeroes `out`; after the call positions below out_off0 + n_frames*hop are final, the rest is the tail). */
-enum { TSB_GEN_HASH = 0, TSB_GEN_BUFFER = 1 };
+enum { TSB_GEN_HASH = 0, TSB_GEN_BUFFER = 1, TSB_GEN_EXPR = 2 };
+/* one program word = opcode | (argument << 8) */
+enum {
+    TSB_X_I_BIN = 1,   /* push i (the bin, 0 < i < frame) */
+    TSB_X_I_CH,        /* push c (the channel) */
+    TSB_X_I_FRAME,     /* push first_frame + f (the frame counter) */
+    TSB_X_I_N,         /* push `frame` (the hack's n = out.size) */
+    TSB_X_I_CONST,     /* push iconst[arg] */
+    TSB_X_I_TAB,       /* push itab[arg][i] */
+    TSB_X_I_PARAM,     /* push iparam[f][arg] */
+    TSB_X_D_CONST,     /* push dconst[arg] */
+    TSB_X_D_TAB,       /* push dtab[arg][i] */
+    TSB_X_D_PARAM,     /* push dparam[f][arg] */
+    TSB_X_I_ADD, TSB_X_I_SUB, TSB_X_I_MUL, TSB_X_I_DIV, TSB_X_I_MOD, /* (a b -- a op b), C truncating / and % */
+    TSB_X_I_AND, TSB_X_I_OR, TSB_X_I_XOR, TSB_X_I_SHL, TSB_X_I_SHR,  /* >> is arithmetic */
+    TSB_X_I_EQ, TSB_X_I_LT,                                          /* (a b -- 0 | 1) */
+    TSB_X_I_NEG, TSB_X_I_NOT, TSB_X_I_WRAP32,                        /* (a -- op a); WRAP32 = (int32_t)a */
+    TSB_X_I2D,         /* (int -- double) */
+    TSB_X_D2I,         /* (double -- int), C truncation */
+    TSB_X_D_ADD, TSB_X_D_SUB, TSB_X_D_MUL, TSB_X_D_DIV, TSB_X_D_FMOD, TSB_X_D_POW,   /* (a b -- a op b) */
+    TSB_X_D_NEG, TSB_X_D_ABS, TSB_X_D_SIN, TSB_X_D_COS, TSB_X_D_EXP, TSB_X_D_SQRT, TSB_X_D_FLOOR,
+    TSB_X_PICK,        /* push a copy of the slot `arg` below the top (0 = dup) */
+    TSB_X_POLAR,       /* (mag phase -- mag*cos(phase) mag*sin(phase)): std::polar */
+    TSB_X__COUNT
+};
+#define TSB_EXPR_MAX_OPS 128
+#define TSB_EXPR_MAX_CONST 24
+#define TSB_EXPR_MAX_TABS 4
+#define TSB_EXPR_STACK 16
+typedef struct tsb_expr {        /* every pointer is a HOST pointer; copied during the call */
+    int32_t n_ops;               /* <= TSB_EXPR_MAX_OPS */
+    const int32_t *ops;
+    int32_t n_iconst, n_dconst;  /* <= TSB_EXPR_MAX_CONST each */
+    const int64_t *iconst;
+    const double *dconst;
+    int32_t n_itab, n_dtab;      /* <= TSB_EXPR_MAX_TABS each; per-bin tables [n_tab][frame] */
+    const int32_t *itab;
+    const double *dtab;
+    int32_t n_iparam, n_dparam;  /* <= TSB_EXPR_MAX_TABS each; per-frame scalars [n_frames][n_param] */
+    const int64_t *iparam;
+    const double *dparam;
+} tsb_expr;
 typedef struct tsb_spectral_args {
     uint32_t frame;          /* power of two, 256 .. 262144; the inverse FFT has 2*frame points */
     int32_t channels;
@@ -157,8 +208,12 @@ typedef struct tsb_spectral_args {
     int64_t out_stride, out_len, out_off0;
     double *state_edge;      /* device float64 [channels][2] or NULL, in (load_state) / out */
     int32_t load_state;
+    const tsb_expr *expr;    /* TSB_GEN_EXPR (ABI 3) */
 } tsb_spectral_args;
 int tsb_spectral_render(tsb_ctx *ctx, const tsb_spectral_args *args);
+/* Host-side (no device needed): the static check tsb_spectral_render applies to an expression — known opcodes, indices
+ * in range, stack depth <= TSB_EXPR_STACK, operand types, exactly (re, im) left.  TSB_OK or TSB_EINVAL + tsb_last_error(). */
+int tsb_expr_check(const tsb_expr *expr);
 
 /* ---- batched granular pitch shift with a frame size, hop and output length that change every frame (BASELINE cfg4;
  * the reference's hacks/pitchshift-simple.cpp:1-11 on the scheduler's gather and float32 overlap-add,

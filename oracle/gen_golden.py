@@ -106,6 +106,29 @@ def bytebeat_case(name, n, ch, frames, every=1):
     print(name, "frames dumped", k, "stream", stream.shape)
 
 
+def hack_case(hack, n, frames, every=1):
+    """An UNMODIFIED spectral_bytebeat hack of the reference (ref/taps/hack_tap.cpp includes the file where it lies):
+    its callback times and per-frame double `out` buffers (two channels, frame n, hop n/2 as the hack sets them)."""
+    r = run_ref("ref_hack_%s_mkl" % hack, dict(TSREF_MAX_FRAMES=frames, TSREF_DUMP_FIRST=frames),
+                [("t", np.float64), ("out", np.float64)])
+    k = len(r["t"])
+    out = r["out"].reshape(k, 2, n)
+    stream = r["stream"].reshape(-1, 2)
+    np.savez_compressed(os.path.join(GOLD, "hack_%s.npz" % hack), meta=np.array([n, 2, frames], np.int64), t=r["t"],
+                        out=out[:, :, ::every], stream=stream[::every], every=np.array([every], np.int64),
+                        stream_len=np.array([stream.shape[0]], np.int64),
+                        frame_sum=out.sum(axis=2), frame_sumsq=(out ** 2).sum(axis=2))
+    print("hack", hack, "frames dumped", k, "stream", stream.shape, "t", r["t"][:4])
+
+
+def hack_cases():
+    hack_case("voidbubbles", 1 << 12, 24)
+    hack_case("acidbattery", 1 << 11, 24)
+    hack_case("brokenconvo", 1 << 15, 8, every=8)
+    hack_case("ghostacid", 1 << 14, 8, every=4)
+    hack_case("andshuffle", 1 << 17, 4, every=32)
+
+
 def control_case(name, samples):
     r = run_ref("ref_control_tap", dict(TSREF_SAMPLES=samples, TSREF_STREAM=1), [("rec", np.float64)])
     rec = r["rec"].reshape(-1, 4)
@@ -128,6 +151,9 @@ def pvmore_case():
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL)
+    if sys.argv[1:] == ["hacks"]:  # only the fixtures of the unmodified spectral_bytebeat hacks
+        hack_cases()
+        sys.exit(0)
     helpers_case()
     # cfg1 shape, short: every frame's state would be 1.3 MB; keep the first 6 + every 16th
     pv_case("pv_cfg1_short", 1024, 0.25, 2.0, 2, 24000, 6, 16)
@@ -146,3 +172,4 @@ if __name__ == "__main__":
     bytebeat_case("bytebeat_n65536", 65536, 2, 6, every=32)
     control_case("control_times", 12000)
     pvmore_case()
+    hack_cases()

@@ -317,3 +317,79 @@ def render_bytebeat(n, ch, frames, hop=None, spectrum=None):
         outs[f] = buf[:, :n].real * tri
         ola[:, f * hop:f * hop + n] += outs[f]
     return dict(out=outs, ola64=ola)
+
+
+# ---- the reference's stateless spectral_bytebeat hacks, restated from their sources (numpy int64 arithmetic with C's
+# truncating division; pow / sin / fmod through numpy or, where a truncation follows, Python's math = the C library) ----
+def _cdiv(a, b):
+    """C's truncating integer division on int64 arrays"""
+    a, b = np.asarray(a, np.int64), np.asarray(b, np.int64)
+    q = np.abs(a) // np.abs(b)
+    return np.where((a < 0) == (b < 0), q, -q)
+
+
+def _cmod(a, b):
+    """C's % (sign of the dividend)"""
+    return np.asarray(a, np.int64) - _cdiv(a, b) * np.asarray(b, np.int64)
+
+
+def _wrap32(v):
+    v = int(v) & 0xFFFFFFFF
+    return v - (1 << 32) if v & 0x80000000 else v
+
+
+def hack_spectrum(hack, t, ch, n):
+    """Bins 1..n-1 that hacks/spectral_bytebeat/<hack>.cpp writes for callback time t: complex128 [ch, n], bin 0 = 0.
+    voidbubbles.cpp:9-13, acidbattery.cpp:9-17, andshuffle.cpp:9-14, brokenconvo.cpp:9-11, ghostacid.cpp:9-12."""
+    import math
+    i = np.arange(n, dtype=np.int64)[None, :]
+    c = np.arange(ch, dtype=np.int64)[:, None]
+    fi = np.arange(n, dtype=np.float64)[None, :]
+    powtab = lambda e, off=0: np.array([math.pow(k + off, e) if k + off > 0 else 1.0 for k in range(n)])[None, :]
+    with np.errstate(all="ignore"):
+        if hack == "voidbubbles":
+            r = _wrap32(int(t * 32) * n) + i
+            ipow = np.array([int(math.pow(k, 1.1)) for k in range(n)], np.int64)[None, :]
+            k = ((c + ipow) & _cdiv(r, 3)) | _cdiv(r, 250) | _cdiv(r, 136) | (r >> 16)
+            re = np.sin(2.0 * math.pi / 64. * k.astype(np.float64)) / powtab(0.7, 1) * 32
+            x = re + 0j
+        elif hack == "acidbattery":
+            r = _wrap32(int(t * 32) * n) + i + 0 * c
+            k = _cmod((r >> 14) ^ (r >> 17), 64) + 2
+            mag = np.sin(powtab(0.1) * k * 16 + _cmod(r & (r >> 13), k).astype(np.float64)
+                         / (1 + _cmod(_cdiv(r, 3) & _cdiv(r, 1023), k).astype(np.float64))) / powtab(1.0, 1) * 32.0
+            x = mag + 1j * mag
+        elif hack == "andshuffle":
+            r = int(_cdiv(_wrap32(int(t * 8) * n), 2)) + n - i
+            j = _cdiv(r, 128) + c
+            m = _cmod(((_cdiv(j, 5) & _cdiv(j, 7) & (_cdiv(j, 64) ^ _cdiv(j, 127))) ^ (j >> 16)), 128)
+            ii = ((i * i + (1 << 31)) % (1 << 32)) - (1 << 31)   # i*i in C's 32-bit int
+            mag = np.sin(1 + np.fmod(ii.astype(np.float64), 1 + m.astype(np.float64))) / powtab(0.75) * 32
+            x = mag + 1j * mag
+        elif hack == "brokenconvo":
+            r = int(_cdiv(_wrap32(int(t * math.pi) * n), 2)) + i
+            m = _cdiv(r, 77) & _cdiv(r, 38) & (_cdiv(r, 24) + c)
+            re = np.sin(2.0 * math.pi * (fi / (1 + np.fmod(1 + m.astype(np.float64), fi + 1)))) / powtab(0.75, 1) * 64
+            x = re + 0j
+        elif hack == "ghostacid":
+            r = _wrap32(int(t * 4) * n) + i
+            den = 1 + (_cdiv(r, 97) ^ (r & _cdiv(r, 2))).astype(np.float64)
+            mag = np.sin(math.pi * np.fmod((_cdiv(i, 24) + c).astype(np.float64), 1 + r / den / 7)) / powtab(1.0, 1) * 128.0
+            x = mag + 1j * mag
+        else:
+            raise ValueError(hack)
+    x = np.array(np.broadcast_to(x, (ch, n)), np.complex128)
+    x[:, 0] = 0
+    return x
+
+
+HACK_FRAMES = {"voidbubbles": 1 << 12, "acidbattery": 1 << 11, "andshuffle": 1 << 17, "brokenconvo": 1 << 15,
+               "ghostacid": 1 << 14}
+
+
+def render_hack(hack, frames, ch=2, rate=48000.0):
+    """render_bytebeat with the spectrum of an unmodified reference hack, at the frame size and hop (n/2) it sets;
+    callback time of frame f = f*hop/rate (tinyspec.cpp:110-112,163-168 with an integral hop)."""
+    n = HACK_FRAMES[hack]
+    hop = n // 2
+    return render_bytebeat(n, ch, frames, hop=hop, spectrum=lambda f: hack_spectrum(hack, f * hop / rate, ch, n))

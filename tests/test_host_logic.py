@@ -22,7 +22,7 @@ def test_abi_exports_match_header():
     lib = ctypes.CDLL(tsb200.lib_path())
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/tsb200.h but not exported"
-    assert tsb200.abi_version() == 2
+    assert tsb200.abi_version() == 3
 
 
 def test_no_cpu_fallback():

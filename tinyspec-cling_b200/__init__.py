@@ -7,8 +7,9 @@ GPU (the host-side schedule logic is usable), every device call fails loudly.
 
 The directory name carries a hyphen, so import it through the repo-root shim: `import tsb200`.
 """
-from .api import (Context, Plan, Stream, TimePar, TsbError, abi_version, bind_host_to_gpu, granular_schedule, hop_fixed, lib_path, schedule_const, shift_map,
+from . import expr
+from .api import (Context, Plan, Stream, TimePar, TsbError, abi_version, bind_host_to_gpu, expr_check, granular_schedule, hop_fixed, lib_path, schedule_const, shift_map,
                   F32, F64, PROG_PV_SHIFT, PROG_GAIN, WIN_NONE, WIN_HANN, WIN_SQRT_HANN)
 
-__all__ = ["Context", "Plan", "Stream", "TimePar", "TsbError", "abi_version", "bind_host_to_gpu", "granular_schedule", "hop_fixed", "lib_path", "schedule_const", "shift_map",
+__all__ = ["Context", "Plan", "Stream", "TimePar", "TsbError", "abi_version", "bind_host_to_gpu", "expr", "expr_check", "granular_schedule", "hop_fixed", "lib_path", "schedule_const", "shift_map",
            "F32", "F64", "PROG_PV_SHIFT", "PROG_GAIN", "WIN_NONE", "WIN_HANN", "WIN_SQRT_HANN"]

@@ -34,7 +34,17 @@ class _SpectralArgs(C.Structure):
     _fields_ = [("frame", C.c_uint32), ("channels", C.c_int32), ("n_frames", C.c_int64), ("first_frame", C.c_int64),
                 ("hop", C.c_int32), ("generator", C.c_int32), ("spectrum", C.c_void_p), ("out", C.c_void_p),
                 ("out_stride", C.c_int64), ("out_len", C.c_int64), ("out_off0", C.c_int64), ("state_edge", C.c_void_p),
-                ("load_state", C.c_int32)]
+                ("load_state", C.c_int32), ("expr", C.c_void_p)]
+
+
+TSB_EXPR_MAX_CONST = 24
+
+
+class _Expr(C.Structure):  # tsb_expr (include/tsb200.h)
+    _fields_ = [("n_ops", C.c_int32), ("ops", C.c_void_p), ("n_iconst", C.c_int32), ("n_dconst", C.c_int32),
+                ("iconst", C.c_void_p), ("dconst", C.c_void_p), ("n_itab", C.c_int32), ("n_dtab", C.c_int32),
+                ("itab", C.c_void_p), ("dtab", C.c_void_p), ("n_iparam", C.c_int32), ("n_dparam", C.c_int32),
+                ("iparam", C.c_void_p), ("dparam", C.c_void_p)]
 
 
 class _GranularArgs(C.Structure):
@@ -83,6 +93,7 @@ def _load():
     L.tsb_chain_render_host.argtypes = [P, P, C.POINTER(_ChainArgs)]
     L.tsb_spectral_render.argtypes = [P, C.POINTER(_SpectralArgs)]
     L.tsb_granular_render.argtypes = [P, C.POINTER(_GranularArgs)]
+    L.tsb_expr_check.argtypes = [C.POINTER(_Expr)]
     I64, D = C.c_int64, C.c_double
     L.tsb_window.argtypes = [P, P, I64, I64, C.c_int32]
     L.tsb_fft_forward.argtypes = [P, P, P, I64, I64]
@@ -121,6 +132,17 @@ def _load():
 def _check(rc):
     if rc != 0:
         raise TsbError(f"libtsb200 error {rc}: {_load().tsb_last_error().decode()}")
+
+
+def expr_check(ops, n_iconst=0, n_dconst=0, n_itab=0, n_dtab=0, n_iparam=0, n_dparam=0):
+    """tsb_expr_check on a raw program (host-side): raises TsbError with the reason when it is malformed"""
+    ops = np.ascontiguousarray(ops, np.int32)
+    dummy = np.zeros(max(1, TSB_EXPR_MAX_CONST), np.int64)
+    x = _Expr()
+    x.n_ops, x.ops = len(ops), ops.ctypes.data
+    x.n_iconst, x.n_dconst, x.n_itab, x.n_dtab, x.n_iparam, x.n_dparam = n_iconst, n_dconst, n_itab, n_dtab, n_iparam, n_dparam
+    x.iconst = x.dconst = x.itab = x.dtab = x.iparam = x.dparam = dummy.ctypes.data
+    _check(_load().tsb_expr_check(C.byref(x)))
 
 
 def abi_version():
@@ -248,10 +270,13 @@ class Context:
         return _load().tsb_launch_count(self.h)
 
     def spectral_render(self, frame, channels, n_frames, hop, out=None, spectrum=None, first_frame=0, out_off0=0,
-                        state_edge=None, load_state=False):
+                        state_edge=None, load_state=False, expr=None, times=None):
         """tsb_spectral_render: the spectral-bytebeat pattern (BASELINE cfg5) fused on the device.  spectrum=None: the
-        seeded integer generator; else CUDA complex128 [n_frames, channels, frame].  Frames are ADDED into `out`
-        (CUDA float64 [channels, >= out_off0 + (n_frames-1)*hop + frame], zeros by default); returns it."""
+        seeded integer generator; else CUDA complex128 [n_frames, channels, frame]; expr = an expr.Program (a hack's
+        per-bin formula, TSB_GEN_EXPR) evaluated in the kernel, with `times` = the callback time of every frame
+        (default: (first_frame + f)*hop/48000, the reference's clock for an integral hop, tinyspec.cpp:110-112).
+        Frames are ADDED into `out` (CUDA float64 [channels, >= out_off0 + (n_frames-1)*hop + frame], zeros by default);
+        returns it."""
         import torch
         if out is None:
             out = torch.zeros((channels, out_off0 + max(n_frames - 1, 0) * hop + frame), dtype=torch.float64,
@@ -259,7 +284,24 @@ class Context:
         assert out.is_cuda and out.dtype == torch.float64 and out.is_contiguous() and out.shape[0] == channels
         a = _SpectralArgs()
         a.frame, a.channels, a.n_frames, a.first_frame, a.hop = frame, channels, n_frames, first_frame, int(hop)
-        a.generator = 0 if spectrum is None else 1
+        a.generator = 2 if expr is not None else (0 if spectrum is None else 1)
+        keep = None
+        if expr is not None:
+            assert spectrum is None, "give a spectrum buffer or an expression, not both"
+            if times is None:
+                times = [(first_frame + f) * int(hop) / 48000.0 for f in range(n_frames)]
+            assert len(times) == n_frames
+            itab, dtab = expr.tables(frame)
+            ipar, dpar = expr.params(times, frame)
+            ops, ic, dc = (np.ascontiguousarray(expr.ops, np.int32), np.ascontiguousarray(expr.iconst, np.int64),
+                           np.ascontiguousarray(expr.dconst, np.float64))
+            x = _Expr()
+            x.n_ops, x.ops = len(ops), ops.ctypes.data
+            x.n_iconst, x.n_dconst, x.iconst, x.dconst = len(ic), len(dc), ic.ctypes.data, dc.ctypes.data
+            x.n_itab, x.n_dtab, x.itab, x.dtab = itab.shape[0], dtab.shape[0], itab.ctypes.data, dtab.ctypes.data
+            x.n_iparam, x.n_dparam, x.iparam, x.dparam = ipar.shape[1], dpar.shape[1], ipar.ctypes.data, dpar.ctypes.data
+            keep = (x, ops, ic, dc, itab, dtab, ipar, dpar)
+            a.expr = C.addressof(x)
         if spectrum is not None:
             assert spectrum.is_cuda and spectrum.dtype == torch.complex128 and spectrum.is_contiguous()
             assert tuple(spectrum.shape) == (n_frames, channels, frame)
@@ -270,6 +312,7 @@ class Context:
             a.state_edge = state_edge.data_ptr()
         a.load_state = int(load_state)
         _check(_load().tsb_spectral_render(self.h, C.byref(a)))
+        del keep  # (the expression's host arrays are copied during the call)
         self._keep_spec = (out, spectrum, state_edge)
         return out
 

@@ -672,7 +672,10 @@ TSB_API int tsb_spectral_render(tsb_ctx *c, const tsb_spectral_args *a) {
     const uint32_t n = a->frame;
     if (n < 256 || n > (1u << 18) || (n & (n - 1))) return fail(TSB_EUNSUPPORTED, "frame size %u: fused spectral synthesis supports powers of two in 256..262144", n);
     if (a->channels < 0 || a->n_frames < 0 || a->hop < 0) return fail(TSB_EINVAL, "negative channels / n_frames / hop");
-    if (a->generator != TSB_GEN_HASH && a->generator != TSB_GEN_BUFFER) return fail(TSB_EINVAL, "bad generator %d", a->generator);
+    if (a->generator != TSB_GEN_HASH && a->generator != TSB_GEN_BUFFER && a->generator != TSB_GEN_EXPR) return fail(TSB_EINVAL, "bad generator %d", a->generator);
+    if (a->generator == TSB_GEN_EXPR) {
+        if (const char *why = expr_check(a->expr)) return fail(TSB_EINVAL, "%s", why);
+    }
     if (a->generator == TSB_GEN_BUFFER && !a->spectrum && a->n_frames * a->channels) return fail(TSB_EINVAL, "TSB_GEN_BUFFER needs a spectrum");
     if (a->channels == 0 || a->n_frames == 0) return TSB_OK;
     if (!a->out || a->out_off0 < 0 || a->out_len < 0 || (a->channels > 1 && a->out_stride < a->out_len)) return fail(TSB_EINVAL, "bad output rows");
@@ -683,7 +686,8 @@ TSB_API int tsb_spectral_render(tsb_ctx *c, const tsb_spectral_args *a) {
     jb.n_frames = a->n_frames;
     jb.first_frame = a->first_frame;
     jb.hop = a->hop;
-    jb.generator = a->generator == TSB_GEN_HASH ? (int)SPEC_GEN_HASH : (int)SPEC_GEN_BUFFER;
+    jb.generator = a->generator == TSB_GEN_HASH ? (int)SPEC_GEN_HASH : a->generator == TSB_GEN_EXPR ? (int)SPEC_GEN_EXPR : (int)SPEC_GEN_BUFFER;
+    jb.expr = a->generator == TSB_GEN_EXPR ? a->expr : nullptr;
     jb.spectrum = a->spectrum;
     jb.out = a->out;
     jb.out_stride = a->out_stride;
@@ -695,6 +699,11 @@ TSB_API int tsb_spectral_render(tsb_ctx *c, const tsb_spectral_args *a) {
     cudaError_t e = op_spectral_render(c->device, jb, c->stream, &l);
     c->launches += l;
     if (e != cudaSuccess) return fail(TSB_ECUDA, "spectral synthesis: %s", cudaGetErrorString(e));
+    return TSB_OK;
+}
+
+TSB_API int tsb_expr_check(const tsb_expr *x) {
+    if (const char *why = expr_check(x)) return fail(TSB_EINVAL, "%s", why);
     return TSB_OK;
 }
 

@@ -24,6 +24,7 @@
 #include <map>
 #include <vector>
 
+#include "../../include/tsb200.h"
 #include "tsb_host.hpp"
 #include "tsb_math.cuh"
 #include "tsb_spectral.hpp"
@@ -63,6 +64,106 @@ struct GenBuffer {
     const cd *spec;
     long long n;
     __device__ __forceinline__ cd operator()(int c, int i) const { return spec[(long long)c * n + i]; }
+};
+
+// A spectrum expression (TSB_GEN_EXPR, include/tsb200.h): the per-bin formula of a spectral_bytebeat hack
+// (hacks/spectral_bytebeat/voidbubbles.cpp:9-13 and its siblings) as a postfix program on a stack of 64-bit slots.
+// The program travels as a kernel parameter (constant bank: every thread reads the same word, a uniform load); the
+// stack is a small local array.  The host has type-checked the program (expr_check): depth and types are static.
+struct ExprCode {
+    int n_ops;
+    int ops[TSB_EXPR_MAX_OPS];
+    long long ic[TSB_EXPR_MAX_CONST];
+    double dc[TSB_EXPR_MAX_CONST];
+};
+struct GenExpr {
+    ExprCode code;
+    const int *itab;         // device [n_itab][n]
+    const double *dtab;      // device [n_dtab][n]
+    const long long *ipar;   // device, this frame's integer parameters
+    const double *dpar;      // device, this frame's double parameters
+    int n;
+    long long frame;
+    __device__ __forceinline__ static long long as_i(double v) { return __double_as_longlong(v); }
+    __device__ __forceinline__ static double as_d(long long v) { return __longlong_as_double(v); }
+    __device__ __noinline__ cd operator()(int c, int i) const {
+        double st[TSB_EXPR_STACK];
+        int sp = 0;  // next free slot
+        for (int pc = 0; pc < code.n_ops; pc++) {
+            const int w = code.ops[pc], arg = w >> 8;
+            switch (w & 255) {
+#define TSB_PUSH_I(v) st[sp++] = as_d((long long)(v))
+#define TSB_PUSH_D(v) st[sp++] = (v)
+#define TSB_BIN_I(expr)                                          \
+    {                                                            \
+        const long long b = as_i(st[sp - 1]), a = as_i(st[sp - 2]); \
+        sp--;                                                    \
+        st[sp - 1] = as_d((long long)(expr));                    \
+    }
+#define TSB_BIN_D(expr)                              \
+    {                                                \
+        const double b = st[sp - 1], a = st[sp - 2]; \
+        sp--;                                        \
+        st[sp - 1] = (expr);                         \
+    }
+                case TSB_X_I_BIN: TSB_PUSH_I(i); break;
+                case TSB_X_I_CH: TSB_PUSH_I(c); break;
+                case TSB_X_I_FRAME: TSB_PUSH_I(frame); break;
+                case TSB_X_I_N: TSB_PUSH_I(n); break;
+                case TSB_X_I_CONST: TSB_PUSH_I(code.ic[arg]); break;
+                case TSB_X_I_TAB: TSB_PUSH_I(__ldg(&itab[(long long)arg * n + i])); break;
+                case TSB_X_I_PARAM: TSB_PUSH_I(__ldg(&ipar[arg])); break;
+                case TSB_X_D_CONST: TSB_PUSH_D(code.dc[arg]); break;
+                case TSB_X_D_TAB: TSB_PUSH_D(__ldg(&dtab[(long long)arg * n + i])); break;
+                case TSB_X_D_PARAM: TSB_PUSH_D(__ldg(&dpar[arg])); break;
+                // two's-complement wrap-around, as every compiler the reference is built with does for `int`
+                case TSB_X_I_ADD: TSB_BIN_I((unsigned long long)a + (unsigned long long)b) break;
+                case TSB_X_I_SUB: TSB_BIN_I((unsigned long long)a - (unsigned long long)b) break;
+                case TSB_X_I_MUL: TSB_BIN_I((unsigned long long)a * (unsigned long long)b) break;
+                case TSB_X_I_DIV: TSB_BIN_I(b == 0 ? 0 : (b == -1 ? (long long)(0ull - (unsigned long long)a) : a / b)) break;
+                case TSB_X_I_MOD: TSB_BIN_I((b == 0 || b == -1) ? 0 : a % b) break;
+                case TSB_X_I_AND: TSB_BIN_I(a & b) break;
+                case TSB_X_I_OR: TSB_BIN_I(a | b) break;
+                case TSB_X_I_XOR: TSB_BIN_I(a ^ b) break;
+                case TSB_X_I_SHL: TSB_BIN_I((unsigned long long)a << (b & 63)) break;
+                case TSB_X_I_SHR: TSB_BIN_I(a >> (b & 63)) break;
+                case TSB_X_I_EQ: TSB_BIN_I(a == b) break;
+                case TSB_X_I_LT: TSB_BIN_I(a < b) break;
+                case TSB_X_I_NEG: st[sp - 1] = as_d((long long)(0ull - (unsigned long long)as_i(st[sp - 1]))); break;
+                case TSB_X_I_NOT: st[sp - 1] = as_d(~as_i(st[sp - 1])); break;
+                case TSB_X_I_WRAP32: st[sp - 1] = as_d((long long)(int)(unsigned)(unsigned long long)as_i(st[sp - 1])); break;
+                case TSB_X_I2D: st[sp - 1] = (double)as_i(st[sp - 1]); break;
+                case TSB_X_D2I: st[sp - 1] = as_d((long long)st[sp - 1]); break;  // C truncation (saturating out of range)
+                case TSB_X_D_ADD: TSB_BIN_D(__dadd_rn(a, b)) break;
+                case TSB_X_D_SUB: TSB_BIN_D(__dsub_rn(a, b)) break;
+                case TSB_X_D_MUL: TSB_BIN_D(__dmul_rn(a, b)) break;
+                case TSB_X_D_DIV: TSB_BIN_D(__ddiv_rn(a, b)) break;
+                case TSB_X_D_FMOD: TSB_BIN_D(fmod(a, b)) break;
+                case TSB_X_D_POW: TSB_BIN_D(pow(a, b)) break;
+                case TSB_X_D_NEG: st[sp - 1] = -st[sp - 1]; break;
+                case TSB_X_D_ABS: st[sp - 1] = fabs(st[sp - 1]); break;
+                case TSB_X_D_SIN: st[sp - 1] = sin(st[sp - 1]); break;
+                case TSB_X_D_COS: st[sp - 1] = cos(st[sp - 1]); break;
+                case TSB_X_D_EXP: st[sp - 1] = exp(st[sp - 1]); break;
+                case TSB_X_D_SQRT: st[sp - 1] = __dsqrt_rn(st[sp - 1]); break;
+                case TSB_X_D_FLOOR: st[sp - 1] = floor(st[sp - 1]); break;
+                case TSB_X_PICK: st[sp] = st[sp - 1 - arg]; sp++; break;
+                case TSB_X_POLAR: {
+                    double sn, cs;
+                    sincos(st[sp - 1], &sn, &cs);
+                    const double mag = st[sp - 2];
+                    st[sp - 2] = __dmul_rn(mag, cs);
+                    st[sp - 1] = __dmul_rn(mag, sn);
+                } break;
+#undef TSB_PUSH_I
+#undef TSB_PUSH_D
+#undef TSB_BIN_I
+#undef TSB_BIN_D
+                default: break;
+            }
+        }
+        return mk<double>(st[0], st[1]);
+    }
 };
 
 // One CTA runs C sub-transforms of M = 2^LM points side by side, T threads each (one radix-8 butterfly per thread and
@@ -267,6 +368,80 @@ spectral_rows_kernel(const cd *scratch, const cd *tw2, int channels, double *out
 }
 
 // ---- host side ----
+// Static check of a spectrum expression: every opcode known, arguments in range, stack depth within TSB_EXPR_STACK,
+// operand types as the opcode wants them, and exactly two doubles (re, im) left at the end.
+const char *expr_check(const tsb_expr *x) {
+    if (!x) return "TSB_GEN_EXPR needs args->expr";
+    if (x->n_ops <= 0 || x->n_ops > TSB_EXPR_MAX_OPS || !x->ops) return "expression: n_ops out of range";
+    if (x->n_iconst < 0 || x->n_iconst > TSB_EXPR_MAX_CONST || x->n_dconst < 0 || x->n_dconst > TSB_EXPR_MAX_CONST)
+        return "expression: too many constants";
+    if (x->n_itab < 0 || x->n_itab > TSB_EXPR_MAX_TABS || x->n_dtab < 0 || x->n_dtab > TSB_EXPR_MAX_TABS)
+        return "expression: too many per-bin tables";
+    if (x->n_iparam < 0 || x->n_iparam > TSB_EXPR_MAX_TABS || x->n_dparam < 0 || x->n_dparam > TSB_EXPR_MAX_TABS)
+        return "expression: too many per-frame parameters";
+    if ((x->n_iconst && !x->iconst) || (x->n_dconst && !x->dconst) || (x->n_itab && !x->itab) || (x->n_dtab && !x->dtab) ||
+        (x->n_iparam && !x->iparam) || (x->n_dparam && !x->dparam))
+        return "expression: a declared constant / table / parameter array is NULL";
+    char ty[TSB_EXPR_STACK];  // 'i' or 'd'
+    int sp = 0;
+    auto need = [&](int k, const char *types) {
+        if (sp < k) return false;
+        for (int j = 0; j < k; j++)
+            if (ty[sp - k + j] != types[j]) return false;
+        return true;
+    };
+    for (int pc = 0; pc < x->n_ops; pc++) {
+        const int w = x->ops[pc], op = w & 255, arg = w >> 8;
+        if (w < 0) return "expression: negative program word";
+        switch (op) {
+            case TSB_X_I_BIN: case TSB_X_I_CH: case TSB_X_I_FRAME: case TSB_X_I_N: case TSB_X_I_CONST: case TSB_X_I_TAB:
+            case TSB_X_I_PARAM: case TSB_X_D_CONST: case TSB_X_D_TAB: case TSB_X_D_PARAM: {
+                const int lim = op == TSB_X_I_CONST ? x->n_iconst : op == TSB_X_I_TAB ? x->n_itab : op == TSB_X_I_PARAM ? x->n_iparam
+                              : op == TSB_X_D_CONST ? x->n_dconst : op == TSB_X_D_TAB ? x->n_dtab : op == TSB_X_D_PARAM ? x->n_dparam : 1;
+                if (arg >= lim) return "expression: constant / table / parameter index out of range";
+                if (sp >= TSB_EXPR_STACK) return "expression: stack overflow";
+                ty[sp++] = (op >= TSB_X_D_CONST) ? 'd' : 'i';
+            } break;
+            case TSB_X_I_ADD: case TSB_X_I_SUB: case TSB_X_I_MUL: case TSB_X_I_DIV: case TSB_X_I_MOD: case TSB_X_I_AND:
+            case TSB_X_I_OR: case TSB_X_I_XOR: case TSB_X_I_SHL: case TSB_X_I_SHR: case TSB_X_I_EQ: case TSB_X_I_LT:
+                if (!need(2, "ii")) return "expression: integer operator needs two integers";
+                sp--;
+                break;
+            case TSB_X_I_NEG: case TSB_X_I_NOT: case TSB_X_I_WRAP32:
+                if (!need(1, "i")) return "expression: integer operator needs an integer";
+                break;
+            case TSB_X_I2D:
+                if (!need(1, "i")) return "expression: I2D needs an integer";
+                ty[sp - 1] = 'd';
+                break;
+            case TSB_X_D2I:
+                if (!need(1, "d")) return "expression: D2I needs a double";
+                ty[sp - 1] = 'i';
+                break;
+            case TSB_X_D_ADD: case TSB_X_D_SUB: case TSB_X_D_MUL: case TSB_X_D_DIV: case TSB_X_D_FMOD: case TSB_X_D_POW:
+                if (!need(2, "dd")) return "expression: floating-point operator needs two doubles";
+                sp--;
+                break;
+            case TSB_X_D_NEG: case TSB_X_D_ABS: case TSB_X_D_SIN: case TSB_X_D_COS: case TSB_X_D_EXP: case TSB_X_D_SQRT:
+            case TSB_X_D_FLOOR:
+                if (!need(1, "d")) return "expression: floating-point function needs a double";
+                break;
+            case TSB_X_PICK:
+                if (arg >= sp) return "expression: PICK below the stack";
+                if (sp >= TSB_EXPR_STACK) return "expression: stack overflow";
+                ty[sp] = ty[sp - 1 - arg];
+                sp++;
+                break;
+            case TSB_X_POLAR:
+                if (!need(2, "dd")) return "expression: POLAR needs (mag, phase)";
+                break;
+            default: return "expression: unknown opcode";
+        }
+    }
+    if (sp != 2 || ty[0] != 'd' || ty[1] != 'd') return "expression: the program must leave exactly two doubles (re, im)";
+    return nullptr;
+}
+
 struct SpecCache {
     std::map<int, cd *> pass_tw;
     std::map<int, std::pair<cd *, cd *>> unit_tabs;  // log2 n -> (wa[n1], wb[n2]) of kernel A
@@ -370,9 +545,41 @@ static cudaError_t run_frames(SpecCache &pc, const SpectralJob &jb, cudaStream_t
     const size_t smB = ((size_t)FB::C * n2 + (size_t)2 * FB::C * (n2 + 1)) * sizeof(cd);  // staging tile + two work tiles
     auto kA_hash = spectral_cols_kernel<L1, L2, GenHash>;
     auto kA_buf = spectral_cols_kernel<L1, L2, GenBuffer>;
+    auto kA_expr = spectral_cols_kernel<L1, L2, GenExpr>;
     auto kB = spectral_rows_kernel<L1, L2>;
     if ((e = cudaFuncSetAttribute(kA_hash, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(kA_buf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(kA_expr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA)) != cudaSuccess) return e;
+    // TSB_GEN_EXPR: the program goes into the kernel's parameter block; tables and per-frame parameters into one
+    // stream-ordered device block: [itab | ipar | dtab | dpar] (8-byte aligned pieces)
+    GenExpr gx{};
+    unsigned char *xblock = nullptr;
+    const tsb_expr *x = reinterpret_cast<const tsb_expr *>(jb.expr);
+    if (jb.generator == SPEC_GEN_EXPR) {
+        gx.code.n_ops = x->n_ops;
+        for (int i = 0; i < x->n_ops; i++) gx.code.ops[i] = x->ops[i];
+        for (int i = 0; i < x->n_iconst; i++) gx.code.ic[i] = x->iconst[i];
+        for (int i = 0; i < x->n_dconst; i++) gx.code.dc[i] = x->dconst[i];
+        gx.n = (int)n;
+        const size_t b_itab = (((size_t)x->n_itab * n * 4) + 7) & ~(size_t)7, b_ipar = (size_t)x->n_iparam * jb.n_frames * 8;
+        const size_t b_dtab = (size_t)x->n_dtab * n * 8, b_dpar = (size_t)x->n_dparam * jb.n_frames * 8;
+        if ((e = cudaMallocAsync(&xblock, b_itab + b_ipar + b_dtab + b_dpar + 8, st)) != cudaSuccess) return e;
+        unsigned char *p = xblock;
+        auto put = [&](const void *src, size_t raw, size_t padded) -> const void * {
+            const void *at = p;
+            if (raw) e = cudaMemcpyAsync(p, src, raw, cudaMemcpyHostToDevice, st);
+            p += padded;
+            return at;
+        };
+        gx.itab = (const int *)put(x->itab, (size_t)x->n_itab * n * 4, b_itab);
+        if (e == cudaSuccess) gx.ipar = (const long long *)put(x->iparam, b_ipar, b_ipar);
+        if (e == cudaSuccess) gx.dtab = (const double *)put(x->dtab, b_dtab, b_dtab);
+        if (e == cudaSuccess) gx.dpar = (const double *)put(x->dparam, b_dpar, b_dpar);
+        if (e != cudaSuccess) {
+            cudaFreeAsync(xblock, st);
+            return e;
+        }
+    }
     if ((e = cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB)) != cudaSuccess) return e;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
@@ -386,6 +593,12 @@ static cudaError_t run_frames(SpecCache &pc, const SpectralJob &jb, cudaStream_t
         if (jb.generator == SPEC_GEN_HASH) {
             GenHash g{(uint32_t)(jb.first_frame + f)};
             kA_hash<<<gridA, FA::NT, smA, st>>>(g, pc.scratch, tw1, wa, wb, jb.channels);
+        } else if (jb.generator == SPEC_GEN_EXPR) {
+            GenExpr g = gx;
+            g.frame = jb.first_frame + f;
+            g.ipar = gx.ipar + (size_t)f * x->n_iparam;
+            g.dpar = gx.dpar + (size_t)f * x->n_dparam;
+            kA_expr<<<gridA, FA::NT, smA, st>>>(g, pc.scratch, tw1, wa, wb, jb.channels);
         } else {
             GenBuffer g{reinterpret_cast<const cd *>(jb.spectrum) + (size_t)f * jb.channels * n, n};
             kA_buf<<<gridA, FA::NT, smA, st>>>(g, pc.scratch, tw1, wa, wb, jb.channels);
@@ -396,6 +609,7 @@ static cudaError_t run_frames(SpecCache &pc, const SpectralJob &jb, cudaStream_t
                                         pc.edge[(f + 1) & 1], aligned);
         *launches += 2;
     }
+    if (xblock) cudaFreeAsync(xblock, st);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (jb.state_edge)
         e = cudaMemcpyAsync(jb.state_edge, pc.edge[jb.n_frames & 1], (size_t)jb.channels * 16, cudaMemcpyDeviceToDevice, st);

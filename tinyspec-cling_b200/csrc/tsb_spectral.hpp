@@ -3,8 +3,10 @@
 #pragma once
 #include <cuda_runtime.h>
 
+struct tsb_expr;
+
 namespace tsb {
-enum { SPEC_GEN_HASH = 0, SPEC_GEN_BUFFER = 1 };
+enum { SPEC_GEN_HASH = 0, SPEC_GEN_BUFFER = 1, SPEC_GEN_EXPR = 2 };
 struct SpectralJob {
     int log2n;               // frame n = 2^log2n (8..18); the spectrum has 2n points
     int channels;
@@ -16,7 +18,9 @@ struct SpectralJob {
     long long out_stride, out_len, out_off0;
     double *state_edge;      // device float64 [channels][2] or nullptr: bins 0 and n carried into the next frame (in/out)
     int load_state;
+    const void *expr;        // SPEC_GEN_EXPR: the caller's tsb_expr (include/tsb200.h), already checked by expr_check
 };
 cudaError_t op_spectral_render(int device, const SpectralJob &job, cudaStream_t st, long long *launches);
 cudaError_t op_spectral_release(int device);
+const char *expr_check(const struct ::tsb_expr *x);  // nullptr = well-formed
 }  // namespace tsb
