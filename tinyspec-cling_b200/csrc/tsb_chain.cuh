@@ -664,9 +664,18 @@ struct Chain {
 #define TSB_TW_DERIVE32 0
 #endif
     static constexpr int TW_DERIVE = sizeof(real) == 8 ? TSB_TW_DERIVE64 : TSB_TW_DERIVE32;
+    // fp64 pipelined kernels: the inverse transform runs IN PLACE (decimation in time; the synthesis writes its
+    // input in digit-reversed order), so it needs one buffer instead of two — at N=1024 that is what lets a sixth
+    // lane fit into an SM's shared memory (36 KB per lane).  (fp32 is bound by registers, not shared memory, and
+    // parks its amplitude exchange array in the second inverse buffer.)
+#ifndef TSB_INV_INPLACE
+#define TSB_INV_INPLACE 1
+#endif
+    static constexpr bool INV_INPLACE = TSB_INV_INPLACE && PIPE && sizeof(real) == 8;
     using C = cpx<real>;
     using Tables = ChainTables<real>;
     using SW = Swz<real>;
+    using ISW = SwzInPlace<real>;  // layout of the in-place inverse buffer
     using otype = typename std::conditional<OUT32, float, real>::type;  // element of the output row and of the tail
     using OC = cpx<otype>;
 
@@ -676,7 +685,7 @@ struct Chain {
         C buf[2][M];  // ping-pong FFT buffers, swizzled (Swz<real>)
         // software pipeline (PIPE): the inverse transform of frame f runs on its own buffers while the other
         // half of the threads runs the forward transform of frame f+1 in `buf`
-        C ibuf[PIPE ? 2 : 1][PIPE ? M : 1];
+        C ibuf[PIPE ? (INV_INPLACE ? 1 : 2) : 1][PIPE ? M : 1];
         // PV amplitude exchange array: fp32 needs its own (the spare FFT buffer is filled by the M fp64
         // increments); in fp64 the spare buffer (16*M bytes) holds both, so nothing extra is reserved.
         real amp_own[(PROG == PROG_PV_SHIFT && sizeof(real) == 4 && !PIPE) ? M : 1];
@@ -715,7 +724,12 @@ struct Chain {
     // into the spare buffer (no barrier between its split and merge).  Inverse pass p reads IB(p), writes IB(p+1).
     static constexpr int INV0 = PIPE ? 0 : (IS_PV ? RB : SB);
     static constexpr int inv_buf(int p) { return (p & 1) ? (INV0 ^ 1) : INV0; }
-    static TSB_HD C *inv_buffer(Smem &sm, int p) { return PIPE ? sm.ibuf[inv_buf(p)] : sm.buf[inv_buf(p)]; }
+    static TSB_HD C *inv_buffer(Smem &sm, int p) {
+        if constexpr (INV_INPLACE) return sm.ibuf[0];
+        else return PIPE ? sm.ibuf[inv_buf(p)] : sm.buf[inv_buf(p)];
+    }
+    // where bin k of the inverse transform's input H goes
+    static TSB_HD int hpos(int k) { return INV_INPLACE ? ISW::f(DitOrder<LOG2M>::pos(k)) : SW::f(k); }
 
     // ------------------------------------------------------------------ state in / out
     // state rows: registers <-> [row][M] arrays, thread `tid` owning bins (k, M-k) of its slots.  The register
@@ -969,8 +983,8 @@ struct Chain {
     static TSB_HD void merge_pair(C *H, const Tables &tb, int k, C Zk, C Zp) {
         C hk, hp;
         merge_vals(tb, k, Zk, Zp, hk, hp);
-        H[SW::f(k)] = hk;
-        H[SW::f(M - k)] = hp;
+        H[hpos(k)] = hk;
+        H[hpos(M - k)] = hp;
     }
     static TSB_HD void merge_vals(const Tables &tb, int k, C Zk, C Zp, C &hk, C &hp) {
         C ee = Zk + conj(Zp);
@@ -1241,8 +1255,8 @@ struct Chain {
             int kb = sp ? HALF : M - k;
             if (!((rg.used >> (16 + 2 * i)) & 3u)) {
                 // neither bin has a source: silent, phase_sum unchanged (rtlib/pv.hpp:34 adds 0)
-                H[SW::f(k)] = mk<real>(0, 0);
-                H[SW::f(kb)] = mk<real>(0, 0);
+                H[hpos(k)] = mk<real>(0, 0);
+                H[hpos(kb)] = mk<real>(0, 0);
                 continue;
             }
             real amp;
@@ -1255,8 +1269,8 @@ struct Chain {
                 C hk, hp;
                 merge_vals(tb, k, conj(Ya), conj(Yb), hk, hp);
                 const real z0 = (real)2 * Ya.x;  // thread 0: Z[0] = Re Y[0] (not halved), Z[M] = 0
-                H[SW::f(k)] = sp ? mk<real>(z0, -z0) : hk;
-                H[SW::f(kb)] = sp ? mk<real>((real)2 * Yb.x, (real)-2 * Yb.y) : hp;  // 2*Z[M/2], Z = conj(Y)
+                H[hpos(k)] = sp ? mk<real>(z0, -z0) : hk;
+                H[hpos(kb)] = sp ? mk<real>((real)2 * Yb.x, (real)-2 * Yb.y) : hp;  // 2*Z[M/2], Z = conj(Y)
             } else {
                 merge_pair(H, tb, k, conj(Ya), conj(Yb));
             }
@@ -1281,8 +1295,8 @@ struct Chain {
                 real x0 = (z0.x + z0.y) * TSB_LDG(&tb.gain[0]);  // X[0]
                 real xm = (z0.x - z0.y) * TSB_LDG(&tb.gain[M]);  // X[N/2]
                 real gh = TSB_LDG(&tb.gain[HALF]);
-                H[SW::f(0)] = mk<real>(x0 + xm, -(x0 - xm));
-                H[SW::f(HALF)] = mk<real>((real)2 * gh * zh.x, (real)-2 * gh * zh.y);  // 2*Z[M/2], Z = g*conj(zh)
+                H[hpos(0)] = mk<real>(x0 + xm, -(x0 - xm));
+                H[hpos(HALF)] = mk<real>((real)2 * gh * zh.x, (real)-2 * gh * zh.y);  // 2*Z[M/2], Z = g*conj(zh)
             }
         }
     }
@@ -1295,11 +1309,14 @@ struct Chain {
     static TSB_HD void inv_pass(int tid, int lane, Smem &sm, const Tables &tb, const ChainArgs &a, long long out_pos,
                                 int hop) {
         const C *src = inv_buffer(sm, P);
-        auto in = [&](int x, int c) { return ld_sw(src, x, c); };
+        auto in = [&](int x, int c) { return INV_INPLACE ? src[ISW::f(x) ^ ISW::f(c)] : ld_sw(src, x, c); };
         if (P < PASSES - 1) {
             C *dst = inv_buffer(sm, P + 1);
-            auto out = [&](int x, int c, C v) { st_sw(dst, x, c, v); };
-            stockham_pass_io<real, LOG2M, NT, P, decltype(in), decltype(out), TW_DERIVE>(tid, tb.tw, in, out);
+            auto out = [&](int x, int c, C v) {
+                if (INV_INPLACE) dst[ISW::f(x) ^ ISW::f(c)] = v;
+                else st_sw(dst, x, c, v);
+            };
+            stockham_pass_io<real, LOG2M, NT, P, decltype(in), decltype(out), TW_DERIVE, INV_INPLACE>(tid, tb.tw, in, out);
         } else {
             otype *dstg = reinterpret_cast<otype *>(a.out) + (long long)lane * a.out_stride + out_pos;
             const C *ws = reinterpret_cast<const C *>(tb.win_s);
@@ -1332,7 +1349,7 @@ struct Chain {
                     if (2 * m < emit_end) *reinterpret_cast<OC *>(dstg + 2 * m) = mk<otype>(emit_val(t.x, vx), emit_val(t.y, vy));
                     *slot = mk<otype>(done ? (otype)0 : tail_val(t.x, vx), done ? (otype)0 : tail_val(t.y, vy));
                 };
-                stockham_pass_io<real, LOG2M, NT, P, decltype(in), decltype(out), TW_DERIVE>(tid, tb.tw, in, out);
+                stockham_pass_io<real, LOG2M, NT, P, decltype(in), decltype(out), TW_DERIVE, INV_INPLACE>(tid, tb.tw, in, out);
             } else {
                 auto out = [&](int x, int c, C f) {
                     const int m = x + c;
@@ -1351,7 +1368,7 @@ struct Chain {
                         sm.ola[slot] = acc;
                     }
                 };
-                stockham_pass_io<real, LOG2M, NT, P, decltype(in), decltype(out), TW_DERIVE>(tid, tb.tw, in, out);
+                stockham_pass_io<real, LOG2M, NT, P, decltype(in), decltype(out), TW_DERIVE, INV_INPLACE>(tid, tb.tw, in, out);
             }
             // hop larger than the frame: nothing overlaps those positions (tinyspec.cpp:184-191)
             for (int n = N + tid; n < hop; n += NT)

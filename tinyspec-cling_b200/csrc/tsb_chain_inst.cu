@@ -13,6 +13,14 @@
 #ifndef TSB_REGS_PV64
 #define TSB_REGS_PV64 96
 #endif
+#ifndef TSB_REGS_PV64_INPLACE
+// pipelined fp64 kernels with the in-place inverse transform (Chain::INV_INPLACE) have shared memory for one more lane
+// per SM than 96 registers allow; at 80 registers they spill a little.  Measured: N=2048 +6 % with the third lane,
+// N=512 +18 %; at N=1024 six lanes at 80 registers equal five at 96 (137 M frame-channels/s either way: the kernel
+// is bound by the L1/shared-memory data pipe, not by latency — even four lanes per SM reach 137 M), so that size keeps
+// 96 registers and gives the shared memory it no longer needs to the L1 cache instead (see launch(): +4 %).
+#define TSB_REGS_PV64_INPLACE 80
+#endif
 
 namespace tsb {
 
@@ -45,14 +53,12 @@ template <class CH>
 constexpr int min_blocks() {
     constexpr int by_smem = (227 * 1024) / ((int)sizeof(typename CH::Smem) + 1024);
     constexpr int by_threads = 2048 / CH::T;
-    constexpr int by_regs = 65536 / (CH::T * (sizeof(typename CH::C) == 8 ? (CH::IS_PV ? TSB_REGS_PV32 : 80) : (CH::IS_PV ? TSB_REGS_PV64 : 96)));
+    constexpr int by_regs = 65536 / (CH::T * (sizeof(typename CH::C) == 8 ? (CH::IS_PV ? TSB_REGS_PV32 : 80) : (CH::IS_PV ? ((CH::INV_INPLACE && CH::N != 1024) ? TSB_REGS_PV64_INPLACE : TSB_REGS_PV64) : 96)));
     int b = by_smem < by_threads ? by_smem : by_threads;
     b = b < by_regs ? b : by_regs;
     return b < 1 ? 1 : (b > 32 ? 32 : b);
 }
 
-template <class CH>
-constexpr int default_carveout_kb() { return 228; }
 
 // PREPASS: the time-parallel pre-pass (ChainArgs::mode == 1: analysis and per-frame increments only)
 // The fp32 pre-pass carries the exact-wrap phase (Chain::phase_wrap_fix) in its plain frame loop; one CTA less per
@@ -82,10 +88,16 @@ static cudaError_t launch(const void *tables, const ChainArgs &a, cudaStream_t s
     size_t smem = sizeof(typename CH::Smem);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    // Shared memory and L1 share 228 KB per SM.  The constant tables (twiddles, windows, per-bin phase
-    // constants, shift map: ~20 KB fp32 / ~34 KB fp64 at N=1024) are read through L1 every frame, so the
-    // carve-out leaves them room instead of packing the last CTA in (TSB_CARVEOUT_KB overrides, for tuning).
-    int carve_kb = default_carveout_kb<CH>();
+    // Shared memory and L1 share 228 KB per SM, and the constant tables (twiddles, windows, per-bin phase constants,
+    // shift map: ~20 KB fp32 / ~34 KB fp64 at N=1024) are read through L1 every frame (TSB_CARVEOUT_KB overrides the
+    // carve-out, for tuning).  The fp64 kernels with the in-place inverse transform ask for exactly what their resident lanes use (N=1024: 5 x
+    // 37 KB -> 43 KB of L1 instead of ~3: 139 -> 143 M frame-channels/s); the others keep the maximum (fp32 at N=1024
+    // measured 1.5-3 % slower with any smaller carve-out).
+    int carve_kb = 228;
+    if (CH::INV_INPLACE) {
+        constexpr int blocks = kernel_blocks<CH, false>();
+        carve_kb = (int)((blocks * (sizeof(typename CH::Smem) + 1024) + 1023) / 1024);
+    }
     if (const char *ev = getenv("TSB_CARVEOUT_KB")) carve_kb = atoi(ev);
     int pct = carve_kb >= 228 ? 100 : (carve_kb * 100 + 227) / 228;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct);

@@ -107,6 +107,31 @@ TSB_HD cpx<T> conj(cpx<T> a) { return mk<T>(a.x, -a.y); }
 template <typename T>
 TSB_HD cpx<T> mul_mi(cpx<T> a) { return mk<T>(a.y, -a.x); }
 
+#ifndef TSB_F32X2
+#define TSB_F32X2 1  // 0: scalar; 1: packed complex sums; 2: packed complex products too (measured slower than 1)
+#endif
+#if defined(__CUDA_ARCH__) && TSB_F32X2 >= 1
+// sm_100a packed single precision (FADD2 / FMUL2 / FFMA2: two IEEE operations per lane and issue slot): a complex
+// float lives in an aligned register pair, so complex sums are one instruction.  Each half rounds exactly like the
+// scalar operation (a - b as fma(b, -1, a): the product is exact).
+TSB_D float2 f2(cpx<float> a) { return make_float2(a.x, a.y); }
+TSB_D cpx<float> operator+(cpx<float> a, cpx<float> b) {
+    const float2 r = __fadd2_rn(f2(a), f2(b));
+    return mk<float>(r.x, r.y);
+}
+TSB_D cpx<float> operator-(cpx<float> a, cpx<float> b) {
+    const float2 r = __ffma2_rn(f2(b), make_float2(-1.f, -1.f), f2(a));
+    return mk<float>(r.x, r.y);
+}
+#if TSB_F32X2 >= 2
+TSB_D cpx<float> cmul(cpx<float> a, cpx<float> b) {  // (a.x b.x - a.y b.y, a.x b.y + a.y b.x)
+    const float2 t = __fmul2_rn(make_float2(a.x, a.x), f2(b));
+    const float2 r = __ffma2_rn(make_float2(a.y, a.y), make_float2(-b.y, b.x), t);
+    return mk<float>(r.x, r.y);
+}
+#endif
+#endif
+
 constexpr int ilog2(unsigned v) { return v <= 1 ? 0 : 1 + ilog2(v >> 1); }
 
 // ---- forward DFTs of size 2, 4, 8 (kernel exp(-2*pi*i*j*k/R)), natural order in and out ----
@@ -181,6 +206,20 @@ struct Swz<double> {  // 16-byte elements: 8 lanes per wavefront
     static TSB_HD constexpr int f(int i) { return i ^ (((i >> 3) ^ (i >> 4)) & 7); }
 };
 
+// Layout of a buffer transformed IN PLACE (stockham_pass_io<..., INPLACE>): every pass reads and writes base + t*Ns,
+// i.e. with per-thread strides 1, 8, 64, ..., and the buffer is filled in digit-reversed order (stride M/8 across
+// lanes).  Folding the second and third octal digits into the first makes all of them conflict-free.
+template <typename T>
+struct SwzInPlace;
+template <>
+struct SwzInPlace<float> {
+    static TSB_HD constexpr int f(int i) { return i ^ (((i >> 4) ^ (i >> 7)) & 15); }
+};
+template <>
+struct SwzInPlace<double> {
+    static TSB_HD constexpr int f(int i) { return i ^ (((i >> 3) ^ (i >> 6)) & 7); }
+};
+
 // Per-pass twiddle tables: for pass P, entry [(t-1)*Ns + jm] = exp(-2*pi*i*jm*t/(Ns*R)), 1 <= t < R, jm < Ns.
 // For a fixed t consecutive threads (consecutive jm) read consecutive entries: one coalesced 8/16-byte load per
 // twiddle (the [jm][t] layout costs 8x the L1 wavefronts: measured, it doubled the kernel's L1 data-pipe load).
@@ -197,7 +236,11 @@ struct TwLayout {
 // radix-R DFT and hands out(base, t*Ns, value) with base = (j/Ns)*Ns*R + (j%Ns).  `in` / `out` are
 // functors so that the first pass can read (and window) the input ring and the last pass can feed the
 // overlap-add directly.  `twp` is the per-pass twiddle table (TwLayout).
-template <typename T, int LOG2M, int THREADS, int P, class In, class Out, int TW_DERIVE = 0>
+//
+// INPLACE: the pass of the in-place decimation-in-time transform instead — the same butterflies and twiddles, but
+// the inputs are read where the outputs go, in(base, t*Ns), so a pass needs no second buffer (each thread reads its
+// R points before it writes them).  The data must then start in digit-reversed order (DitOrder<LOG2M>::pos).
+template <typename T, int LOG2M, int THREADS, int P, class In, class Out, int TW_DERIVE = 0, bool INPLACE = false>
 TSB_HD void stockham_pass_io(int tid, const cpx<T> *twp, In in, Out out) {
     using RP = RadixPlan<LOG2M>;
     constexpr int M = 1 << LOG2M;
@@ -235,23 +278,39 @@ TSB_HD void stockham_pass_io(int tid, const cpx<T> *twp, In in, Out out) {
 #pragma unroll
                 for (int t = 1; t < R; t++) tw[t] = TSB_LDG(&w[(t - 1) * Ns]);
             }
+            int base = ((j - jm) * R) + jm;
 #pragma unroll
-            for (int t = 0; t < R; t++) v[t] = in(j, t * NB);
+            for (int t = 0; t < R; t++) v[t] = INPLACE ? in(base, t * Ns) : in(j, t * NB);
 #pragma unroll
             for (int t = 1; t < R; t++) v[t] = cmul(v[t], tw[t]);
             dftR<R>(v);
-            int base = ((j - jm) * R) + jm;
 #pragma unroll
             for (int t = 0; t < R; t++) out(base, t * Ns, v[t]);
         } else {
 #pragma unroll
-            for (int t = 0; t < R; t++) v[t] = in(j, t * NB);
+            for (int t = 0; t < R; t++) v[t] = INPLACE ? in(j * R, t) : in(j, t * NB);
             dftR<R>(v);
 #pragma unroll
             for (int t = 0; t < R; t++) out(j * R, t, v[t]);
         }
     }
 }
+
+// Where sample k of the natural-order input must lie for the in-place passes (INPLACE above) to end in natural order:
+// pass p joins R_p sub-transforms of Ns_p points that hold the samples congruent to t modulo R_p (decimation in time),
+// so k = t_{P-1} + R_{P-1} (t_{P-2} + R_{P-2} (... t_0)) sits at sum t_p Ns_p — the digits of k, reversed.
+template <int LOG2M>
+struct DitOrder {
+    using RP = RadixPlan<LOG2M>;
+    static TSB_HD constexpr int pos(int k) {
+        int at = 0;
+        for (int p = RP::passes - 1; p >= 0; p--) {
+            at += (k & (RP::radix(p) - 1)) * RP::ns(p);
+            k /= RP::radix(p);
+        }
+        return at;
+    }
+};
 
 // plain buffer-to-buffer pass (unswizzled), used by the unit tests and the standalone FFT kernels
 template <typename T, int LOG2M, int THREADS, int P>

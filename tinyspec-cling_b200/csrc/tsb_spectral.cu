@@ -14,7 +14,8 @@
 // Real samples from a Hermitian spectrum of 2n points need one complex FFT of n points: with W = e^{-i pi / n},
 //     G[k] = (X[k] + conj(X[n-k])) + i W^k (X[k] - conj(X[n-k])),   v = FFT_n(G),   y[2j] = Re v[j], y[2j+1] = Im v[j]
 // and the n-point FFT is a four-step one (n = n1*n2, k = n2*k1 + k2, j = j1 + n1*j2):
-//     kernel A  generator + G + n2 column FFTs of n1 points + twiddle e^{-2 pi i k2 j1 / n}  -> scratch[j1][k2]
+//     kernel A  generator + G (bins k and n-k together, from the same two spectrum values) + n2 column FFTs of n1 points
+//               + twiddle e^{-2 pi i k2 j1 / n}  -> scratch[j1][k2]
 //     kernel B  n1 row FFTs of n2 points; only j < n/2 is needed (the first n samples): unpack, 1/sqrt(2n), the
 //               carried bins 0 / n added analytically, window, overlap-add into the output rows
 // The scratch of one frame (channels * n * 16 bytes; 64 MiB at cfg5) is written and read back to back, i.e. from L2.
@@ -43,7 +44,9 @@ struct GenHash {
         h *= 2246822519u;
         h ^= h >> 13;
         // x / 32768.0 / (double)(1 + (i >> 4)): the first division is exact; the second as a Newton reciprocal
-        // (shared by both components) and one exact-remainder correction of each quotient (Markstein)
+        // (shared by both components) and one exact-remainder correction of each quotient (Markstein).  (A table of
+        // correctly rounded reciprocals saves a tenth of the kernel's instructions and costs time: the load's latency
+        // sits in front of everything else the iteration does — measured, profiles/README.md)
         const double d = (double)(1 + (i >> 4));
         double r;
         asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
@@ -202,36 +205,73 @@ __device__ __forceinline__ cd unit_w(long long q, double inv_n) {
     return mk<double>(c, s);
 }
 
-// ---- kernel A: one CTA = C consecutive columns k2 of one channel ----
+#ifndef TSB_SPEC_UG
+#define TSB_SPEC_UG 2  // unroll factor of kernel A's generation loop
+#endif
+#ifndef TSB_SPEC_UO
+#define TSB_SPEC_UO 1  // ... of its output loop
+#endif
+// ---- kernel A: one CTA = C/2 columns k2 of one channel together with their mirror columns n2 - k2 ----
+// G[k] and G[n-k] are made of the same two spectrum values: with a = X[k], b = X[n-k], sm = a + conj(b),
+// wd = W^k (a - conj(b)) (and W^(n-k) = -conj(W^k)):   G[k] = sm + i wd,   G[n-k] = conj(sm) + i conj(wd).
+// So a CTA takes column pairs (k2, n2 - k2) — the mirror of row k1 of column k2 is row n1-1-k1 of column n2-k2 — and
+// every spectrum value is generated once instead of twice (for an interpreted expression that is half the kernel).
+// Columns 0 and n2/2 mirror into themselves (rows k1 <-> n1-k1 and k1 <-> n1-1-k1): they share the pair slot that
+// column 0 would otherwise leave half empty.  Tile slot 2p holds the low column of pair p, slot 2p+1 its mirror.
 // wa[k1] = e^{-i pi k1 / n1} (n1 entries), wb[k2] = e^{-i pi k2 / n} (n2 entries): W^k = wa[k1] * wb[k2] for k = n2*k1 + k2
 template <int L1, int L2, class Gen>
 __global__ void __launch_bounds__(SubFft<L1, L2>::NT, SubFft<L1, L2>::NT >= 256 ? 3 : 4)
 spectral_cols_kernel(Gen gen, cd *scratch, const cd *tw1, const cd *wa, const cd *wb, int channels) {
     using F = SubFft<L1, L2>;
-    constexpr int n1 = 1 << L1, n2 = 1 << L2, C = F::C, NT = F::NT;
+    constexpr int n1 = 1 << L1, n2 = 1 << L2, C = F::C, NT = F::NT, CP = C / 2;
     constexpr long long n = (long long)n1 * n2;
+    static_assert(C >= 2 && C % 2 == 0 && n1 >= 2 && n2 >= 4, "column pairs need an even tile and n2 >= 4");
     // sub-transform c lives at c * SP of a tile: the stride is padded by one element so that the C columns a warp touches
     // together (consecutive threads = consecutive columns) fall into different banks
     constexpr int SP = n1 + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cd *bufA = reinterpret_cast<cd *>(smem_raw), *bufB = bufA + C * SP;
     const int groups = n2 / C;
-    // a thread keeps one column (c) and walks k1 / j1 in steps of NT / C
+    // generation: a thread keeps one column pair (p) and walks k1 in steps of NT / CP
+    constexpr int STEPG = NT / CP;
+    constexpr int UG = TSB_SPEC_UG, UO = TSB_SPEC_UO;
+    const int p = threadIdx.x % CP, rg = threadIdx.x / CP;
+    // output: a thread keeps one tile slot (c) and walks j1 in steps of NT / C
     constexpr int STEP = NT / C;
     const int c = threadIdx.x % C, r0 = threadIdx.x / C;
     for (long long b = blockIdx.x; b < (long long)channels * groups; b += gridDim.x) {
-        const int ch = (int)(b / groups), k2 = (int)(b % groups) * C + c;
-        const cd wk2 = TSB_LDG(&wb[k2]);
-        for (int k1 = r0; k1 < n1; k1 += STEP) {  // G[k], k = n2*k1 + k2
-            const long long k = (long long)n2 * k1 + k2;
-            cd g = mk<double>(0.0, 0.0);
-            if (k > 0) {  // (bins 0 and n are the carried ones: kernel B adds their contribution)
-                const cd a = gen(ch, (int)k), bb = conj(gen(ch, (int)(n - k)));
-                const cd sm = a + bb, d = a - bb;
-                const cd wd = cmul(cmul(TSB_LDG(&wa[k1]), wk2), d);  // W^k * d
-                g = mk<double>(sm.x - wd.y, sm.y + wd.x);          // sm + i*W^k*d
+        const int ch = (int)(b / groups), g = (int)(b % groups);
+        const int col_lo = g * CP + p;
+        const bool self = col_lo == 0;  // the pair slot of the two self-mirrored columns, 0 and n2/2
+        const cd wk_lo = TSB_LDG(&wb[col_lo]);
+#pragma unroll UG
+        for (int it = 0; it < (n1 + STEPG - 1) / STEPG; it++) {
+            const int k1 = rg + it * STEPG;
+            if (n1 % STEPG != 0 && k1 >= n1) break;
+            // element A = (slot_a, k1a) of column col_a, bin ka; its mirror B = bin n - ka
+            int slot_a = 2 * p, k1a = k1, col_a = col_lo;
+            if (self && k1 >= n1 / 2) {
+                slot_a = 2 * p + 1;
+                k1a = k1 - n1 / 2;
+                col_a = n2 / 2;
             }
-            bufA[c * SP + Swz<double>::f(k1)] = g;
+            long long ka = (long long)n2 * k1a + col_a;
+            cd wk = self ? TSB_LDG(&wb[col_a]) : wk_lo;
+            const bool first = ka == 0;  // bin 0 is a carried one (kernel B adds its contribution): G[0] = 0, and this
+            if (first) {                 // iteration takes the bin that mirrors into itself instead, n/2
+                bufA[slot_a * SP + Swz<double>::f(0)] = mk<double>(0.0, 0.0);
+                k1a = n1 / 2;
+                ka = n / 2;
+            }
+            const long long kb = n - ka;
+            const cd a = gen(ch, (int)ka), bb = conj(first ? a : gen(ch, (int)kb));
+            const cd sm = a + bb, d = a - bb;
+            const cd wd = cmul(cmul(TSB_LDG(&wa[k1a]), wk), d);              // W^k * d
+            bufA[slot_a * SP + Swz<double>::f(k1a)] = mk<double>(sm.x - wd.y, sm.y + wd.x);  // sm + i*W^k*d
+            if (!first) {
+                const int slot_b = self ? slot_a : 2 * p + 1, k1b = (int)(kb >> L2);
+                bufA[slot_b * SP + Swz<double>::f(k1b)] = mk<double>(sm.x + wd.y, wd.x - sm.y);  // conj(sm) + i*conj(wd)
+            }
         }
         __syncthreads();
         const int gi = threadIdx.x / F::T, lt = threadIdx.x % F::T;
@@ -239,6 +279,9 @@ spectral_cols_kernel(Gen gen, cd *scratch, const cd *tw1, const cd *wa, const cd
         __syncthreads();
         {   // A[k2][j1] * e^{-2 pi i k2 j1 / n} -> scratch[ch][j1][k2]: the factor is base^j1 with base = wb[k2]^2; the
             // thread starts at base^r0 (square-and-multiply) and advances by base^STEP (at most 8 steps: no drift)
+            const int lo = g * CP + (c >> 1);
+            const int k2 = (c & 1) ? (lo == 0 ? n2 / 2 : n2 - lo) : lo;
+            const cd wk2 = TSB_LDG(&wb[k2]);
             const cd base = cmul(wk2, wk2);
             cd w = mk<double>(1.0, 0.0), pw = base;
 #pragma unroll
@@ -248,7 +291,10 @@ spectral_cols_kernel(Gen gen, cd *scratch, const cd *tw1, const cd *wa, const cd
             }
             const cd out_step = pw;  // base^STEP (STEP is a power of two)
             cd *dst = scratch + (long long)ch * n + k2;
-            for (int j1 = r0; j1 < n1; j1 += STEP) {
+#pragma unroll UO
+            for (int it = 0; it < (n1 + STEP - 1) / STEP; it++) {
+                const int j1 = r0 + it * STEP;
+                if (n1 % STEP != 0 && j1 >= n1) break;
                 dst[(long long)j1 * n2] = cmul(res[c * SP + Swz<double>::f(j1)], w);
                 w = cmul(w, out_step);
             }
