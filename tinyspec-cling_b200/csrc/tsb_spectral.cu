@@ -21,6 +21,8 @@
 // The scratch of one frame (channels * n * 16 bytes; 64 MiB at cfg5) is written and read back to back, i.e. from L2.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include <cmath>
 #include <map>
 #include <vector>
@@ -491,8 +493,12 @@ const char *expr_check(const tsb_expr *x) {
 struct SpecCache {
     std::map<int, cd *> pass_tw;
     std::map<int, std::pair<cd *, cd *>> unit_tabs;  // log2 n -> (wa[n1], wb[n2]) of kernel A
-    cd *scratch = nullptr;
+    cd *scratch = nullptr;  // two frames' worth when the frames are pipelined (scratch_slots == 2)
     size_t scratch_elems = 0;
+    int scratch_slots = 0;
+    // frame pipeline: kernel A of frame f+1 runs on `aux` beside kernel B of frame f (see run_frames)
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_a[2] = {nullptr, nullptr}, ev_b[2] = {nullptr, nullptr};
     double *edge[2] = {nullptr, nullptr};
     size_t edge_ch = 0;
 };
@@ -519,6 +525,7 @@ cudaError_t op_spectral_release(int device) {
     if (pc.scratch) cudaFree(pc.scratch);
     pc.scratch = nullptr;
     pc.scratch_elems = 0;
+    pc.scratch_slots = 0;
     for (double *&p : pc.edge) {
         if (p) cudaFree(p);
         p = nullptr;
@@ -563,13 +570,26 @@ static cudaError_t run_frames(SpecCache &pc, const SpectralJob &jb, cudaStream_t
     if ((e = spec_twiddles(pc, L1, &tw1)) != cudaSuccess) return e;
     if ((e = spec_twiddles(pc, L2, &tw2)) != cudaSuccess) return e;
     if ((e = spec_unit_tables(pc, L1, L2, &wa, &wb)) != cudaSuccess) return e;
-    const size_t need = (size_t)jb.channels * n;
-    if (pc.scratch_elems < need) {
+    // Frame pipeline (TSB_SPEC_OVERLAP=1, more than one frame): kernel A of frame f+1 depends on nothing kernel B of
+    // frame f produces (the carried bins travel from B to B), so it runs on a second stream into the other half of
+    // a two-frame scratch: A is bound by the fp64 pipe, B by the latency of its L2 round trips — side by side on an
+    // SM they fill each other's gaps.  Events order A(f) -> B(f) and B(f) -> A(f+2) (same scratch half).
+    static const bool want_overlap = [] { const char *v = getenv("TSB_SPEC_OVERLAP"); return v && atoi(v) != 0; }();
+    const bool overlap = want_overlap && jb.n_frames > 1;
+    const size_t per_frame = (size_t)jb.channels * n;
+    const int slots = overlap ? 2 : 1;
+    if (pc.scratch_elems < per_frame * slots) {
         if (pc.scratch) cudaFree(pc.scratch);
         pc.scratch = nullptr;
         pc.scratch_elems = 0;
-        if ((e = cudaMalloc(&pc.scratch, need * sizeof(cd))) != cudaSuccess) return e;
-        pc.scratch_elems = need;
+        if ((e = cudaMalloc(&pc.scratch, per_frame * slots * sizeof(cd))) != cudaSuccess) return e;
+        pc.scratch_elems = per_frame * slots;
+    }
+    if (overlap && !pc.aux) {
+        if ((e = cudaStreamCreateWithFlags(&pc.aux, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        cudaEvent_t *evs[5] = {&pc.ev_start, &pc.ev_a[0], &pc.ev_a[1], &pc.ev_b[0], &pc.ev_b[1]};
+        for (cudaEvent_t *ev : evs)
+            if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return e;
     }
     if (pc.edge_ch < (size_t)jb.channels) {
         for (double *&p : pc.edge) {
@@ -633,26 +653,42 @@ static cudaError_t run_frames(SpecCache &pc, const SpectralJob &jb, cudaStream_t
     int perB = 1;  // resident CTAs of kernel B per SM: it is launched persistent, one wave
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perB, kB, FB::NT, smB)) != cudaSuccess) return e;
     if (perB < 1) perB = 1;
+    if (const char *v = getenv("TSB_SPEC_BPERSM")) {  // tuning: persistent CTAs of kernel B per SM
+        const int w = atoi(v);
+        if (w >= 1 && w < perB) perB = w;
+    }
     const unsigned gridA = (unsigned)((long long)jb.channels * (n2 / CA));
     const unsigned gridB = (unsigned)(tilesB < (long long)sms * perB ? tilesB : (long long)sms * perB);
+    if (overlap) {  // everything queued on `st` so far (tables, the caller's spectrum, earlier renders) precedes the first A
+        if ((e = cudaEventRecord(pc.ev_start, st)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(pc.aux, pc.ev_start, 0)) != cudaSuccess) return e;
+    }
+    const cudaStream_t sa = overlap ? pc.aux : st;
     for (long long f = 0; f < jb.n_frames; f++) {
+        cd *scr = pc.scratch + (overlap ? (size_t)(f & 1) * per_frame : 0);
+        if (overlap && f >= 2 && (e = cudaStreamWaitEvent(sa, pc.ev_b[f & 1], 0)) != cudaSuccess) return e;
         if (jb.generator == SPEC_GEN_HASH) {
             GenHash g{(uint32_t)(jb.first_frame + f)};
-            kA_hash<<<gridA, FA::NT, smA, st>>>(g, pc.scratch, tw1, wa, wb, jb.channels);
+            kA_hash<<<gridA, FA::NT, smA, sa>>>(g, scr, tw1, wa, wb, jb.channels);
         } else if (jb.generator == SPEC_GEN_EXPR) {
             GenExpr g = gx;
             g.frame = jb.first_frame + f;
             g.ipar = gx.ipar + (size_t)f * x->n_iparam;
             g.dpar = gx.dpar + (size_t)f * x->n_dparam;
-            kA_expr<<<gridA, FA::NT, smA, st>>>(g, pc.scratch, tw1, wa, wb, jb.channels);
+            kA_expr<<<gridA, FA::NT, smA, sa>>>(g, scr, tw1, wa, wb, jb.channels);
         } else {
             GenBuffer g{reinterpret_cast<const cd *>(jb.spectrum) + (size_t)f * jb.channels * n, n};
-            kA_buf<<<gridA, FA::NT, smA, st>>>(g, pc.scratch, tw1, wa, wb, jb.channels);
+            kA_buf<<<gridA, FA::NT, smA, sa>>>(g, scr, tw1, wa, wb, jb.channels);
+        }
+        if (overlap) {
+            if ((e = cudaEventRecord(pc.ev_a[f & 1], sa)) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(st, pc.ev_a[f & 1], 0)) != cudaSuccess) return e;
         }
         const long long pos0 = jb.out_off0 + f * jb.hop;
         const int aligned = ((pos0 | jb.out_stride) & 1) == 0 && (reinterpret_cast<uintptr_t>(jb.out) & 15) == 0;
-        kB<<<gridB, FB::NT, smB, st>>>(pc.scratch, tw2, jb.channels, jb.out, jb.out_stride, jb.out_len, pos0, pc.edge[f & 1],
+        kB<<<gridB, FB::NT, smB, st>>>(scr, tw2, jb.channels, jb.out, jb.out_stride, jb.out_len, pos0, pc.edge[f & 1],
                                         pc.edge[(f + 1) & 1], aligned);
+        if (overlap && (e = cudaEventRecord(pc.ev_b[f & 1], st)) != cudaSuccess) return e;
         *launches += 2;
     }
     if (xblock) cudaFreeAsync(xblock, st);
