@@ -488,6 +488,25 @@ def main():
             line["cfg5"]["voidbubbles_expr"] = {"what": "hacks/spectral_bytebeat/voidbubbles.cpp:9-13 as a TSB_GEN_EXPR program "
                                                         "(36 words, interpreted per bin in kernel A), same shape",
                                                 "ms_per_render": msx, "frame_channels_per_s": ch5 * f5 / (msx * 1e-3)}
+            # the same with the spectrum READ from HBM (TSB_GEN_BUFFER): the case SURVEY.md §8d's algorithmic bytes
+            # describe literally (1.5 GB of spectra for the 24 frames: larger than L2)
+            g5 = torch.Generator(device=dev)
+            g5.manual_seed(5)
+            spec5 = torch.view_as_complex(torch.rand((f5, ch5, n5, 2), generator=g5, device=dev, dtype=torch.float64) - 0.5)
+            for _ in range(2):
+                ctx.spectral_render(n5, ch5, f5, hop5, out=out5, spectrum=spec5)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps5):
+                ctx.spectral_render(n5, ch5, f5, hop5, out=out5, spectrum=spec5)
+            e1.record()
+            torch.cuda.synchronize()
+            msb = e0.elapsed_time(e1) / reps5
+            fcb = ch5 * f5 / (msb * 1e-3)
+            line["cfg5"]["spectrum_from_hbm"] = {"what": "caller's complex128 spectra resident in HBM instead of the in-kernel generator",
+                                                 "ms_per_render": msb, "frame_channels_per_s": fcb,
+                                                 "roofline_frac": fcb * balg5 / 1e9 / peak}
+            del spec5
             bb = os.path.join(ROOT, "oracle", "_ref", "ref_bytebeat_tap_mkl")
             if os.path.exists(bb):
                 try:

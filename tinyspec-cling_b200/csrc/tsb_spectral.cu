@@ -498,7 +498,7 @@ struct SpecCache {
     int scratch_slots = 0;
     // frame pipeline: kernel A of frame f+1 runs on `aux` beside kernel B of frame f (see run_frames)
     cudaStream_t aux = nullptr;
-    cudaEvent_t ev_start = nullptr, ev_a[2] = {nullptr, nullptr}, ev_b[2] = {nullptr, nullptr};
+    cudaEvent_t ev_start = nullptr, ev_a[4] = {nullptr, nullptr, nullptr, nullptr}, ev_b[4] = {nullptr, nullptr, nullptr, nullptr};
     double *edge[2] = {nullptr, nullptr};
     size_t edge_ch = 0;
 };
@@ -570,14 +570,14 @@ static cudaError_t run_frames(SpecCache &pc, const SpectralJob &jb, cudaStream_t
     if ((e = spec_twiddles(pc, L1, &tw1)) != cudaSuccess) return e;
     if ((e = spec_twiddles(pc, L2, &tw2)) != cudaSuccess) return e;
     if ((e = spec_unit_tables(pc, L1, L2, &wa, &wb)) != cudaSuccess) return e;
-    // Frame pipeline (TSB_SPEC_OVERLAP=1, more than one frame): kernel A of frame f+1 depends on nothing kernel B of
+    // Frame pipeline (more than one frame; TSB_SPEC_OVERLAP = scratch slots, default 2, 1 = off): kernel A of frame f+1 depends on nothing kernel B of
     // frame f produces (the carried bins travel from B to B), so it runs on a second stream into the other half of
     // a two-frame scratch: A is bound by the fp64 pipe, B by the latency of its L2 round trips — side by side on an
     // SM they fill each other's gaps.  Events order A(f) -> B(f) and B(f) -> A(f+2) (same scratch half).
-    static const bool want_overlap = [] { const char *v = getenv("TSB_SPEC_OVERLAP"); return v && atoi(v) != 0; }();
-    const bool overlap = want_overlap && jb.n_frames > 1;
+    static const int want_slots = [] { const char *v = getenv("TSB_SPEC_OVERLAP"); const int w = v ? atoi(v) : 2; return w < 2 ? 1 : (w > 4 ? 4 : w); }();
+    const bool overlap = want_slots > 1 && jb.n_frames > 1;
     const size_t per_frame = (size_t)jb.channels * n;
-    const int slots = overlap ? 2 : 1;
+    const int slots = overlap ? want_slots : 1;
     if (pc.scratch_elems < per_frame * slots) {
         if (pc.scratch) cudaFree(pc.scratch);
         pc.scratch = nullptr;
@@ -586,8 +586,11 @@ static cudaError_t run_frames(SpecCache &pc, const SpectralJob &jb, cudaStream_t
         pc.scratch_elems = per_frame * slots;
     }
     if (overlap && !pc.aux) {
-        if ((e = cudaStreamCreateWithFlags(&pc.aux, cudaStreamNonBlocking)) != cudaSuccess) return e;
-        cudaEvent_t *evs[5] = {&pc.ev_start, &pc.ev_a[0], &pc.ev_a[1], &pc.ev_b[0], &pc.ev_b[1]};
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        const char *pv = getenv("TSB_SPEC_PRIO");
+        if ((e = cudaStreamCreateWithPriority(&pc.aux, cudaStreamNonBlocking, (pv && atoi(pv)) ? prio_hi : prio_lo)) != cudaSuccess) return e;
+        cudaEvent_t *evs[9] = {&pc.ev_start, &pc.ev_a[0], &pc.ev_a[1], &pc.ev_a[2], &pc.ev_a[3], &pc.ev_b[0], &pc.ev_b[1], &pc.ev_b[2], &pc.ev_b[3]};
         for (cudaEvent_t *ev : evs)
             if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return e;
     }
@@ -665,8 +668,9 @@ static cudaError_t run_frames(SpecCache &pc, const SpectralJob &jb, cudaStream_t
     }
     const cudaStream_t sa = overlap ? pc.aux : st;
     for (long long f = 0; f < jb.n_frames; f++) {
-        cd *scr = pc.scratch + (overlap ? (size_t)(f & 1) * per_frame : 0);
-        if (overlap && f >= 2 && (e = cudaStreamWaitEvent(sa, pc.ev_b[f & 1], 0)) != cudaSuccess) return e;
+        const int slot = (int)(f % slots);
+        cd *scr = pc.scratch + (size_t)slot * per_frame;
+        if (overlap && f >= slots && (e = cudaStreamWaitEvent(sa, pc.ev_b[slot], 0)) != cudaSuccess) return e;
         if (jb.generator == SPEC_GEN_HASH) {
             GenHash g{(uint32_t)(jb.first_frame + f)};
             kA_hash<<<gridA, FA::NT, smA, sa>>>(g, scr, tw1, wa, wb, jb.channels);
@@ -681,14 +685,14 @@ static cudaError_t run_frames(SpecCache &pc, const SpectralJob &jb, cudaStream_t
             kA_buf<<<gridA, FA::NT, smA, sa>>>(g, scr, tw1, wa, wb, jb.channels);
         }
         if (overlap) {
-            if ((e = cudaEventRecord(pc.ev_a[f & 1], sa)) != cudaSuccess) return e;
-            if ((e = cudaStreamWaitEvent(st, pc.ev_a[f & 1], 0)) != cudaSuccess) return e;
+            if ((e = cudaEventRecord(pc.ev_a[slot], sa)) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(st, pc.ev_a[slot], 0)) != cudaSuccess) return e;
         }
         const long long pos0 = jb.out_off0 + f * jb.hop;
         const int aligned = ((pos0 | jb.out_stride) & 1) == 0 && (reinterpret_cast<uintptr_t>(jb.out) & 15) == 0;
         kB<<<gridB, FB::NT, smB, st>>>(scr, tw2, jb.channels, jb.out, jb.out_stride, jb.out_len, pos0, pc.edge[f & 1],
                                         pc.edge[(f + 1) & 1], aligned);
-        if (overlap && (e = cudaEventRecord(pc.ev_b[f & 1], st)) != cudaSuccess) return e;
+        if (overlap && (e = cudaEventRecord(pc.ev_b[slot], st)) != cudaSuccess) return e;
         *launches += 2;
     }
     if (xblock) cudaFreeAsync(xblock, st);
