@@ -173,11 +173,17 @@ struct GenExpr {
 
 // One CTA runs C sub-transforms of M = 2^LM points side by side, T threads each (one radix-8 butterfly per thread and
 // pass): C * T = 256 threads and 64 KB of tiles, fewer when the other dimension (2^LO sub-transforms in all) is smaller.
-template <int LM, int LO>
+#ifndef TSB_SPEC_CAP_A
+#define TSB_SPEC_CAP_A 2048  // points per tile of kernel A (columns x n1)
+#endif
+#ifndef TSB_SPEC_CAP_B
+#define TSB_SPEC_CAP_B 2048  // ... of kernel B (rows x n2)
+#endif
+template <int LM, int LO, int CAP = 2048>
 struct SubFft {
     static constexpr int M = 1 << LM;
     static constexpr int T = M / 8 < 1 ? 1 : M / 8;
-    static constexpr int CMAX = (2048 / M) < 1 ? 1 : (2048 / M);
+    static constexpr int CMAX = (CAP / M) < 2 ? 2 : (CAP / M);
     static constexpr int C = CMAX < (1 << LO) ? CMAX : (1 << LO);
     static constexpr int NT = C * T;
 };
@@ -213,6 +219,15 @@ __device__ __forceinline__ cd unit_w(long long q, double inv_n) {
 #ifndef TSB_SPEC_UO
 #define TSB_SPEC_UO 1  // ... of its output loop
 #endif
+// resident CTAs per SM kernel A is compiled for (register budget): 3 of 256 threads, 6 of 128
+#ifdef TSB_SPEC_OCC_A
+constexpr int spec_occ_a(int) { return TSB_SPEC_OCC_A; }
+#else
+constexpr int spec_occ_a(int nt) { return nt >= 256 ? 3 : (nt >= 128 ? 6 : 8); }
+#endif
+#ifndef TSB_SPEC_OCC_B
+#define TSB_SPEC_OCC_B 2
+#endif
 // ---- kernel A: one CTA = C/2 columns k2 of one channel together with their mirror columns n2 - k2 ----
 // G[k] and G[n-k] are made of the same two spectrum values: with a = X[k], b = X[n-k], sm = a + conj(b),
 // wd = W^k (a - conj(b)) (and W^(n-k) = -conj(W^k)):   G[k] = sm + i wd,   G[n-k] = conj(sm) + i conj(wd).
@@ -222,9 +237,9 @@ __device__ __forceinline__ cd unit_w(long long q, double inv_n) {
 // column 0 would otherwise leave half empty.  Tile slot 2p holds the low column of pair p, slot 2p+1 its mirror.
 // wa[k1] = e^{-i pi k1 / n1} (n1 entries), wb[k2] = e^{-i pi k2 / n} (n2 entries): W^k = wa[k1] * wb[k2] for k = n2*k1 + k2
 template <int L1, int L2, class Gen>
-__global__ void __launch_bounds__(SubFft<L1, L2>::NT, SubFft<L1, L2>::NT >= 256 ? 3 : 4)
+__global__ void __launch_bounds__(SubFft<L1, L2, TSB_SPEC_CAP_A>::NT, spec_occ_a(SubFft<L1, L2, TSB_SPEC_CAP_A>::NT))
 spectral_cols_kernel(Gen gen, cd *scratch, const cd *tw1, const cd *wa, const cd *wb, int channels) {
-    using F = SubFft<L1, L2>;
+    using F = SubFft<L1, L2, TSB_SPEC_CAP_A>;
     constexpr int n1 = 1 << L1, n2 = 1 << L2, C = F::C, NT = F::NT, CP = C / 2;
     constexpr long long n = (long long)n1 * n2;
     static_assert(C >= 2 && C % 2 == 0 && n1 >= 2 && n2 >= 4, "column pairs need an even tile and n2 >= 4");
@@ -246,6 +261,21 @@ spectral_cols_kernel(Gen gen, cd *scratch, const cd *tw1, const cd *wa, const cd
         const int col_lo = g * CP + p;
         const bool self = col_lo == 0;  // the pair slot of the two self-mirrored columns, 0 and n2/2
         const cd wk_lo = TSB_LDG(&wb[col_lo]);
+        if (g != 0) {
+            // no self-mirrored column in this group (every group but the first): bin ka of column col_lo pairs with bin
+            // n - ka = (n1 - 1 - k1, n2 - col_lo) of the mirror column — straight-line code in 32-bit indices
+#pragma unroll UG
+            for (int it = 0; it < (n1 + STEPG - 1) / STEPG; it++) {
+                const int k1 = rg + it * STEPG;
+                if (n1 % STEPG != 0 && k1 >= n1) break;
+                const int ka = n2 * k1 + col_lo;
+                const cd a = gen(ch, ka), bb = conj(gen(ch, (int)n - ka));
+                const cd sm = a + bb, d = a - bb;
+                const cd wd = cmul(cmul(TSB_LDG(&wa[k1]), wk_lo), d);
+                bufA[(2 * p) * SP + Swz<double>::f(k1)] = mk<double>(sm.x - wd.y, sm.y + wd.x);
+                bufA[(2 * p + 1) * SP + Swz<double>::f(n1 - 1 - k1)] = mk<double>(sm.x + wd.y, wd.x - sm.y);
+            }
+        } else {
 #pragma unroll UG
         for (int it = 0; it < (n1 + STEPG - 1) / STEPG; it++) {
             const int k1 = rg + it * STEPG;
@@ -274,6 +304,7 @@ spectral_cols_kernel(Gen gen, cd *scratch, const cd *tw1, const cd *wa, const cd
                 const int slot_b = self ? slot_a : 2 * p + 1, k1b = (int)(kb >> L2);
                 bufA[slot_b * SP + Swz<double>::f(k1b)] = mk<double>(sm.x + wd.y, wd.x - sm.y);  // conj(sm) + i*conj(wd)
             }
+        }
         }
         __syncthreads();
         const int gi = threadIdx.x / F::T, lt = threadIdx.x % F::T;
@@ -330,10 +361,10 @@ __device__ __forceinline__ void bar_wait(unsigned long long *bar, unsigned phase
         : "memory");
 }
 template <int L1, int L2>
-__global__ void __launch_bounds__(SubFft<L2, L1>::NT, 2)
+__global__ void __launch_bounds__(SubFft<L2, L1, TSB_SPEC_CAP_B>::NT, TSB_SPEC_OCC_B)
 spectral_rows_kernel(const cd *scratch, const cd *tw2, int channels, double *out, long long out_stride, long long out_len,
                      long long pos0, const double *edge_in, double *edge_out, int pairs_aligned) {
-    using F = SubFft<L2, L1>;
+    using F = SubFft<L2, L1, TSB_SPEC_CAP_B>;
     constexpr int n1 = 1 << L1, n2 = 1 << L2, C = F::C, NT = F::NT;
     constexpr long long n = (long long)n1 * n2;
     constexpr int SP = n2 + 1;  // padded stride of a sub-transform inside a work tile (see kernel A)
@@ -606,8 +637,8 @@ static cudaError_t run_frames(SpecCache &pc, const SpectralJob &jb, cudaStream_t
     if (jb.state_edge && jb.load_state) e = cudaMemcpyAsync(pc.edge[0], jb.state_edge, (size_t)jb.channels * 16, cudaMemcpyDeviceToDevice, st);
     else e = cudaMemsetAsync(pc.edge[0], 0, (size_t)jb.channels * 16, st);
     if (e != cudaSuccess) return e;
-    using FA = SubFft<L1, L2>;
-    using FB = SubFft<L2, L1>;
+    using FA = SubFft<L1, L2, TSB_SPEC_CAP_A>;
+    using FB = SubFft<L2, L1, TSB_SPEC_CAP_B>;
     constexpr int n1 = 1 << L1, n2 = 1 << L2;
     constexpr int CA = FA::C, CB = FB::C;
     const size_t smA = (size_t)2 * FA::C * (n1 + 1) * sizeof(cd);
