@@ -179,14 +179,79 @@ struct GenExpr {
 #ifndef TSB_SPEC_CAP_B
 #define TSB_SPEC_CAP_B 2048  // ... of kernel B (rows x n2)
 #endif
+#ifndef TSB_SPEC_R16
+#define TSB_SPEC_R16 1  // 256-point sub-transforms as two radix-16 passes (16 threads each) instead of 8 x 8 x 4
+#endif
 template <int LM, int LO, int CAP = 2048>
 struct SubFft {
     static constexpr int M = 1 << LM;
-    static constexpr int T = M / 8 < 1 ? 1 : M / 8;
+    // 256 = 16 x 16: two passes, i.e. one shared-memory round trip less than 8 x 8 x 4 (both spectral kernels are bound
+    // by the L1/shared-memory data pipe: 16-byte points cost four wavefronts per warp access), and the 16 threads of a
+    // sub-transform hold all of its points in registers between reading and writing a pass, so one buffer is enough
+    static constexpr bool R16 = TSB_SPEC_R16 && LM == 8;
+    static constexpr int T = R16 ? 16 : (M / 8 < 1 ? 1 : M / 8);
     static constexpr int CMAX = (CAP / M) < 2 ? 2 : (CAP / M);
     static constexpr int C = CMAX < (1 << LO) ? CMAX : (1 << LO);
     static constexpr int NT = C * T;
+    static constexpr int BUFS = R16 ? 1 : 2;  // work tiles of C * (M + 1) points
+    // position of point i inside a sub-transform's tile row
+    static TSB_HD constexpr int sw(int i) { return R16 ? (i ^ ((i >> 4) & 7)) : Swz<double>::f(i); }
 };
+// 16-point forward DFT, natural order in; output X[b + 4c] is left in v[4b + c]
+__device__ __forceinline__ void dft16_t(cd *v) {
+    const double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173, h = 0.70710678118654752440;
+#pragma unroll
+    for (int a = 0; a < 4; a++) dft4(v[a], v[a + 4], v[a + 8], v[a + 12]);
+    // v[a + 4b] *= W16^(a b), W16 = e^{-i pi/8}
+    auto rot = [](cd x, double c, double s) { return mk<double>(x.x * c + x.y * s, x.y * c - x.x * s); };  // x * (c - i s)
+    v[5] = rot(v[5], c1, s1);                                             // W^1
+    v[9] = mk<double>((v[9].x + v[9].y) * h, (v[9].y - v[9].x) * h);      // W^2
+    v[13] = rot(v[13], s1, c1);                                           // W^3
+    v[6] = mk<double>((v[6].x + v[6].y) * h, (v[6].y - v[6].x) * h);      // W^2
+    v[10] = mul_mi(v[10]);                                                // W^4 = -i
+    v[14] = mk<double>((v[14].y - v[14].x) * h, -(v[14].x + v[14].y) * h);  // W^6
+    v[7] = rot(v[7], s1, c1);                                             // W^3
+    v[11] = mk<double>((v[11].y - v[11].x) * h, -(v[11].x + v[11].y) * h);  // W^6
+    v[15] = rot(v[15], -c1, -s1);                                         // W^9 = -W^1
+#pragma unroll
+    for (int b = 0; b < 4; b++) dft4(v[4 * b], v[4 * b + 1], v[4 * b + 2], v[4 * b + 3]);
+}
+// One of the two radix-16 passes of a 256-point forward transform, thread j of 16.  PASS 0: y[16 j + t'] = DFT16_t(x[j + 16 t]);
+// PASS 1: X[j + 16 t'] = DFT16_t(W256^(j t) y[j + 16 t]).  `w` = W256^j (pass 1): its powers are formed by products, at
+// most four deep.  The caller separates the reads of a pass from its writes when both use the same buffer
+// (rd(i) -> value, then sync(), then wr(i, value)).
+template <int PASS, class Rd, class Sync, class Wr>
+__device__ __forceinline__ void r16_pass(int j, cd w, Rd rd, Sync sync, Wr wr) {
+    cd v[16];
+#pragma unroll
+    for (int t = 0; t < 16; t++) v[t] = rd(j + 16 * t);
+    sync();
+    if (PASS == 1) {
+        const cd p2 = cmul(w, w), p4 = cmul(p2, p2), p8 = cmul(p4, p4), p3 = cmul(p2, w);
+        v[1] = cmul(v[1], w);
+        v[2] = cmul(v[2], p2);
+        v[3] = cmul(v[3], p3);
+        v[4] = cmul(v[4], p4);
+        v[5] = cmul(v[5], cmul(p4, w));
+        v[6] = cmul(v[6], cmul(p4, p2));
+        const cd p7 = cmul(p4, p3);
+        v[7] = cmul(v[7], p7);
+        v[8] = cmul(v[8], p8);
+        v[9] = cmul(v[9], cmul(p8, w));
+        v[10] = cmul(v[10], cmul(p8, p2));
+        v[11] = cmul(v[11], cmul(p8, p3));
+        v[12] = cmul(v[12], cmul(p8, p4));
+        v[13] = cmul(v[13], cmul(p8, cmul(p4, w)));
+        v[14] = cmul(v[14], cmul(p8, cmul(p4, p2)));
+        v[15] = cmul(v[15], cmul(p8, p7));
+    }
+    dft16_t(v);
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+        const int tp = (r >> 2) + 4 * (r & 3);  // v[4b + c] holds output b + 4c
+        wr(PASS == 0 ? 16 * j + tp : j + 16 * tp, v[r]);
+    }
+}
 // LIN: the first pass reads its input unswizzled (a tile just copied in from global memory)
 template <int LOG2M, int T, int P, int END, bool LIN = false>
 struct SpecPasses {
@@ -217,16 +282,19 @@ __device__ __forceinline__ cd unit_w(long long q, double inv_n) {
 #define TSB_SPEC_UG 2  // unroll factor of kernel A's generation loop
 #endif
 #ifndef TSB_SPEC_UO
-#define TSB_SPEC_UO 1  // ... of its output loop
+#define TSB_SPEC_UO 2  // ... of its output loop (2: two shared-memory reads in flight per thread; 54.5 us per cfg5 frame instead of 55.8)
 #endif
-// resident CTAs per SM kernel A is compiled for (register budget): 3 of 256 threads, 6 of 128
+// resident CTAs per SM the kernels are compiled for (register budget): A 3 of 256 threads (4 of the 128 threads of the
+// radix-16 variant: 128 registers for the 16 points a thread holds); B 2 (3 of 128 threads with radix 16)
 #ifdef TSB_SPEC_OCC_A
-constexpr int spec_occ_a(int) { return TSB_SPEC_OCC_A; }
+constexpr int spec_occ_a(int, bool) { return TSB_SPEC_OCC_A; }
 #else
-constexpr int spec_occ_a(int nt) { return nt >= 256 ? 3 : (nt >= 128 ? 6 : 8); }
+constexpr int spec_occ_a(int nt, bool r16) { return r16 ? 4 : (nt >= 256 ? 3 : (nt >= 128 ? 6 : 8)); }
 #endif
-#ifndef TSB_SPEC_OCC_B
-#define TSB_SPEC_OCC_B 2
+#ifdef TSB_SPEC_OCC_B
+constexpr int spec_occ_b(bool) { return TSB_SPEC_OCC_B; }
+#else
+constexpr int spec_occ_b(bool r16) { return r16 ? 3 : 2; }
 #endif
 // ---- kernel A: one CTA = C/2 columns k2 of one channel together with their mirror columns n2 - k2 ----
 // G[k] and G[n-k] are made of the same two spectrum values: with a = X[k], b = X[n-k], sm = a + conj(b),
@@ -237,7 +305,7 @@ constexpr int spec_occ_a(int nt) { return nt >= 256 ? 3 : (nt >= 128 ? 6 : 8); }
 // column 0 would otherwise leave half empty.  Tile slot 2p holds the low column of pair p, slot 2p+1 its mirror.
 // wa[k1] = e^{-i pi k1 / n1} (n1 entries), wb[k2] = e^{-i pi k2 / n} (n2 entries): W^k = wa[k1] * wb[k2] for k = n2*k1 + k2
 template <int L1, int L2, class Gen>
-__global__ void __launch_bounds__(SubFft<L1, L2, TSB_SPEC_CAP_A>::NT, spec_occ_a(SubFft<L1, L2, TSB_SPEC_CAP_A>::NT))
+__global__ void __launch_bounds__(SubFft<L1, L2, TSB_SPEC_CAP_A>::NT, spec_occ_a(SubFft<L1, L2, TSB_SPEC_CAP_A>::NT, SubFft<L1, L2, TSB_SPEC_CAP_A>::R16))
 spectral_cols_kernel(Gen gen, cd *scratch, const cd *tw1, const cd *wa, const cd *wb, int channels) {
     using F = SubFft<L1, L2, TSB_SPEC_CAP_A>;
     constexpr int n1 = 1 << L1, n2 = 1 << L2, C = F::C, NT = F::NT, CP = C / 2;
@@ -247,7 +315,7 @@ spectral_cols_kernel(Gen gen, cd *scratch, const cd *tw1, const cd *wa, const cd
     // together (consecutive threads = consecutive columns) fall into different banks
     constexpr int SP = n1 + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cd *bufA = reinterpret_cast<cd *>(smem_raw), *bufB = bufA + C * SP;
+    cd *bufA = reinterpret_cast<cd *>(smem_raw), *bufB = bufA + C * SP;  // (bufB: only with two work tiles, F::BUFS)
     const int groups = n2 / C;
     // generation: a thread keeps one column pair (p) and walks k1 in steps of NT / CP
     constexpr int STEPG = NT / CP;
@@ -272,8 +340,8 @@ spectral_cols_kernel(Gen gen, cd *scratch, const cd *tw1, const cd *wa, const cd
                 const cd a = gen(ch, ka), bb = conj(gen(ch, (int)n - ka));
                 const cd sm = a + bb, d = a - bb;
                 const cd wd = cmul(cmul(TSB_LDG(&wa[k1]), wk_lo), d);
-                bufA[(2 * p) * SP + Swz<double>::f(k1)] = mk<double>(sm.x - wd.y, sm.y + wd.x);
-                bufA[(2 * p + 1) * SP + Swz<double>::f(n1 - 1 - k1)] = mk<double>(sm.x + wd.y, wd.x - sm.y);
+                bufA[(2 * p) * SP + F::sw(k1)] = mk<double>(sm.x - wd.y, sm.y + wd.x);
+                bufA[(2 * p + 1) * SP + F::sw(n1 - 1 - k1)] = mk<double>(sm.x + wd.y, wd.x - sm.y);
             }
         } else {
 #pragma unroll UG
@@ -291,7 +359,7 @@ spectral_cols_kernel(Gen gen, cd *scratch, const cd *tw1, const cd *wa, const cd
             cd wk = self ? TSB_LDG(&wb[col_a]) : wk_lo;
             const bool first = ka == 0;  // bin 0 is a carried one (kernel B adds its contribution): G[0] = 0, and this
             if (first) {                 // iteration takes the bin that mirrors into itself instead, n/2
-                bufA[slot_a * SP + Swz<double>::f(0)] = mk<double>(0.0, 0.0);
+                bufA[slot_a * SP + F::sw(0)] = mk<double>(0.0, 0.0);
                 k1a = n1 / 2;
                 ka = n / 2;
             }
@@ -299,16 +367,31 @@ spectral_cols_kernel(Gen gen, cd *scratch, const cd *tw1, const cd *wa, const cd
             const cd a = gen(ch, (int)ka), bb = conj(first ? a : gen(ch, (int)kb));
             const cd sm = a + bb, d = a - bb;
             const cd wd = cmul(cmul(TSB_LDG(&wa[k1a]), wk), d);              // W^k * d
-            bufA[slot_a * SP + Swz<double>::f(k1a)] = mk<double>(sm.x - wd.y, sm.y + wd.x);  // sm + i*W^k*d
+            bufA[slot_a * SP + F::sw(k1a)] = mk<double>(sm.x - wd.y, sm.y + wd.x);  // sm + i*W^k*d
             if (!first) {
                 const int slot_b = self ? slot_a : 2 * p + 1, k1b = (int)(kb >> L2);
-                bufA[slot_b * SP + Swz<double>::f(k1b)] = mk<double>(sm.x + wd.y, wd.x - sm.y);  // conj(sm) + i*conj(wd)
+                bufA[slot_b * SP + F::sw(k1b)] = mk<double>(sm.x + wd.y, wd.x - sm.y);  // conj(sm) + i*conj(wd)
             }
         }
         }
         __syncthreads();
         const int gi = threadIdx.x / F::T, lt = threadIdx.x % F::T;
-        cd *res = SpecPasses<L1, F::T, 0, RadixPlan<L1>::passes>::run(lt, bufA + gi * SP, bufB + gi * SP, bufA + gi * SP, tw1) - gi * SP;
+        cd *res;
+        if constexpr (F::R16) {
+            // two radix-16 passes in the one tile: the 16 threads of a column (half a warp) hold all 256 points
+            // between the reads and the writes of a pass
+            cd *col = bufA + gi * SP;
+            const cd w = TSB_LDG(&tw1[TwLayout<8>::offset(2) + lt]);  // W256^lt
+            auto rd = [&](int i) { return col[F::sw(i)]; };
+            auto wr = [&](int i, cd v) { col[F::sw(i)] = v; };
+            auto sync = [] { __syncwarp(); };
+            r16_pass<0>(lt, w, rd, sync, wr);
+            __syncwarp();
+            r16_pass<1>(lt, w, rd, sync, wr);
+            res = bufA;
+        } else {
+            res = SpecPasses<L1, F::T, 0, RadixPlan<L1>::passes>::run(lt, bufA + gi * SP, bufB + gi * SP, bufA + gi * SP, tw1) - gi * SP;
+        }
         __syncthreads();
         {   // A[k2][j1] * e^{-2 pi i k2 j1 / n} -> scratch[ch][j1][k2]: the factor is base^j1 with base = wb[k2]^2; the
             // thread starts at base^r0 (square-and-multiply) and advances by base^STEP (at most 8 steps: no drift)
@@ -328,7 +411,7 @@ spectral_cols_kernel(Gen gen, cd *scratch, const cd *tw1, const cd *wa, const cd
             for (int it = 0; it < (n1 + STEP - 1) / STEP; it++) {
                 const int j1 = r0 + it * STEP;
                 if (n1 % STEP != 0 && j1 >= n1) break;
-                dst[(long long)j1 * n2] = cmul(res[c * SP + Swz<double>::f(j1)], w);
+                dst[(long long)j1 * n2] = cmul(res[c * SP + F::sw(j1)], w);
                 w = cmul(w, out_step);
             }
         }
@@ -361,7 +444,7 @@ __device__ __forceinline__ void bar_wait(unsigned long long *bar, unsigned phase
         : "memory");
 }
 template <int L1, int L2>
-__global__ void __launch_bounds__(SubFft<L2, L1, TSB_SPEC_CAP_B>::NT, TSB_SPEC_OCC_B)
+__global__ void __launch_bounds__(SubFft<L2, L1, TSB_SPEC_CAP_B>::NT, spec_occ_b(SubFft<L2, L1, TSB_SPEC_CAP_B>::R16))
 spectral_rows_kernel(const cd *scratch, const cd *tw2, int channels, double *out, long long out_stride, long long out_len,
                      long long pos0, const double *edge_in, double *edge_out, int pairs_aligned) {
     using F = SubFft<L2, L1, TSB_SPEC_CAP_B>;
@@ -408,14 +491,26 @@ spectral_rows_kernel(const cd *scratch, const cd *tw2, int channels, double *out
         bar_wait(&bar, phase);  // the tile is in `stage`
         phase ^= 1;
         const int gi = threadIdx.x / F::T, lt = threadIdx.x % F::T;
-        constexpr int PASSES = RadixPlan<L2>::passes;
-        // first pass: stage -> bufA; then the staging buffer is free for the next tile's copy
-        stockham_pass_io<double, L2, F::T, 0>(
-            lt, tw2, [&](int a, int cc) { return stage[gi * n2 + a + cc]; },
-            [&](int a, int cc, cd v) { bufA[gi * SP + (Swz<double>::f(a) ^ Swz<double>::f(cc))] = v; });
-        __syncthreads();
-        if (threadIdx.x == 0 && b + gridDim.x < tiles) bulk_load(stage, scratch + (b + gridDim.x) * C * n2, TILE_BYTES, &bar);
-        cd *res = SpecPasses<L2, F::T, 1, PASSES>::run(lt, bufA + gi * SP, bufB + gi * SP, bufA + gi * SP, tw2) - gi * SP;
+        cd *res;
+        if constexpr (F::R16) {
+            cd *rowb = bufA + gi * SP;
+            const cd w = TSB_LDG(&tw2[TwLayout<8>::offset(2) + lt]);  // W256^lt
+            // first pass: stage (as it lies in the scratch) -> the work tile; then the staging buffer is free
+            r16_pass<0>(lt, w, [&](int i) { return stage[gi * n2 + i]; }, [] {}, [&](int i, cd v) { rowb[F::sw(i)] = v; });
+            __syncthreads();
+            if (threadIdx.x == 0 && b + gridDim.x < tiles) bulk_load(stage, scratch + (b + gridDim.x) * C * n2, TILE_BYTES, &bar);
+            r16_pass<1>(lt, w, [&](int i) { return rowb[F::sw(i)]; }, [] { __syncwarp(); }, [&](int i, cd v) { rowb[F::sw(i)] = v; });
+            res = bufA;
+        } else {
+            constexpr int PASSES = RadixPlan<L2>::passes;
+            // first pass: stage -> bufA; then the staging buffer is free for the next tile's copy
+            stockham_pass_io<double, L2, F::T, 0>(
+                lt, tw2, [&](int a, int cc) { return stage[gi * n2 + a + cc]; },
+                [&](int a, int cc, cd v) { bufA[gi * SP + (Swz<double>::f(a) ^ Swz<double>::f(cc))] = v; });
+            __syncthreads();
+            if (threadIdx.x == 0 && b + gridDim.x < tiles) bulk_load(stage, scratch + (b + gridDim.x) * C * n2, TILE_BYTES, &bar);
+            res = SpecPasses<L2, F::T, 1, PASSES>::run(lt, bufA + gi * SP, bufB + gi * SP, bufA + gi * SP, tw2) - gi * SP;
+        }
         __syncthreads();
         // the carried bins 0 and n of the spectrum: X0 + Xn*(-1)^m, i.e. (d + q) on even and (d - q) on odd samples
         const double d = edge_in ? edge_in[2 * ch] : 0.0, q = edge_in ? edge_in[2 * ch + 1] : 0.0;
@@ -424,7 +519,7 @@ spectral_rows_kernel(const cd *scratch, const cd *tw2, int channels, double *out
         for (int u = 0; u < NOUT; u++) {
             const int j2 = r0 + u * STEP;
             if (j2 >= n2 / 2) continue;
-            const cd v = res[c * SP + Swz<double>::f(j2)];
+            const cd v = res[c * SP + F::sw(j2)];
             const long long m = 2 * ((long long)(j1_0 + c) + (long long)n1 * j2);
             const double y0 = fma(v.x, inv_sqrt, e_even), y1 = fma(v.y, inv_sqrt, e_odd);
             // the hack's window, `1.0 - abs(1.0 - i/(n/2.0))`, same expression
@@ -439,8 +534,8 @@ spectral_rows_kernel(const cd *scratch, const cd *tw2, int channels, double *out
         }
         if (edge_out && j1_0 == 0 && threadIdx.x == 0) {
             // what the in-place frft leaves in bins 0 and n for the next frame: y[0] and y[n] (j = 0 and j = n/2)
-            edge_out[2 * ch] = fma(res[Swz<double>::f(0)].x, inv_sqrt, e_even);
-            edge_out[2 * ch + 1] = fma(res[Swz<double>::f(n2 / 2)].x, inv_sqrt, e_even);
+            edge_out[2 * ch] = fma(res[F::sw(0)].x, inv_sqrt, e_even);
+            edge_out[2 * ch + 1] = fma(res[F::sw(n2 / 2)].x, inv_sqrt, e_even);
         }
         __syncthreads();
     }
@@ -529,6 +624,8 @@ struct SpecCache {
     int scratch_slots = 0;
     // frame pipeline: kernel A of frame f+1 runs on `aux` beside kernel B of frame f (see run_frames)
     cudaStream_t aux = nullptr;
+    cudaStream_t bhi = nullptr;  // TSB_SPEC_PRIO=2: kernel B on a high-priority stream of its own (joined to the caller's at the end)
+    cudaEvent_t ev_end = nullptr;
     cudaEvent_t ev_start = nullptr, ev_a[4] = {nullptr, nullptr, nullptr, nullptr}, ev_b[4] = {nullptr, nullptr, nullptr, nullptr};
     double *edge[2] = {nullptr, nullptr};
     size_t edge_ch = 0;
@@ -620,8 +717,10 @@ static cudaError_t run_frames(SpecCache &pc, const SpectralJob &jb, cudaStream_t
         int prio_lo = 0, prio_hi = 0;
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
         const char *pv = getenv("TSB_SPEC_PRIO");
-        if ((e = cudaStreamCreateWithPriority(&pc.aux, cudaStreamNonBlocking, (pv && atoi(pv)) ? prio_hi : prio_lo)) != cudaSuccess) return e;
-        cudaEvent_t *evs[9] = {&pc.ev_start, &pc.ev_a[0], &pc.ev_a[1], &pc.ev_a[2], &pc.ev_a[3], &pc.ev_b[0], &pc.ev_b[1], &pc.ev_b[2], &pc.ev_b[3]};
+        const int pmode = pv ? atoi(pv) : 0;
+        if ((e = cudaStreamCreateWithPriority(&pc.aux, cudaStreamNonBlocking, pmode == 1 ? prio_hi : prio_lo)) != cudaSuccess) return e;
+        if (pmode == 2 && (e = cudaStreamCreateWithPriority(&pc.bhi, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return e;
+        cudaEvent_t *evs[10] = {&pc.ev_start, &pc.ev_a[0], &pc.ev_a[1], &pc.ev_a[2], &pc.ev_a[3], &pc.ev_b[0], &pc.ev_b[1], &pc.ev_b[2], &pc.ev_b[3], &pc.ev_end};
         for (cudaEvent_t *ev : evs)
             if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return e;
     }
@@ -641,8 +740,8 @@ static cudaError_t run_frames(SpecCache &pc, const SpectralJob &jb, cudaStream_t
     using FB = SubFft<L2, L1, TSB_SPEC_CAP_B>;
     constexpr int n1 = 1 << L1, n2 = 1 << L2;
     constexpr int CA = FA::C, CB = FB::C;
-    const size_t smA = (size_t)2 * FA::C * (n1 + 1) * sizeof(cd);
-    const size_t smB = ((size_t)FB::C * n2 + (size_t)2 * FB::C * (n2 + 1)) * sizeof(cd);  // staging tile + two work tiles
+    const size_t smA = (size_t)FA::BUFS * FA::C * (n1 + 1) * sizeof(cd);
+    const size_t smB = ((size_t)FB::C * n2 + (size_t)FB::BUFS * FB::C * (n2 + 1)) * sizeof(cd);  // staging tile + work tiles
     auto kA_hash = spectral_cols_kernel<L1, L2, GenHash>;
     auto kA_buf = spectral_cols_kernel<L1, L2, GenBuffer>;
     auto kA_expr = spectral_cols_kernel<L1, L2, GenExpr>;
@@ -696,8 +795,10 @@ static cudaError_t run_frames(SpecCache &pc, const SpectralJob &jb, cudaStream_t
     if (overlap) {  // everything queued on `st` so far (tables, the caller's spectrum, earlier renders) precedes the first A
         if ((e = cudaEventRecord(pc.ev_start, st)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(pc.aux, pc.ev_start, 0)) != cudaSuccess) return e;
+        if (pc.bhi && (e = cudaStreamWaitEvent(pc.bhi, pc.ev_start, 0)) != cudaSuccess) return e;
     }
     const cudaStream_t sa = overlap ? pc.aux : st;
+    const cudaStream_t sb = overlap && pc.bhi ? pc.bhi : st;
     for (long long f = 0; f < jb.n_frames; f++) {
         const int slot = (int)(f % slots);
         cd *scr = pc.scratch + (size_t)slot * per_frame;
@@ -717,14 +818,18 @@ static cudaError_t run_frames(SpecCache &pc, const SpectralJob &jb, cudaStream_t
         }
         if (overlap) {
             if ((e = cudaEventRecord(pc.ev_a[slot], sa)) != cudaSuccess) return e;
-            if ((e = cudaStreamWaitEvent(st, pc.ev_a[slot], 0)) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(sb, pc.ev_a[slot], 0)) != cudaSuccess) return e;
         }
         const long long pos0 = jb.out_off0 + f * jb.hop;
         const int aligned = ((pos0 | jb.out_stride) & 1) == 0 && (reinterpret_cast<uintptr_t>(jb.out) & 15) == 0;
-        kB<<<gridB, FB::NT, smB, st>>>(scr, tw2, jb.channels, jb.out, jb.out_stride, jb.out_len, pos0, pc.edge[f & 1],
+        kB<<<gridB, FB::NT, smB, sb>>>(scr, tw2, jb.channels, jb.out, jb.out_stride, jb.out_len, pos0, pc.edge[f & 1],
                                         pc.edge[(f + 1) & 1], aligned);
-        if (overlap && (e = cudaEventRecord(pc.ev_b[slot], st)) != cudaSuccess) return e;
+        if (overlap && (e = cudaEventRecord(pc.ev_b[slot], sb)) != cudaSuccess) return e;
         *launches += 2;
+    }
+    if (sb != st) {  // the caller's stream continues after the last kernel B
+        if ((e = cudaEventRecord(pc.ev_end, sb)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(st, pc.ev_end, 0)) != cudaSuccess) return e;
     }
     if (xblock) cudaFreeAsync(xblock, st);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
