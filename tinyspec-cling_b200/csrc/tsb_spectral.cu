@@ -39,6 +39,7 @@ using cd = cpx<double>;
 // ---- generators: the spectrum value of bin i (0 < i < n) of channel c ----
 // The seeded integer formula of oracle/ref/taps/bytebeat_tap.cpp / examples/bytebeat.cpp.
 struct GenHash {
+    static constexpr bool in_registers = true;  // no memory behind it: kernel A may generate straight into the first pass
     uint32_t frame;
     __device__ __forceinline__ cd operator()(int c, int i) const {
         uint32_t h = frame * 2654435761u ^ ((uint32_t)c * 40503u + (uint32_t)i * 2246822519u);
@@ -66,6 +67,7 @@ struct GenHash {
 };
 // Spectrum values computed by the caller: device complex128 rows [channels][n] of this frame, bins 1..n-1 are read.
 struct GenBuffer {
+    static constexpr bool in_registers = false;  // column reads want neighbouring columns in neighbouring lanes
     const cd *spec;
     long long n;
     __device__ __forceinline__ cd operator()(int c, int i) const { return spec[(long long)c * n + i]; }
@@ -82,6 +84,7 @@ struct ExprCode {
     double dc[TSB_EXPR_MAX_CONST];
 };
 struct GenExpr {
+    static constexpr bool in_registers = true;
     ExprCode code;
     const int *itab;         // device [n_itab][n]
     const double *dtab;      // device [n_dtab][n]
@@ -220,12 +223,9 @@ __device__ __forceinline__ void dft16_t(cd *v) {
 // PASS 1: X[j + 16 t'] = DFT16_t(W256^(j t) y[j + 16 t]).  `w` = W256^j (pass 1): its powers are formed by products, at
 // most four deep.  The caller separates the reads of a pass from its writes when both use the same buffer
 // (rd(i) -> value, then sync(), then wr(i, value)).
-template <int PASS, class Rd, class Sync, class Wr>
-__device__ __forceinline__ void r16_pass(int j, cd w, Rd rd, Sync sync, Wr wr) {
-    cd v[16];
-#pragma unroll
-    for (int t = 0; t < 16; t++) v[t] = rd(j + 16 * t);
-    sync();
+// second half of a pass: twiddles (pass 1), the 16-point DFT, the stores.  HALF: only outputs X[0..127] are wanted
+template <int PASS, bool HALF = false, class Wr>
+__device__ __forceinline__ void r16_finish(int j, cd w, cd (&v)[16], Wr wr) {
     if (PASS == 1) {
         const cd p2 = cmul(w, w), p4 = cmul(p2, p2), p8 = cmul(p4, p4), p3 = cmul(p2, w);
         v[1] = cmul(v[1], w);
@@ -249,8 +249,20 @@ __device__ __forceinline__ void r16_pass(int j, cd w, Rd rd, Sync sync, Wr wr) {
 #pragma unroll
     for (int r = 0; r < 16; r++) {
         const int tp = (r >> 2) + 4 * (r & 3);  // v[4b + c] holds output b + 4c
+        if (HALF && (tp > 8 || (tp == 8 && j != 0))) continue;  // (PASS 1: X[j + 16 tp], tp >= 8, is the upper half; X[128] is kept)
         wr(PASS == 0 ? 16 * j + tp : j + 16 * tp, v[r]);
     }
+}
+template <int PASS, bool HALF = false, class Rd, class Sync, class Wr>
+__device__ __forceinline__ void r16_pass(int j, cd w, Rd rd, Sync sync, Wr wr) {
+    cd v[16];
+#pragma unroll
+    for (int t = 0; t < 16; t++) v[t] = rd(j + 16 * t);
+    sync();
+    r16_finish<PASS, HALF>(j, w, v, wr);
+}
+__device__ __forceinline__ cd shfl_xor_cd(cd v, int mask) {
+    return mk<double>(__shfl_xor_sync(0xffffffffu, v.x, mask), __shfl_xor_sync(0xffffffffu, v.y, mask));
 }
 // LIN: the first pass reads its input unswizzled (a tile just copied in from global memory)
 template <int LOG2M, int T, int P, int END, bool LIN = false>
@@ -328,6 +340,34 @@ spectral_cols_kernel(Gen gen, cd *scratch, const cd *tw1, const cd *wa, const cd
         const int ch = (int)(b / groups), g = (int)(b % groups);
         const int col_lo = g * CP + p;
         const bool self = col_lo == 0;  // the pair slot of the two self-mirrored columns, 0 and n2/2
+        const int gi = threadIdx.x / F::T, lt = threadIdx.x % F::T;
+        constexpr bool FUSE = F::R16 && Gen::in_registers;
+        cd *res;
+        if (FUSE && g != 0) {
+            // Generation straight into the first radix-16 pass.  Lane lt of the low column of a pair (lanes 0..15 of the
+            // warp) needs rows lt + 16 t of its column; the mirror of row k1 is row n1-1-k1 of the mirror column, whose
+            // lanes 16..31 run the other way round: lane L and lane 31 - L need exactly each other's mirrors.  Each
+            // generates the eight pairs anchored at rows lt + 16 t, t < 8, of its OWN column (G[k] = sm + i W^k d holds
+            // for any anchor k), keeps that element and hands the mirror element over by shuffle: it is the
+            // partner's row (15 - lt) + 16 (15 - t).  No shared-memory round trip between generator and transform.
+            if constexpr (FUSE) {
+                const int col_own = (gi & 1) ? n2 - (g * CP + (gi >> 1)) : g * CP + (gi >> 1);
+                const cd wk = TSB_LDG(&wb[col_own]);
+                cd v[16];
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    const int k1 = lt + 16 * t;
+                    const int k = n2 * k1 + col_own;
+                    const cd a = gen(ch, k), bb = conj(gen(ch, (int)n - k));
+                    const cd sm = a + bb, d = a - bb;
+                    const cd wd = cmul(cmul(TSB_LDG(&wa[k1]), wk), d);
+                    v[t] = mk<double>(sm.x - wd.y, sm.y + wd.x);
+                    v[15 - t] = shfl_xor_cd(mk<double>(sm.x + wd.y, wd.x - sm.y), 31);
+                }
+                cd *col = bufA + gi * SP;
+                r16_finish<0>(lt, wk, v, [&](int i, cd x) { col[F::sw(i)] = x; });
+            }
+        } else {
         const cd wk_lo = TSB_LDG(&wb[col_lo]);
         if (g != 0) {
             // no self-mirrored column in this group (every group but the first): bin ka of column col_lo pairs with bin
@@ -375,8 +415,7 @@ spectral_cols_kernel(Gen gen, cd *scratch, const cd *tw1, const cd *wa, const cd
         }
         }
         __syncthreads();
-        const int gi = threadIdx.x / F::T, lt = threadIdx.x % F::T;
-        cd *res;
+        }
         if constexpr (F::R16) {
             // two radix-16 passes in the one tile: the 16 threads of a column (half a warp) hold all 256 points
             // between the reads and the writes of a pass
@@ -385,7 +424,7 @@ spectral_cols_kernel(Gen gen, cd *scratch, const cd *tw1, const cd *wa, const cd
             auto rd = [&](int i) { return col[F::sw(i)]; };
             auto wr = [&](int i, cd v) { col[F::sw(i)] = v; };
             auto sync = [] { __syncwarp(); };
-            r16_pass<0>(lt, w, rd, sync, wr);
+            if (!(FUSE && g != 0)) r16_pass<0>(lt, w, rd, sync, wr);
             __syncwarp();
             r16_pass<1>(lt, w, rd, sync, wr);
             res = bufA;
@@ -469,8 +508,12 @@ spectral_rows_kernel(const cd *scratch, const cd *tw2, int channels, double *out
     __syncthreads();
     if (threadIdx.x == 0 && (long long)blockIdx.x < tiles) bulk_load(stage, scratch + (long long)blockIdx.x * C * n2, TILE_BYTES, &bar);
     unsigned phase = 0;
+    cd w16 = mk<double>(1.0, 0.0);  // W256^lt of the radix-16 passes
+    if constexpr (F::R16) w16 = TSB_LDG(&tw2[TwLayout<8>::offset(2) + threadIdx.x % F::T]);
     for (long long b = blockIdx.x; b < tiles; b += gridDim.x) {
         const int ch = (int)(b / groups), j1_0 = (int)(b % groups) * C;
+        // the carried bins 0 and n of the spectrum (requested here, used after the transform)
+        const double d = edge_in ? edge_in[2 * ch] : 0.0, q = edge_in ? edge_in[2 * ch + 1] : 0.0;
         // the output samples this thread will add to (v[j], j = j1 + n1*j2 < n/2 -> samples 2j, 2j+1): requested now,
         // they arrive while the rows are transformed
         double *row = out + (long long)ch * out_stride + pos0;
@@ -494,12 +537,11 @@ spectral_rows_kernel(const cd *scratch, const cd *tw2, int channels, double *out
         cd *res;
         if constexpr (F::R16) {
             cd *rowb = bufA + gi * SP;
-            const cd w = TSB_LDG(&tw2[TwLayout<8>::offset(2) + lt]);  // W256^lt
             // first pass: stage (as it lies in the scratch) -> the work tile; then the staging buffer is free
-            r16_pass<0>(lt, w, [&](int i) { return stage[gi * n2 + i]; }, [] {}, [&](int i, cd v) { rowb[F::sw(i)] = v; });
+            r16_pass<0>(lt, w16, [&](int i) { return stage[gi * n2 + i]; }, [] {}, [&](int i, cd v) { rowb[F::sw(i)] = v; });
             __syncthreads();
             if (threadIdx.x == 0 && b + gridDim.x < tiles) bulk_load(stage, scratch + (b + gridDim.x) * C * n2, TILE_BYTES, &bar);
-            r16_pass<1>(lt, w, [&](int i) { return rowb[F::sw(i)]; }, [] { __syncwarp(); }, [&](int i, cd v) { rowb[F::sw(i)] = v; });
+            r16_pass<1, true>(lt, w16, [&](int i) { return rowb[F::sw(i)]; }, [] { __syncwarp(); }, [&](int i, cd v) { rowb[F::sw(i)] = v; });
             res = bufA;
         } else {
             constexpr int PASSES = RadixPlan<L2>::passes;
@@ -512,8 +554,7 @@ spectral_rows_kernel(const cd *scratch, const cd *tw2, int channels, double *out
             res = SpecPasses<L2, F::T, 1, PASSES>::run(lt, bufA + gi * SP, bufB + gi * SP, bufA + gi * SP, tw2) - gi * SP;
         }
         __syncthreads();
-        // the carried bins 0 and n of the spectrum: X0 + Xn*(-1)^m, i.e. (d + q) on even and (d - q) on odd samples
-        const double d = edge_in ? edge_in[2 * ch] : 0.0, q = edge_in ? edge_in[2 * ch + 1] : 0.0;
+        // their contribution: X0 + Xn*(-1)^m, i.e. (d + q) on even and (d - q) on odd samples
         const double e_even = (d + q) * inv_sqrt, e_odd = (d - q) * inv_sqrt;
 #pragma unroll
         for (int u = 0; u < NOUT; u++) {
