@@ -25,9 +25,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_FRAME, HOP, CH, RATE, SHIFT = 1024, 256, 2, 48000.0, 2.0
-# One lane = one CTA of 128 threads; resident CTAs per SM: 5 (fp64 kernel: 96 regs, 28 KB smem) / 8 (fp32: 64 regs,
-# 18 KB).  148 SMs x that many CTAs = one full wave of lanes; 2 lanes per stereo stream; fp32 runs two waves.
-STREAMS = {"f64": 148 * 5 // 2, "f32": 148 * 8}
+# One lane = one CTA of 128 threads; resident CTAs per SM: 4 (fp64 kernel: 128 regs — the overlap tail lives in
+# registers — 37 KB smem) / 8 (fp32: 64 regs, 18 KB).  148 SMs x that many CTAs = one full wave of lanes; 2 lanes per
+# stereo stream; both precisions run two waves.
+STREAMS = {"f64": 148 * 4, "f32": 148 * 8}
 
 
 def peaks():

@@ -675,6 +675,17 @@ struct Chain {
 #define TSB_INV_INPLACE 1
 #endif
     static constexpr bool INV_INPLACE = TSB_INV_INPLACE && PIPE && sizeof(real) == 8;
+    // Register-resident overlap tail (fp64, N = 1024, constant hop N/4): the last inverse pass gives thread j the
+    // sample pairs m = j + T0*u, u = 0..7, of every frame, and a hop of N/4 moves an output position from pair m of
+    // one frame to pair m - 2*T0 of the next — the same thread, slot u - 2.  So the six pairs a frame leaves
+    // unfinished stay in that thread's registers instead of making a read-modify-write trip through the shared-memory
+    // ring every frame (160 of the kernel's ~1,480 data-pipe wavefronts per frame-channel, the busiest unit).  Same
+    // additions in the same order as the ring path: bit-identical.  Launches with any other hop use the ring.
+#ifndef TSB_RTAIL
+#define TSB_RTAIL 1
+#endif
+    static constexpr bool RT_OK = TSB_RTAIL && PIPE && sizeof(real) == 8 && LOG2N == 10;
+    static constexpr int RT_N = RT_OK ? 6 : 1;
     using C = cpx<real>;
     using Tables = ChainTables<real>;
     using SW = Swz<real>;
@@ -709,6 +720,7 @@ struct Chain {
         uint32_t used;
         uint32_t dpair[(S + 1) / 2];  // destination pair of slot i (16 bits each): k of the synthesis side
         uint32_t doubts;              // WRAP_FIX: doubt bits of the frame just analysed (bit 2 * slot + side)
+        OC tail[RT_N];                // RT_OK: the overlap tail of this thread's sample pairs (inverse half of the CTA)
     };
 
     // Forward pass p writes buf[p & 1] (pass 0 reads the ring), so the packed spectrum ends up in RB.
@@ -1304,12 +1316,30 @@ struct Chain {
         }
     }
 
+    // register tail <-> the shared-memory ring (start and end of a launch; `out_pos` = position of the next frame)
+    static TSB_HD void tail_load(int tid, Smem &sm, Regs &rg, long long out_pos) {
+        if (tid < T0) return;
+#pragma unroll
+        for (int u = 0; u < RT_N; u++) {
+            const long long n = out_pos + 2 * (tid - T0 + T0 * u);
+            rg.tail[u] = mk<otype>(sm.ola[(int)(n & (N - 1))], sm.ola[(int)((n + 1) & (N - 1))]);
+        }
+    }
+    static TSB_HD void tail_store(int tid, Smem &sm, const Regs &rg, long long out_pos) {
+        if (tid < T0) return;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const long long n = out_pos + 2 * (tid - T0 + T0 * u);
+            sm.ola[(int)(n & (N - 1))] = u < RT_N ? rg.tail[u < RT_N ? u : 0].x : (otype)0;
+            sm.ola[(int)((n + 1) & (N - 1))] = u < RT_N ? rg.tail[u < RT_N ? u : 0].y : (otype)0;
+        }
+    }
     // ------------------------------------------------------------------ inverse passes
     // The last pass hands its outputs F[m] straight to the synthesis window and the overlap-add:
     // x[2m] = Re F[m], x[2m+1] = -Im F[m]; out = x*ws; accumulate into the ring; the first `hop`
     // positions are complete (tinyspec.cpp:173-182) and leave the chip, the rest is the tail (194-200).
-    template <int P, int NT = T, bool EMIT = true>
-    static TSB_HD void inv_pass(int tid, int lane, Smem &sm, const Tables &tb, const ChainArgs &a, long long out_pos,
+    template <int P, int NT = T, bool EMIT = true, bool RT = false>
+    static TSB_HD void inv_pass(int tid, int lane, Smem &sm, Regs &rg, const Tables &tb, const ChainArgs &a, long long out_pos,
                                 int hop) {
         const C *src = inv_buffer(sm, P);
         auto in = [&](int x, int c) { return INV_INPLACE ? src[ISW::f(x) ^ ISW::f(c)] : ld_sw(src, x, c); };
@@ -1335,7 +1365,33 @@ struct Chain {
             // of the two code paths below produced it (chunked and whole renders are bit-identical).
             auto emit_val = [](otype tail, real v) -> otype { return (otype)add_rn((real)tail, v); };
             auto tail_val = [](otype tail, real v) -> otype { return OUT32 ? add_rn(tail, (otype)v) : (otype)add_rn((real)tail, v); };
-            if (((ob | hop | (lim == 0x7fffffff ? 0 : lim)) & 1) == 0 &&
+            if constexpr (RT) {
+                // the tail lives in registers (see RT_OK): pair u of this thread finishes for u < 2 and moves to slot
+                // u - 2 otherwise; slots 6 and 7 start from nothing
+                static_assert(!RT || (RadixPlan<LOG2M>::ns(PASSES - 1) == T0 && M / RadixPlan<LOG2M>::radix(PASSES - 1) == T0 && NT == T0),
+                              "register tail: one butterfly per thread in the last pass, outputs T0 apart");
+                const bool al = (reinterpret_cast<uintptr_t>(dstg) & (2 * sizeof(otype) - 1)) == 0;
+                const int emit_end = hop < lim ? hop : lim;
+                auto out = [&](int x, int c, C f) {
+                    const int u = c / T0;  // a constant once the pass is unrolled (c = u * Ns)
+                    const int m = x + c;
+                    C w = TSB_LDG(ws + m);
+                    const real vx = mul_rn(f.x, w.x), vy = -mul_rn(f.y, w.y);
+                    const OC t = u < RT_N ? rg.tail[u < RT_N ? u : 0] : mk<otype>((otype)0, (otype)0);
+                    if (u < 2) {
+                        const otype ex = emit_val(t.x, vx), ey = emit_val(t.y, vy);
+                        if (al && 2 * m + 1 < emit_end) {
+                            *reinterpret_cast<OC *>(dstg + 2 * m) = mk<otype>(ex, ey);
+                        } else {
+                            if (2 * m < emit_end) dstg[2 * m] = ex;
+                            if (2 * m + 1 < emit_end) dstg[2 * m + 1] = ey;
+                        }
+                    } else {
+                        rg.tail[u >= 2 ? u - 2 : 0] = mk<otype>(tail_val(t.x, vx), tail_val(t.y, vy));
+                    }
+                };
+                stockham_pass_io<real, LOG2M, NT, P, decltype(in), decltype(out), TW_DERIVE, INV_INPLACE>(tid, tb.tw, in, out);
+            } else if (((ob | hop | (lim == 0x7fffffff ? 0 : lim)) & 1) == 0 &&
                 ((reinterpret_cast<uintptr_t>(dstg) & (2 * sizeof(otype) - 1)) == 0)) {
                 // pairs (2m, 2m+1) never straddle the hop boundary or the end of the row and are aligned in the
                 // ring and in the row: one 2-sample load / add / (predicated) store per pair, no branches
@@ -1405,8 +1461,8 @@ struct InvPasses {
     template <bool EMIT, class Exec>
     static TSB_HD void run(Exec &ex, int lane, typename CH::Smem &sm, const typename CH::Tables &tb, const ChainArgs &a,
                            long long out_pos, int hop) {
-        ex.each([&](int tid, typename CH::Regs &) {
-            CH::template inv_pass<P, CH::T, EMIT>(tid, lane, sm, tb, a, out_pos, hop);
+        ex.each([&](int tid, typename CH::Regs &rg) {
+            CH::template inv_pass<P, CH::T, EMIT>(tid, lane, sm, rg, tb, a, out_pos, hop);
             if (P == END - 1) CH::ring_wait();
         });
         InvPasses<CH, P + 1, END>::template run<EMIT>(ex, lane, sm, tb, a, out_pos, hop);
@@ -1423,11 +1479,11 @@ struct InvPasses<CH, END, END> {
 // split is at warp granularity).  Both transforms have the same pass structure, so they stay in step.
 template <class CH, int P, int END>
 struct PipePasses {
-    template <bool EMIT, class Exec>
+    template <bool EMIT, bool RT, class Exec>
     static TSB_HD void run(Exec &ex, int lane, typename CH::Smem &sm, const typename CH::Tables &tb, const ChainArgs &a,
                            bool have_next, long long next_in_off, long long fetch_first, int fetch_cnt, bool have_cur,
                            long long out_pos, int hop) {
-        auto body = [&](int tid, typename CH::Regs &) {
+        auto body = [&](int tid, typename CH::Regs &rg) {
             if (tid < CH::T0) {
                 if (have_next) {
                     // The samples this frame adds were requested during the previous frame's last pass (below) and
@@ -1439,7 +1495,7 @@ struct PipePasses {
                     if (P == END - 1 && fetch_cnt > 0) CH::template ring_fill<CH::T0>(tid, lane, sm, a, fetch_first, fetch_cnt);
                 }
             } else if (have_cur) {
-                CH::template inv_pass<P, CH::T0, EMIT>(tid - CH::T0, lane, sm, tb, a, out_pos, hop);
+                CH::template inv_pass<P, CH::T0, EMIT, RT>(tid - CH::T0, lane, sm, rg, tb, a, out_pos, hop);
             }
         };
         // The two halves work on buffers of their own (buf / ibuf) and meet again only in the PV phases: between
@@ -1447,13 +1503,13 @@ struct PipePasses {
         // pass on one side (the windowed load, the overlap-add) no longer holds up the other side pass by pass.
         if (P < END - 1) ex.each_half(body, CH::T0);
         else ex.each(body);
-        PipePasses<CH, P + 1, END>::template run<EMIT>(ex, lane, sm, tb, a, have_next, next_in_off, fetch_first, fetch_cnt,
-                                                       have_cur, out_pos, hop);
+        PipePasses<CH, P + 1, END>::template run<EMIT, RT>(ex, lane, sm, tb, a, have_next, next_in_off, fetch_first, fetch_cnt,
+                                                           have_cur, out_pos, hop);
     }
 };
 template <class CH, int END>
 struct PipePasses<CH, END, END> {
-    template <bool EMIT, class Exec>
+    template <bool EMIT, bool RT, class Exec>
     static TSB_HD void run(Exec &, int, typename CH::Smem &, const typename CH::Tables &, const ChainArgs &, bool, long long,
                            long long, int, bool, long long, int) {}
 };
@@ -1549,12 +1605,15 @@ TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const t
         if (ff_first < own) {
             int hop0 = hop_of(ff_first);
             int cnt = ff_first + 1 < own ? (hop0 < N ? hop0 : N) : 0;
-            PipePasses<CH, 0, CH::PASSES>::template run<false>(ex, lane, sm, tb, a, true, in_off, in_off + hop0 + N - cnt, cnt,
-                                                               false, out_pos, 0);
+            PipePasses<CH, 0, CH::PASSES>::template run<false, false>(ex, lane, sm, tb, a, true, in_off, in_off + hop0 + N - cnt, cnt,
+                                                                      false, out_pos, 0);
         }
+        // the overlap tail in registers for the whole launch (Chain::RT_OK)
+        const bool rt = CH::RT_OK && !hop_tab && a.hop == N / 4;
+        if (rt) ex.each([&](int tid, Regs &rg) { CH::tail_load(tid, sm, rg, out_pos); });
         // one frame; EMIT is a type so that the lead-in frames get their own (cold) copy of the passes and the
         // steady-state loop carries nothing extra
-        auto frame = [&](int ff, auto EMIT) {
+        auto frame = [&](int ff, auto EMIT, auto RT) {
             const int hop = hop_of(ff);
             if (CH::IS_PV) {
                 const bool all = ff + 1 == own;  // last_phase is state: the last frame of a launch analyses every bin
@@ -1579,14 +1638,21 @@ TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const t
                 cnt = hop1 < N ? hop1 : N;
                 first = next_in + hop1 + N - cnt;
             }
-            PipePasses<CH, 0, CH::PASSES>::template run<decltype(EMIT)::value>(ex, lane, sm, tb, a, have_next, next_in, first, cnt,
-                                                                              true, out_pos, hop);
+            PipePasses<CH, 0, CH::PASSES>::template run<decltype(EMIT)::value, decltype(RT)::value>(ex, lane, sm, tb, a, have_next, next_in,
+                                                                                                   first, cnt, true, out_pos, hop);
             in_off = next_in;
             out_pos += hop;
         };
         int ff = ff_first;
-        for (; ff < 0 && ff < own; ff++) frame(ff, std::false_type{});
-        for (; ff < own; ff++) frame(ff, std::true_type{});
+        if (CH::RT_OK && rt) {
+            using RTT = std::integral_constant<bool, CH::RT_OK>;
+            for (; ff < 0 && ff < own; ff++) frame(ff, std::false_type{}, RTT{});
+            for (; ff < own; ff++) frame(ff, std::true_type{}, RTT{});
+            ex.each([&](int tid, Regs &rg) { CH::tail_store(tid, sm, rg, out_pos); });
+        } else {
+            for (; ff < 0 && ff < own; ff++) frame(ff, std::false_type{}, std::false_type{});
+            for (; ff < own; ff++) frame(ff, std::true_type{}, std::false_type{});
+        }
     } else {
     bool warm_pending = warm;
     for (int ff = ff_first; ff < own; ff++) {

@@ -301,7 +301,7 @@ __device__ __forceinline__ cd unit_w(long long q, double inv_n) {
 #ifdef TSB_SPEC_OCC_A
 constexpr int spec_occ_a(int, bool) { return TSB_SPEC_OCC_A; }
 #else
-constexpr int spec_occ_a(int nt, bool r16) { return r16 ? 4 : (nt >= 256 ? 3 : (nt >= 128 ? 6 : 8)); }
+constexpr int spec_occ_a(int nt, bool r16) { return r16 ? (nt >= 256 ? 2 : 4) : (nt >= 256 ? 3 : (nt >= 128 ? 6 : 8)); }
 #endif
 #ifdef TSB_SPEC_OCC_B
 constexpr int spec_occ_b(bool) { return TSB_SPEC_OCC_B; }
