@@ -758,7 +758,11 @@ static cudaError_t run_frames(SpecCache &pc, const SpectralJob &jb, cudaStream_t
         int prio_lo = 0, prio_hi = 0;
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
         const char *pv = getenv("TSB_SPEC_PRIO");
-        const int pmode = pv ? atoi(pv) : 0;
+        // default 2: kernel B on a high-priority stream of its own.  With equal priorities the block scheduler's choice
+        // between B(f) and A(f+1) differs from process to process: a frame takes 40 us in some, 49 us in others
+        // (measured, profiles/r2_cfg5_priority.txt); B first is the fast order, every time.  (0: B on the caller's
+        // stream, 1: A on a high-priority stream)
+        const int pmode = pv ? atoi(pv) : 2;
         if ((e = cudaStreamCreateWithPriority(&pc.aux, cudaStreamNonBlocking, pmode == 1 ? prio_hi : prio_lo)) != cudaSuccess) return e;
         if (pmode == 2 && (e = cudaStreamCreateWithPriority(&pc.bhi, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return e;
         cudaEvent_t *evs[10] = {&pc.ev_start, &pc.ev_a[0], &pc.ev_a[1], &pc.ev_a[2], &pc.ev_a[3], &pc.ev_b[0], &pc.ev_b[1], &pc.ev_b[2], &pc.ev_b[3], &pc.ev_end};
