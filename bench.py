@@ -26,9 +26,9 @@ sys.path.insert(0, ROOT)
 
 N_FRAME, HOP, CH, RATE, SHIFT = 1024, 256, 2, 48000.0, 2.0
 # One lane = one CTA of 128 threads; resident CTAs per SM: 4 (fp64 kernel: 128 regs — the overlap tail lives in
-# registers — 37 KB smem) / 8 (fp32: 64 regs, 18 KB).  148 SMs x that many CTAs = one full wave of lanes; 2 lanes per
+# registers — 37 KB smem) / 5 (fp32: 96 regs, 18 KB).  148 SMs x that many CTAs = one full wave of lanes; 2 lanes per
 # stereo stream; both precisions run two waves.
-STREAMS = {"f64": 148 * 4, "f32": 148 * 8}
+STREAMS = {"f64": 148 * 4, "f32": 148 * 5}
 
 
 def peaks():

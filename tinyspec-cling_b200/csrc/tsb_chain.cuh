@@ -675,7 +675,7 @@ struct Chain {
 #define TSB_INV_INPLACE 1
 #endif
     static constexpr bool INV_INPLACE = TSB_INV_INPLACE && PIPE && sizeof(real) == 8;
-    // Register-resident overlap tail (fp64, N = 1024, constant hop N/4): the last inverse pass gives thread j the
+    // Register-resident overlap tail (N = 1024, constant hop N/4): the last inverse pass gives thread j the
     // sample pairs m = j + T0*u, u = 0..7, of every frame, and a hop of N/4 moves an output position from pair m of
     // one frame to pair m - 2*T0 of the next — the same thread, slot u - 2.  So the six pairs a frame leaves
     // unfinished stay in that thread's registers instead of making a read-modify-write trip through the shared-memory
@@ -684,7 +684,10 @@ struct Chain {
 #ifndef TSB_RTAIL
 #define TSB_RTAIL 1
 #endif
-    static constexpr bool RT_OK = TSB_RTAIL && PIPE && sizeof(real) == 8 && LOG2N == 10;
+#ifndef TSB_RTAIL_F32
+#define TSB_RTAIL_F32 1  // fp32 too: 12 registers of tail; the kernel then gets 96 registers and five lanes per SM (+3.5 %)
+#endif
+    static constexpr bool RT_OK = TSB_RTAIL && PIPE && (sizeof(real) == 8 || TSB_RTAIL_F32) && LOG2N == 10;
     static constexpr int RT_N = RT_OK ? 6 : 1;
     using C = cpx<real>;
     using Tables = ChainTables<real>;

@@ -13,6 +13,11 @@
 #ifndef TSB_REGS_PV64
 #define TSB_REGS_PV64 96
 #endif
+#ifndef TSB_REGS_PV32_RT
+// fp32 with the overlap tail in registers (N=1024): 96 registers, five lanes per SM (80 registers / six lanes spill: measured
+// 227 M frame-channels/s against 231 M; without the tail 64 registers / eight lanes: 223 M)
+#define TSB_REGS_PV32_RT 96
+#endif
 #ifndef TSB_REGS_PV64_RT
 // the kernel that keeps its overlap tail in registers (Chain::RT_OK, N=1024): four lanes per SM, 128 registers
 #define TSB_REGS_PV64_RT 128
@@ -57,7 +62,7 @@ template <class CH>
 constexpr int min_blocks() {
     constexpr int by_smem = (227 * 1024) / ((int)sizeof(typename CH::Smem) + 1024);
     constexpr int by_threads = 2048 / CH::T;
-    constexpr int by_regs = 65536 / (CH::T * (sizeof(typename CH::C) == 8 ? (CH::IS_PV ? TSB_REGS_PV32 : 80) : (CH::IS_PV ? (CH::RT_OK ? TSB_REGS_PV64_RT : ((CH::INV_INPLACE && CH::N != 1024) ? TSB_REGS_PV64_INPLACE : TSB_REGS_PV64)) : (CH::RT_OK ? TSB_REGS_PV64_RT : 96))));
+    constexpr int by_regs = 65536 / (CH::T * (sizeof(typename CH::C) == 8 ? (CH::IS_PV ? (CH::RT_OK ? TSB_REGS_PV32_RT : TSB_REGS_PV32) : 80) : (CH::IS_PV ? (CH::RT_OK ? TSB_REGS_PV64_RT : ((CH::INV_INPLACE && CH::N != 1024) ? TSB_REGS_PV64_INPLACE : TSB_REGS_PV64)) : (CH::RT_OK ? TSB_REGS_PV64_RT : 96))));
     int b = by_smem < by_threads ? by_smem : by_threads;
     b = b < by_regs ? b : by_regs;
     return b < 1 ? 1 : (b > 32 ? 32 : b);
