@@ -166,6 +166,31 @@ def test_pv_segments_bit_identical(env):
         assert torch.equal(again, whole)  # deterministic: no atomics anywhere
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["f64", "f64o32", "f32"])
+@pytest.mark.parametrize("n,program", [(1024, "pv"), (1024, "gain"), (512, "pv"), (2048, "pv"), (2048, "gain")])
+def test_register_overlap_tail_is_the_ring_path(env, precision, n, program):
+    """At a constant hop of N/4 some kernels keep the overlap tail in registers (Chain::RT_OK: N=1024 everywhere, 512 and
+    2048 in fp64, 2048 gain in fp32): bit-identical to the shared-memory ring path, which a hop table of the same hops
+    selects; also with a row that ends mid-frame."""
+    torch, tsb, orc = env["torch"], env["tsb"], env["orc"]
+    hop, ch = n // 4, 3
+    x = orc.gen_signal(0, ch, 30000)
+    sch = tsb.schedule_const(x.shape[0], n, hop)
+    F = sch["n_frames"]
+    xd = torch.from_numpy(np.ascontiguousarray(x.T)).cuda()
+    plan = tsb.Plan(env["ctx"], n, precision=precision, program=program, hop=hop, ratio=1.5)
+    a = plan.render(xd, F, hop).clone()
+    b = plan.render(xd, F, hop, hop_tab=np.full(F, hop, np.int32)).clone()
+    torch.cuda.synchronize()
+    assert float(a.abs().max()) > 0.1
+    assert torch.equal(a, b)
+    short = torch.zeros((ch, F * hop - 301), dtype=a.dtype, device="cuda")
+    plan.render(xd, F, hop, out=short)
+    torch.cuda.synchronize()
+    assert torch.equal(short, a[:, :F * hop - 301])
+
+
 @pytest.mark.parametrize("n,ch,filt", [(2048, 1, False), (2048, 1, True), (512, 2, True), (64, 2, True), (8192, 1, True)])
 @pytest.mark.parametrize("precision", ["f64", "f32"])
 def test_gain_vs_oracle(env, n, ch, filt, precision):

@@ -264,3 +264,26 @@ def test_time_segment_with_lead_in_frames_is_the_sequential_render(precision):
     assert np.array_equal(out1[:, lead * hop:], seq[:, first * hop:])
     for k in ("last_phase", "phase_sum", "ola"):
         assert np.array_equal(st1[k], st_seq[k])
+
+
+@pytest.mark.parametrize("precision", ["f64", "f64o32", "f32"])
+@pytest.mark.parametrize("n,program", [(1024, "pv"), (512, "pv"), (2048, "pv"), (2048, "gain")])
+def test_register_overlap_tail_is_the_ring_path(precision, n, program):
+    """At a constant hop of N/4 some kernels keep the overlap tail in registers (Chain::RT_OK, tsb_chain.cuh: N=1024
+    everywhere, 512 and 2048 in fp64, 2048 gain in fp32): same samples, same state as the shared-memory ring path
+    (forced here by a hop table of the same hops), across a state hand-over and with a row that ends mid-frame."""
+    rng = np.random.default_rng(3)
+    hop, F = n // 4, 21
+    x = (rng.random((2, 2048 + F * hop + n), dtype=np.float32) - 0.5)
+    a, sa = emul.chain_render(x, n, hop, F, precision=precision, program=program, ratio=1.5)
+    b, sb = emul.chain_render(x, n, hop, F, precision=precision, program=program, ratio=1.5, hop_tab=np.full(F, hop, np.int32))
+    assert np.abs(a).max() > 0.1
+    assert np.array_equal(a, b)
+    for k in ("ola", "phase_sum", "last_phase"):
+        assert np.array_equal(sa[k], sb[k])
+    a1, s1 = emul.chain_render(x, n, hop, 9, precision=precision, program=program, ratio=1.5)
+    a2, _ = emul.chain_render(x, n, hop, F - 9, precision=precision, program=program, ratio=1.5, in_off0=2048 + 9 * hop,
+                              state=s1, prev_hop=hop)
+    assert np.array_equal(np.concatenate([a1, a2], axis=1), a)
+    c, _ = emul.chain_render(x, n, hop, F, precision=precision, program=program, ratio=1.5, out_len=F * hop - 301)
+    assert np.array_equal(c, a[:, :F * hop - 301])

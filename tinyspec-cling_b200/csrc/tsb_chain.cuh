@@ -675,7 +675,7 @@ struct Chain {
 #define TSB_INV_INPLACE 1
 #endif
     static constexpr bool INV_INPLACE = TSB_INV_INPLACE && PIPE && sizeof(real) == 8;
-    // Register-resident overlap tail (N = 1024, constant hop N/4): the last inverse pass gives thread j the
+    // Register-resident overlap tail (constant hop N/4; N = 1024 in the text): the last inverse pass gives thread j the
     // sample pairs m = j + T0*u, u = 0..7, of every frame, and a hop of N/4 moves an output position from pair m of
     // one frame to pair m - 2*T0 of the next — the same thread, slot u - 2.  So the six pairs a frame leaves
     // unfinished stay in that thread's registers instead of making a read-modify-write trip through the shared-memory
@@ -684,11 +684,27 @@ struct Chain {
 #ifndef TSB_RTAIL
 #define TSB_RTAIL 1
 #endif
-#ifndef TSB_RTAIL_F32
-#define TSB_RTAIL_F32 1  // fp32 too: 12 registers of tail; the kernel then gets 96 registers and five lanes per SM (+3.5 %)
+    // frame sizes (bit log2 N) whose kernels keep the tail in registers, per precision: every size costs its kernel
+    // registers, i.e. resident lanes, so each is enabled only where it was measured faster (tsb_chain_inst.cu)
+    // (measured, M frame-channels/s without -> with: fp64 N=512 PV 262 -> 310, N=2048 PV 64.4 -> 69.3, gain 81.2 -> 85.8,
+    // N=4096 28.3 -> 27.8; fp32 N=2048 gain 128.5 -> 134.6, but PV 100.7 -> 89.2 and N=512 PV 416 -> 364: the fp32 PV
+    // kernels lose more to the lanes the extra registers cost than the tail saves)
+#ifndef TSB_RTAIL_SIZES64
+#define TSB_RTAIL_SIZES64 ((1u << 9) | (1u << 10) | (1u << 11))
 #endif
-    static constexpr bool RT_OK = TSB_RTAIL && PIPE && (sizeof(real) == 8 || TSB_RTAIL_F32) && LOG2N == 10;
-    static constexpr int RT_N = RT_OK ? 6 : 1;
+#ifndef TSB_RTAIL_SIZES32
+#define TSB_RTAIL_SIZES32 (1u << 10)
+#endif
+#ifndef TSB_RTAIL_SIZES32_GAIN
+#define TSB_RTAIL_SIZES32_GAIN ((1u << 10) | (1u << 11))
+#endif
+    // the last inverse pass is run by INV_NT threads; thread j gets the pairs m = j + T0*u, u < RT_PP, and a hop of
+    // N/4 shifts a position by RT_SH slots
+    static constexpr int INV_NT = PIPE ? T0 : T;
+    static constexpr int RT_PP = M / T0, RT_SH = (N / 8) / T0;
+    static constexpr bool RT_OK = TSB_RTAIL && INV_NT == T0 && RT_SH >= 1 && RT_SH * T0 * 8 == N &&
+                                  (((sizeof(real) == 8 ? TSB_RTAIL_SIZES64 : (PROG == PROG_GAIN ? TSB_RTAIL_SIZES32_GAIN : TSB_RTAIL_SIZES32)) >> LOG2N) & 1u);
+    static constexpr int RT_N = RT_OK ? RT_PP - RT_SH : 1;
     using C = cpx<real>;
     using Tables = ChainTables<real>;
     using SW = Swz<real>;
@@ -1321,18 +1337,20 @@ struct Chain {
 
     // register tail <-> the shared-memory ring (start and end of a launch; `out_pos` = position of the next frame)
     static TSB_HD void tail_load(int tid, Smem &sm, Regs &rg, long long out_pos) {
-        if (tid < T0) return;
+        if (PIPE && tid < T0) return;
+        const int j = PIPE ? tid - T0 : tid;
 #pragma unroll
         for (int u = 0; u < RT_N; u++) {
-            const long long n = out_pos + 2 * (tid - T0 + T0 * u);
+            const long long n = out_pos + 2 * (j + T0 * u);
             rg.tail[u] = mk<otype>(sm.ola[(int)(n & (N - 1))], sm.ola[(int)((n + 1) & (N - 1))]);
         }
     }
     static TSB_HD void tail_store(int tid, Smem &sm, const Regs &rg, long long out_pos) {
-        if (tid < T0) return;
+        if (PIPE && tid < T0) return;
+        const int j = PIPE ? tid - T0 : tid;
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const long long n = out_pos + 2 * (tid - T0 + T0 * u);
+        for (int u = 0; u < RT_PP; u++) {
+            const long long n = out_pos + 2 * (j + T0 * u);
             sm.ola[(int)(n & (N - 1))] = u < RT_N ? rg.tail[u < RT_N ? u : 0].x : (otype)0;
             sm.ola[(int)((n + 1) & (N - 1))] = u < RT_N ? rg.tail[u < RT_N ? u : 0].y : (otype)0;
         }
@@ -1371,17 +1389,17 @@ struct Chain {
             if constexpr (RT) {
                 // the tail lives in registers (see RT_OK): pair u of this thread finishes for u < 2 and moves to slot
                 // u - 2 otherwise; slots 6 and 7 start from nothing
-                static_assert(!RT || (RadixPlan<LOG2M>::ns(PASSES - 1) == T0 && M / RadixPlan<LOG2M>::radix(PASSES - 1) == T0 && NT == T0),
-                              "register tail: one butterfly per thread in the last pass, outputs T0 apart");
+                static_assert(!RT || NT == T0, "register tail: the last inverse pass is run by T0 threads");
                 const bool al = (reinterpret_cast<uintptr_t>(dstg) & (2 * sizeof(otype) - 1)) == 0;
                 const int emit_end = hop < lim ? hop : lim;
+                OC nt[RT_N];  // the new tail (the pass does not hand its outputs over in slot order)
                 auto out = [&](int x, int c, C f) {
-                    const int u = c / T0;  // a constant once the pass is unrolled (c = u * Ns)
+                    const int u = c / T0;  // a constant once the pass is unrolled (last pass: x = tid, c = T0 * u)
                     const int m = x + c;
                     C w = TSB_LDG(ws + m);
                     const real vx = mul_rn(f.x, w.x), vy = -mul_rn(f.y, w.y);
                     const OC t = u < RT_N ? rg.tail[u < RT_N ? u : 0] : mk<otype>((otype)0, (otype)0);
-                    if (u < 2) {
+                    if (u < RT_SH) {
                         const otype ex = emit_val(t.x, vx), ey = emit_val(t.y, vy);
                         if (al && 2 * m + 1 < emit_end) {
                             *reinterpret_cast<OC *>(dstg + 2 * m) = mk<otype>(ex, ey);
@@ -1390,10 +1408,12 @@ struct Chain {
                             if (2 * m + 1 < emit_end) dstg[2 * m + 1] = ey;
                         }
                     } else {
-                        rg.tail[u >= 2 ? u - 2 : 0] = mk<otype>(tail_val(t.x, vx), tail_val(t.y, vy));
+                        nt[u >= RT_SH ? u - RT_SH : 0] = mk<otype>(tail_val(t.x, vx), tail_val(t.y, vy));
                     }
                 };
                 stockham_pass_io<real, LOG2M, NT, P, decltype(in), decltype(out), TW_DERIVE, INV_INPLACE>(tid, tb.tw, in, out);
+#pragma unroll
+                for (int u = 0; u < RT_N; u++) rg.tail[u] = nt[u];
             } else if (((ob | hop | (lim == 0x7fffffff ? 0 : lim)) & 1) == 0 &&
                 ((reinterpret_cast<uintptr_t>(dstg) & (2 * sizeof(otype) - 1)) == 0)) {
                 // pairs (2m, 2m+1) never straddle the hop boundary or the end of the row and are aligned in the
@@ -1461,19 +1481,19 @@ struct FwdPasses<CH, END, END> {
 };
 template <class CH, int P, int END>
 struct InvPasses {
-    template <bool EMIT, class Exec>
+    template <bool EMIT, bool RT, class Exec>
     static TSB_HD void run(Exec &ex, int lane, typename CH::Smem &sm, const typename CH::Tables &tb, const ChainArgs &a,
                            long long out_pos, int hop) {
         ex.each([&](int tid, typename CH::Regs &rg) {
-            CH::template inv_pass<P, CH::T, EMIT>(tid, lane, sm, rg, tb, a, out_pos, hop);
+            CH::template inv_pass<P, CH::T, EMIT, RT>(tid, lane, sm, rg, tb, a, out_pos, hop);
             if (P == END - 1) CH::ring_wait();
         });
-        InvPasses<CH, P + 1, END>::template run<EMIT>(ex, lane, sm, tb, a, out_pos, hop);
+        InvPasses<CH, P + 1, END>::template run<EMIT, RT>(ex, lane, sm, tb, a, out_pos, hop);
     }
 };
 template <class CH, int END>
 struct InvPasses<CH, END, END> {
-    template <bool EMIT, class Exec>
+    template <bool EMIT, bool RT, class Exec>
     static TSB_HD void run(Exec &, int, typename CH::Smem &, const typename CH::Tables &, const ChainArgs &, long long, int) {}
 };
 
@@ -1657,6 +1677,9 @@ TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const t
             for (; ff < own; ff++) frame(ff, std::true_type{}, std::false_type{});
         }
     } else {
+    // (the overlap tail in registers, as above; never in the pre-pass, which writes no samples)
+    const bool rt = CH::RT_OK && !CH::PIPE && !prepass && !hop_tab && a.hop == N / 4;
+    if (CH::RT_OK && !CH::PIPE && rt) ex.each([&](int tid, Regs &rg) { CH::tail_load(tid, sm, rg, out_pos); });
     bool warm_pending = warm;
     for (int ff = ff_first; ff < own; ff++) {
         const bool is_warm = warm_pending;
@@ -1689,11 +1712,18 @@ TSB_HD void run_lane(Exec &ex, int lane, int seg, typename CH::Smem &sm, const t
         } else {
             ex.each([&](int tid, Regs &) { CH::phase_gain(tid, sm, tb); });
         }
-        if (ff >= 0) InvPasses<CH, 0, CH::PASSES>::template run<true>(ex, lane, sm, tb, a, out_pos, hop);
-        else InvPasses<CH, 0, CH::PASSES>::template run<false>(ex, lane, sm, tb, a, out_pos, hop);
+        if (CH::RT_OK && !CH::PIPE && rt) {
+            constexpr bool RTT = CH::RT_OK && !CH::PIPE;
+            if (ff >= 0) InvPasses<CH, 0, CH::PASSES>::template run<true, RTT>(ex, lane, sm, tb, a, out_pos, hop);
+            else InvPasses<CH, 0, CH::PASSES>::template run<false, RTT>(ex, lane, sm, tb, a, out_pos, hop);
+        } else {
+            if (ff >= 0) InvPasses<CH, 0, CH::PASSES>::template run<true, false>(ex, lane, sm, tb, a, out_pos, hop);
+            else InvPasses<CH, 0, CH::PASSES>::template run<false, false>(ex, lane, sm, tb, a, out_pos, hop);
+        }
         in_off += hop;
         out_pos += hop;
     }
+    if (CH::RT_OK && !CH::PIPE && rt) ex.each([&](int tid, Regs &rg) { CH::tail_store(tid, sm, rg, out_pos); });
     }
     {
         SegInfo sg = seg_info<CH>(a, lane, seg);

@@ -284,8 +284,14 @@ TSB_HD void stockham_pass_io(int tid, const cpx<T> *twp, In in, Out out) {
 #pragma unroll
             for (int t = 1; t < R; t++) v[t] = cmul(v[t], tw[t]);
             dftR<R>(v);
+            // last pass (Ns * R == M): base == j == tid + it * THREADS, so the per-thread part of the output index is
+            // tid alone and the rest a compile-time constant (what lets a caller keep per-output state in registers)
+            constexpr bool LAST = Ns * R == M && (THREADS & (THREADS - 1)) == 0;
 #pragma unroll
-            for (int t = 0; t < R; t++) out(base, t * Ns, v[t]);
+            for (int t = 0; t < R; t++) {
+                if (LAST) out(tid, it * THREADS + t * Ns, v[t]);
+                else out(base, t * Ns, v[t]);
+            }
         } else {
 #pragma unroll
             for (int t = 0; t < R; t++) v[t] = INPLACE ? in(j * R, t) : in(j, t * NB);
