@@ -616,3 +616,27 @@ def test_pv_arbitrary_bin_map(env, kind):
             assert np.abs(st["last_phase"].cpu().numpy() - pv.last_phase[:, :half]).max() < 1e-10
         else:
             assert rmsrel(out, want) <= F32_RMSREL
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_fused_pv_with_its_own_hop(env, precision):
+    """PhaseVocoder::set_hop (rtinc/pv.hpp:46-53): the hop inside phase_to_frequency / frequency_to_phase is the
+    object's own (the plan's `hop`), while frames advance by the scheduler's hop (render's `hop`)."""
+    torch, tsb, orc = env["torch"], env["tsb"], env["orc"]
+    n, hs, ch, pv_hop, ratio = 1024, 256, 2, 200.0, 1.5
+    x = orc.gen_signal(0, ch, 2048 + 60 * hs + n)
+    F = orc.n_frames(x.shape[0], n, hs)
+    pv = orc.PV(pv_hop)
+    acc = np.zeros((ch, F * hs + n))
+    for f in range(F):
+        fr = np.ascontiguousarray(x[2048 + f * hs:2048 + f * hs + n].T.astype(np.float64))
+        pv.analyze(fr)
+        pv.shift(ratio)
+        acc[:, f * hs:f * hs + n] += pv.synthesize()
+    plan = tsb.Plan(env["ctx"], n, precision=precision, program="pv", hop=pv_hop, ratio=ratio)
+    out = plan.render(torch.from_numpy(np.ascontiguousarray(x.T)).cuda(), F, hs).cpu().numpy().astype(np.float64)
+    ref = acc[:, :F * hs]
+    if precision == "f64":
+        assert np.abs(out - ref).max() <= 1e-9 * np.abs(ref).max()
+    else:
+        assert np.sqrt(np.mean((out - ref) ** 2)) <= 1e-5 * np.sqrt(np.mean(ref ** 2))

@@ -287,3 +287,22 @@ def test_register_overlap_tail_is_the_ring_path(precision, n, program):
     assert np.array_equal(np.concatenate([a1, a2], axis=1), a)
     c, _ = emul.chain_render(x, n, hop, F, precision=precision, program=program, ratio=1.5, out_len=F * hop - 301)
     assert np.array_equal(c, a[:, :F * hop - 301])
+
+
+def test_pv_chain_with_its_own_hop():
+    """PhaseVocoder::set_hop (rtinc/pv.hpp:46-53): the hop inside phase_to_frequency / frequency_to_phase is the
+    object's own, not the scheduler's.  The fused plan takes it as `hop_d`; frames still advance by the scheduler's."""
+    n, hs, ch, pv_hop, ratio = 1024, 256, 2, 200.0, 1.5
+    x = orc.gen_signal(0, ch, 2048 + 30 * hs + n)
+    F = orc.n_frames(x.shape[0], n, hs)
+    pv = orc.PV(pv_hop)
+    acc = np.zeros((ch, F * hs + n))
+    for f in range(F):
+        fr = np.ascontiguousarray(x[2048 + f * hs:2048 + f * hs + n].T.astype(np.float64))
+        pv.analyze(fr)
+        pv.shift(ratio)
+        acc[:, f * hs:f * hs + n] += pv.synthesize()
+    out, _ = emul.chain_render(np.ascontiguousarray(x.T), n, hs, F, precision="f64", ratio=ratio, hop_d=pv_hop)
+    assert np.abs(out[:, :F * hs] - acc[:, :F * hs]).max() <= 1e-9 * np.abs(acc).max()
+    wrong, _ = emul.chain_render(np.ascontiguousarray(x.T), n, hs, F, precision="f64", ratio=ratio)
+    assert np.abs(wrong[:, :F * hs] - acc[:, :F * hs]).max() > 0.1 * np.abs(acc).max()  # the scheduler's hop is another PV

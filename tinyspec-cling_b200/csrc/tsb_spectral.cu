@@ -291,7 +291,7 @@ __device__ __forceinline__ cd unit_w(long long q, double inv_n) {
 }
 
 #ifndef TSB_SPEC_UG
-#define TSB_SPEC_UG 2  // unroll factor of kernel A's generation loop
+#define TSB_SPEC_UG 8  // unroll factor of kernel A's tile-path generation loop (caller spectra: 8 column reads in flight per thread, 56.1 -> 54.3 us)
 #endif
 #ifndef TSB_SPEC_UO
 #define TSB_SPEC_UO 2  // ... of its output loop (2: two shared-memory reads in flight per thread; 54.5 us per cfg5 frame instead of 55.8)
