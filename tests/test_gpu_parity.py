@@ -168,7 +168,7 @@ def test_pv_segments_bit_identical(env):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("precision", ["f64", "f64o32", "f32"])
-@pytest.mark.parametrize("n,program", [(1024, "pv"), (1024, "gain"), (512, "pv"), (2048, "pv"), (2048, "gain")])
+@pytest.mark.parametrize("n,program", [(1024, "pv"), (1024, "gain"), (512, "pv"), (2048, "pv"), (2048, "gain"), (4096, "pv")])
 def test_register_overlap_tail_is_the_ring_path(env, precision, n, program):
     """At a constant hop of N/4 some kernels keep the overlap tail in registers (Chain::RT_OK: N=1024 everywhere, 512 and
     2048 in fp64, 2048 gain in fp32): bit-identical to the shared-memory ring path, which a hop table of the same hops

@@ -267,7 +267,7 @@ def test_time_segment_with_lead_in_frames_is_the_sequential_render(precision):
 
 
 @pytest.mark.parametrize("precision", ["f64", "f64o32", "f32"])
-@pytest.mark.parametrize("n,program", [(1024, "pv"), (512, "pv"), (2048, "pv"), (2048, "gain")])
+@pytest.mark.parametrize("n,program", [(1024, "pv"), (512, "pv"), (2048, "pv"), (2048, "gain"), (4096, "pv")])
 def test_register_overlap_tail_is_the_ring_path(precision, n, program):
     """At a constant hop of N/4 some kernels keep the overlap tail in registers (Chain::RT_OK, tsb_chain.cuh: N=1024
     everywhere, 512 and 2048 in fp64, 2048 gain in fp32): same samples, same state as the shared-memory ring path

@@ -643,7 +643,8 @@ struct Chain {
 #ifdef TSB_TMUL
     static constexpr int TMUL = N >= 256 ? TSB_TMUL : 1;
 #else
-    static constexpr int TMUL = (N >= 256 && N <= (sizeof(real) == 4 ? 4096 : 2048)) ? 2 : 1;  // fp64 at 4096: one 512-thread CTA per SM, measured slower
+    static constexpr int TMUL = (N >= 256 && N <= 4096) ? 2 : 1;  // (fp64 at 4096: one 512-thread CTA per SM; with the in-place
+                                                                  // inverse transform and the register tail 27.7 -> 29.2 M frame-channels/s)
 #endif
     static constexpr int T = T0 * TMUL > 1024 ? 1024 : T0 * TMUL;
     // With twice the FFT's threads, the two halves of the CTA transform two frames at once (see run_lane).
@@ -687,10 +688,10 @@ struct Chain {
     // frame sizes (bit log2 N) whose kernels keep the tail in registers, per precision: every size costs its kernel
     // registers, i.e. resident lanes, so each is enabled only where it was measured faster (tsb_chain_inst.cu)
     // (measured, M frame-channels/s without -> with: fp64 N=512 PV 262 -> 310, N=2048 PV 64.4 -> 69.3, gain 81.2 -> 85.8,
-    // N=4096 28.3 -> 27.8; fp32 N=2048 gain 128.5 -> 134.6, but PV 100.7 -> 89.2 and N=512 PV 416 -> 364: the fp32 PV
+    // N=4096 28.7 -> 29.2 once pipelined (TMUL); fp32 N=2048 gain 128.5 -> 134.6, but PV 100.7 -> 89.2 and N=512 PV 416 -> 364: the fp32 PV
     // kernels lose more to the lanes the extra registers cost than the tail saves)
 #ifndef TSB_RTAIL_SIZES64
-#define TSB_RTAIL_SIZES64 ((1u << 9) | (1u << 10) | (1u << 11))
+#define TSB_RTAIL_SIZES64 ((1u << 9) | (1u << 10) | (1u << 11) | (1u << 12))
 #endif
 #ifndef TSB_RTAIL_SIZES32
 #define TSB_RTAIL_SIZES32 (1u << 10)
