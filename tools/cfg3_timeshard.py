@@ -56,7 +56,7 @@ def _timed(fn, dist, dev, warmup, reps):
 
 def run(dist, rank, world, dev, ctx, seconds=600.0, precision="f64", segments=74, warmup=2, reps=3, check=True, peer=True):
     """cfg3 (8 channels, frame 4096, hop 1024, x1.5) for `seconds` of audio as ONE render split by time over the
-    `world` ranks, and the same render on rank 0 alone (time-parallel over world * segments segments): times, the
+    `world` ranks, and the same render on rank 0 alone (time-parallel over `segments` segments): times, the
     strong-scaling efficiency and whether the stitched output is the one-GPU render bit for bit.  dist: the
     initialised torch.distributed module, or None for a single process.  Every rank returns the same dict."""
     plan = tsb200.Plan(ctx, N, precision=precision, program="pv", hop=HOP, rate=RATE, ratio=RATIO)
@@ -67,6 +67,19 @@ def run(dist, rank, world, dev, ctx, seconds=600.0, precision="f64", segments=74
            "frames; the exact running phase_sum is handed down the ranks)", "frame": N, "hop": HOP, "channels": CH,
            "ratio": RATIO, "seconds": seconds, "frames": F, "n_gpus": world, "precision": precision,
            "segments_per_gpu": segments}
+    # the same render on one GPU (rank 0; the others wait) — first, before the ranks map each other's memory: the
+    # baseline is the plain one-GPU render a single process would do
+    whole, ms1 = None, 0.0
+    if rank == 0:
+        xw = synth(0, L, dev)
+        # (with the segment count of a one-GPU run: the render is bit-identical whatever the segmentation, and more
+        # segments only add lead-in frames — the baseline should be the fastest one-GPU render, not a handicapped one)
+        whole, ms1 = _timed(lambda: plan.render_timepar(xw, F, HOP, segments), None, dev, 1, reps)
+        del xw
+    t = torch.tensor([ms1], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms1 = float(t.item())
     out = None
     if world > 1:
         b = shard.plan_time_blocks(sch, N, world)[rank]
@@ -91,16 +104,6 @@ def run(dist, rank, world, dev, ctx, seconds=600.0, precision="f64", segments=74
         allv = [None] * world
         dist.all_gather_object(allv, (rank, round(tp, 3), round(tc, 3), round(tr, 3)))
         res["trace_prepass_chain_render_ms"] = allv
-    # the same render on one GPU (rank 0; the others wait)
-    whole, ms1 = None, 0.0
-    if rank == 0:
-        xw = synth(0, L, dev)
-        whole, ms1 = _timed(lambda: plan.render_timepar(xw, F, HOP, segments * world), None, dev, 1, reps)
-        del xw
-    t = torch.tensor([ms1], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms1 = float(t.item())
     if world == 1:
         ms = ms1
     res.update({"ms": ms, "ms_1gpu": ms1, "frames_per_s": F / ms * 1e3, "frame_channels_per_s": F * CH / ms * 1e3,
