@@ -19,6 +19,10 @@
 //     kernel B  n1 row FFTs of n2 points; only j < n/2 is needed (the first n samples): unpack, 1/sqrt(2n), the
 //               carried bins 0 / n added analytically, window, overlap-add into the output rows
 // The scratch of one frame (channels * n * 16 bytes; 64 MiB at cfg5) is written and read back to back, i.e. from L2.
+// Both kernels are bound by the L1/shared-memory data pipe (a complex double costs a warp four wavefronts per access), so
+// 256-point sub-transforms run as two radix-16 passes by 16 threads that hold the whole sub-transform in registers between
+// the reads and the writes of a pass (SubFft::R16), and kernel A generates straight into its first pass (mirror elements
+// of the Hermitian pairs cross the warp by shuffle).  Kernel A of frame f+1 and kernel B of frame f run on two streams.
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -272,7 +276,7 @@ struct SpecPasses {
             lt, tw,
             [&](int a, int c) { return (LIN && P == 0) ? src[a + c] : src[Swz<double>::f(a) ^ Swz<double>::f(c)]; },
             [&](int a, int c, cd v) { dst[Swz<double>::f(a) ^ Swz<double>::f(c)] = v; });
-        // a sub-transform of 256 points is run by exactly one warp (T = 32): its passes need no block barrier
+        // (radix-8 plan) a sub-transform of 256 points is run by exactly one warp (T = 32): its passes need no block barrier
         if (T == 32) __syncwarp();
         else __syncthreads();
         return SpecPasses<LOG2M, T, P + 1, END, LIN>::run(lt, dst, other, dst, tw);
