@@ -170,6 +170,33 @@ extern "C" int emul_fft(int precision, int log2m, const double *in, double *out)
     return -1;
 }
 
+// The two radix-16 passes of the spectral-synthesis kernels' 256-point sub-transforms (tsb_math.cuh: r16_pass), run by
+// sixteen "threads" over the tile layout r16_sw.  On the device a thread reads its sixteen points, the half-warp
+// synchronises, and the points are written back into the same tile; here every thread's reads precede every write
+// because each pass goes from one buffer into another.  half != 0: the last pass stores X[0..128] only (kernel B).
+extern "C" void emul_fft256_r16(const double *in, double *out, int half) {
+    using cd = cpx<double>;
+    std::vector<cd> a(256), b(256), c(256);
+    for (int i = 0; i < 256; i++) {
+        a[r16_sw(i)] = mk<double>(in[2 * i], in[2 * i + 1]);
+        c[i] = mk<double>(0.0, 0.0);
+    }
+    const double tau = 6.283185307179586476925286766559;
+    for (int j = 0; j < 16; j++)
+        r16_pass<0>(j, mk<double>(1.0, 0.0), [&](int i) { return a[r16_sw(i)]; }, [] {}, [&](int i, cd v) { b[r16_sw(i)] = v; });
+    for (int j = 0; j < 16; j++) {
+        const cd w = mk<double>(cos(tau * j / 256.0), -sin(tau * j / 256.0));  // W256^j
+        auto rd = [&](int i) { return b[r16_sw(i)]; };
+        auto wr = [&](int i, cd v) { c[r16_sw(i)] = v; };
+        if (half) r16_pass<1, true>(j, w, rd, [] {}, wr);
+        else r16_pass<1>(j, w, rd, [] {}, wr);
+    }
+    for (int i = 0; i < 256; i++) {
+        out[2 * i] = c[r16_sw(i)].x;
+        out[2 * i + 1] = c[r16_sw(i)].y;
+    }
+}
+
 // The branch-free fp64 kernels of the PV stages (host build of the same source), element-wise over arrays.
 extern "C" void emul_pv_math(long long n, const double *y, const double *x, double *atan2_out, double *sqrt_out,
                              int *wrap_out, double *sin_out, double *cos_out) {

@@ -306,3 +306,29 @@ def test_pv_chain_with_its_own_hop():
     assert np.abs(out[:, :F * hs] - acc[:, :F * hs]).max() <= 1e-9 * np.abs(acc).max()
     wrong, _ = emul.chain_render(np.ascontiguousarray(x.T), n, hs, F, precision="f64", ratio=ratio)
     assert np.abs(wrong[:, :F * hs] - acc[:, :F * hs]).max() > 0.1 * np.abs(acc).max()  # the scheduler's hop is another PV
+
+
+def test_radix16_passes_of_the_spectral_kernels():
+    """tsb_math.cuh r16_pass: 256 points = two radix-16 passes by sixteen threads over the r16_sw tile layout (what
+    kernels A and B of tsb_spectral.cu run for cfg5's 256 x 256 four-step transform), against numpy's FFT; the
+    half-output variant of kernel B must deliver X[0..128] and leave the rest alone; and the layout must be free of
+    shared-memory bank conflicts for every access of both passes (16-byte elements: 8 lanes per wavefront)."""
+    import ctypes as C
+    rng = np.random.default_rng(16)
+    x = rng.standard_normal(256) + 1j * rng.standard_normal(256)
+    want = np.fft.fft(x)
+    y = np.empty(256, np.complex128)
+    fn = emul.lib().emul_fft256_r16
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    fn.restype = None
+    fn(x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), 0)
+    assert maxrel(y, want) < 2e-15
+    fn(x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), 1)
+    assert maxrel(y[:129], want[:129]) < 2e-15
+    assert np.all(y[129:] == 0)
+    sw = lambda i: i ^ ((i >> 4) & 7)
+    for t in range(16):  # lanes j = 8 q .. 8 q + 7 form one wavefront
+        for q in range(2):
+            lanes = range(8 * q, 8 * q + 8)
+            assert len({sw(j + 16 * t) % 8 for j in lanes}) == 8   # reads of both passes, writes of pass 1
+            assert len({sw(16 * j + t) % 8 for j in lanes}) == 8   # writes of pass 0

@@ -318,6 +318,76 @@ struct DitOrder {
     }
 };
 
+// ---- 256-point transforms as two radix-16 passes (the spectral-synthesis kernels, tsb_spectral.cu) ----
+// Sixteen threads run one sub-transform and hold all of its points in registers between the reads and the writes of a
+// pass, so a pass may write the tile it read.  Position of point i inside a sub-transform's tile row: r16_sw(i)
+// (conflict-free for every access of both passes with 16-byte elements).
+TSB_HD constexpr int r16_sw(int i) { return i ^ ((i >> 4) & 7); }
+// 16-point forward DFT, natural order in; output X[b + 4c] is left in v[4b + c]
+template <typename T>
+TSB_HD void dft16_t(cpx<T> *v) {
+    using cd = cpx<T>;
+    const T c1 = (T)0.92387953251128675613, s1 = (T)0.38268343236508977173, h = (T)0.70710678118654752440;
+#pragma unroll
+    for (int a = 0; a < 4; a++) dft4(v[a], v[a + 4], v[a + 8], v[a + 12]);
+    // v[a + 4b] *= W16^(a b), W16 = e^{-i pi/8}
+    auto rot = [](cd x, T c, T s) { return mk<T>(x.x * c + x.y * s, x.y * c - x.x * s); };  // x * (c - i s)
+    v[5] = rot(v[5], c1, s1);                                             // W^1
+    v[9] = mk<T>((v[9].x + v[9].y) * h, (v[9].y - v[9].x) * h);      // W^2
+    v[13] = rot(v[13], s1, c1);                                           // W^3
+    v[6] = mk<T>((v[6].x + v[6].y) * h, (v[6].y - v[6].x) * h);      // W^2
+    v[10] = mul_mi(v[10]);                                                // W^4 = -i
+    v[14] = mk<T>((v[14].y - v[14].x) * h, -(v[14].x + v[14].y) * h);  // W^6
+    v[7] = rot(v[7], s1, c1);                                             // W^3
+    v[11] = mk<T>((v[11].y - v[11].x) * h, -(v[11].x + v[11].y) * h);  // W^6
+    v[15] = rot(v[15], -c1, -s1);                                         // W^9 = -W^1
+#pragma unroll
+    for (int b = 0; b < 4; b++) dft4(v[4 * b], v[4 * b + 1], v[4 * b + 2], v[4 * b + 3]);
+}
+// One of the two radix-16 passes of a 256-point forward transform, thread j of 16.  PASS 0: y[16 j + t'] = DFT16_t(x[j + 16 t]);
+// PASS 1: X[j + 16 t'] = DFT16_t(W256^(j t) y[j + 16 t]).  `w` = W256^j (pass 1): its powers are formed by products, at
+// most four deep.  The caller separates the reads of a pass from its writes when both use the same buffer
+// (rd(i) -> value, then sync(), then wr(i, value)).
+// second half of a pass: twiddles (pass 1), the 16-point DFT, the stores.  HALF: only outputs X[0..127] are wanted
+template <int PASS, bool HALF = false, typename T, class Wr>
+TSB_HD void r16_finish(int j, cpx<T> w, cpx<T> (&v)[16], Wr wr) {
+    using cd = cpx<T>;
+    if (PASS == 1) {
+        const cd p2 = cmul(w, w), p4 = cmul(p2, p2), p8 = cmul(p4, p4), p3 = cmul(p2, w);
+        v[1] = cmul(v[1], w);
+        v[2] = cmul(v[2], p2);
+        v[3] = cmul(v[3], p3);
+        v[4] = cmul(v[4], p4);
+        v[5] = cmul(v[5], cmul(p4, w));
+        v[6] = cmul(v[6], cmul(p4, p2));
+        const cd p7 = cmul(p4, p3);
+        v[7] = cmul(v[7], p7);
+        v[8] = cmul(v[8], p8);
+        v[9] = cmul(v[9], cmul(p8, w));
+        v[10] = cmul(v[10], cmul(p8, p2));
+        v[11] = cmul(v[11], cmul(p8, p3));
+        v[12] = cmul(v[12], cmul(p8, p4));
+        v[13] = cmul(v[13], cmul(p8, cmul(p4, w)));
+        v[14] = cmul(v[14], cmul(p8, cmul(p4, p2)));
+        v[15] = cmul(v[15], cmul(p8, p7));
+    }
+    dft16_t(v);
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+        const int tp = (r >> 2) + 4 * (r & 3);  // v[4b + c] holds output b + 4c
+        if (HALF && (tp > 8 || (tp == 8 && j != 0))) continue;  // (PASS 1: X[j + 16 tp], tp >= 8, is the upper half; X[128] is kept)
+        wr(PASS == 0 ? 16 * j + tp : j + 16 * tp, v[r]);
+    }
+}
+template <int PASS, bool HALF = false, typename T, class Rd, class Sync, class Wr>
+TSB_HD void r16_pass(int j, cpx<T> w, Rd rd, Sync sync, Wr wr) {
+    cpx<T> v[16];
+#pragma unroll
+    for (int t = 0; t < 16; t++) v[t] = rd(j + 16 * t);
+    sync();
+    r16_finish<PASS, HALF>(j, w, v, wr);
+}
+
 // plain buffer-to-buffer pass (unswizzled), used by the unit tests and the standalone FFT kernels
 template <typename T, int LOG2M, int THREADS, int P>
 TSB_HD void stockham_pass(int tid, const cpx<T> *src, cpx<T> *dst, const cpx<T> *twp) {
